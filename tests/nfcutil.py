@@ -1,0 +1,164 @@
+"""Shared test utilities: WAV fixtures, ctypes bindings of the oracle (test-only) and of the host simulation.
+
+Nothing here is imported by the product package.
+"""
+import ctypes as C
+import json
+import lzma
+import os
+import struct
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ORACLE = os.path.join(ROOT, "oracle")
+REF_SO = os.path.join(ORACLE, "_ref", "libnfcref.so")
+PORT_SO = os.path.join(ORACLE, "libnfcoracle.so")
+HOSTSIM_SO = os.path.join(ROOT, "build", "libhostsim.so")
+
+
+class RefFrame(C.Structure):
+    """oracle/ref_wrap.h nfcref_frame"""
+    _fields_ = [
+        ("tech_type", C.c_uint32), ("frame_type", C.c_uint32), ("frame_flags", C.c_uint32),
+        ("frame_phase", C.c_uint32), ("frame_rate", C.c_uint32), ("length", C.c_uint32),
+        ("sample_start", C.c_uint64), ("sample_end", C.c_uint64), ("sample_rate", C.c_uint64),
+        ("time_start", C.c_double), ("time_end", C.c_double), ("date_time", C.c_double),
+        ("data", C.c_uint8 * 512),
+    ]
+
+
+class SimFrame(C.Structure):
+    _fields_ = [
+        ("tech", C.c_uint32), ("type", C.c_uint32), ("flags", C.c_uint32), ("phase", C.c_uint32),
+        ("rate", C.c_uint32), ("start", C.c_uint32), ("end", C.c_uint32), ("len", C.c_uint32),
+        ("data", C.c_uint8 * 512),
+    ]
+
+
+class SimResult(C.Structure):
+    _fields_ = [("stop", C.c_uint32), ("dormant", C.c_uint32), ("locked", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+def frame_tuple(tech, ftype, flags, phase, rate, start, end, data):
+    return (int(tech), int(ftype), int(flags), int(phase), int(rate), int(start), int(end), bytes(data))
+
+
+def read_wav(path):
+    """mono / multi channel 16-bit PCM -> float32 scaled like RecordDevice::readScaledSamples (x / 32768.f)"""
+    opener = lzma.open if path.endswith(".xz") else open
+    with opener(path, "rb") as f:
+        raw = f.read()
+    assert raw[:4] == b"RIFF" and raw[8:12] == b"WAVE"
+    pos = 12
+    fmt = None
+    while pos + 8 <= len(raw):
+        cid, size = raw[pos:pos + 4], struct.unpack("<I", raw[pos + 4:pos + 8])[0]
+        if cid == b"fmt ":
+            fmt = struct.unpack("<HHIIHH", raw[pos + 8:pos + 24])
+        elif cid == b"data":
+            assert fmt is not None and fmt[5] == 16
+            pcm = np.frombuffer(raw, dtype="<i2", count=min(size, len(raw) - pos - 8) // 2, offset=pos + 8)
+            return (pcm.astype(np.float32) / np.float32(32768.0)), fmt[2], fmt[1]
+        pos += 8 + size + (size & 1)
+    raise ValueError("no data chunk in " + path)
+
+
+def fixture_names():
+    names = []
+    for fn in sorted(os.listdir(GOLDEN)):
+        if fn.endswith(".wav.xz"):
+            names.append(fn[:-7])
+    return names
+
+
+def fixture_wav(name):
+    return read_wav(os.path.join(GOLDEN, name + ".wav.xz"))
+
+
+def fixture_golden(name):
+    """frames pinned by the reference's own regression JSON (Poll / Listen only)"""
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        frames = json.load(f)["frames"]
+    out = []
+    for e in frames:
+        data = bytes(int(b, 16) for b in e["frameData"].split(":")) if e["frameData"] else b""
+        out.append(frame_tuple(e["techType"], e["frameType"], e["frameFlags"], e["framePhase"], e["frameRate"],
+                               e["sampleStart"], e["sampleEnd"], data))
+    return out
+
+
+_ref = None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_SO):
+            return None
+        lib = C.CDLL(REF_SO)
+        lib.nfcref_decode.restype = C.c_long
+        lib.nfcref_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint, C.POINTER(RefFrame), C.c_long]
+        lib.nfcref_iq_magnitude.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.nfcref_time_batch.restype = C.c_double
+        lib.nfcref_time_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_long)]
+        _ref = lib
+    return _ref
+
+
+def ref_decode(mag, rate=10000000, chunk=65536, enabled=0xF, cap=65536):
+    """all frames (carrier frames included) of the UNMODIFIED reference decoder"""
+    lib = ref_lib()
+    mag = np.ascontiguousarray(mag, dtype=np.float32)
+    buf = (RefFrame * cap)()
+    n = lib.nfcref_decode(mag.ctypes.data, mag.size, rate, chunk, enabled, buf, cap)
+    assert n <= cap
+    return [frame_tuple(f.tech_type, f.frame_type, f.frame_flags, f.frame_phase, f.frame_rate, f.sample_start, f.sample_end,
+                        bytes(f.data[:f.length])) for f in buf[:n]]
+
+
+def build_hostsim():
+    src = os.path.join(ROOT, "tests", "native", "host_sim.cpp")
+    deps = [src, os.path.join(ROOT, "nfc_laboratory_b200", "csrc", "nfc_core.h"), os.path.join(ROOT, "nfc_laboratory_b200", "csrc", "nfc_params.h")]
+    if os.path.exists(HOSTSIM_SO) and all(os.path.getmtime(HOSTSIM_SO) >= os.path.getmtime(d) for d in deps):
+        return
+    os.makedirs(os.path.dirname(HOSTSIM_SO), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-msse2", "-mfpmath=sse", "-ffp-contract=off", "-shared", "-fPIC",
+                           src, "-o", HOSTSIM_SO])
+
+
+_sim = None
+
+
+def sim_lib():
+    global _sim
+    if _sim is None:
+        build_hostsim()
+        lib = C.CDLL(HOSTSIM_SO)
+        lib.hostsim_run.restype = C.c_long
+        lib.hostsim_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                    C.c_void_p, C.c_void_p, C.POINTER(SimFrame), C.c_long, C.POINTER(SimResult)]
+        lib.hostsim_carry_size.restype = C.c_int
+        _sim = lib
+    return _sim
+
+
+def sim_run(mag, rate=10000000, enabled=0xF, first=0, warm=4096, own_end=0, carry_in=None, cap=65536):
+    """host build of the device lane machine; returns (frames, carry_out bytes, SimResult)"""
+    lib = sim_lib()
+    mag = np.ascontiguousarray(mag, dtype=np.float32)
+    buf = (SimFrame * cap)()
+    res = SimResult()
+    csz = lib.hostsim_carry_size()
+    cout = C.create_string_buffer(csz)
+    cin = C.create_string_buffer(carry_in, csz) if carry_in is not None else None
+    n = lib.hostsim_run(mag.ctypes.data, mag.size, rate, enabled, first, warm, own_end, cin, cout, buf, cap, C.byref(res))
+    assert 0 <= n <= cap
+    frames = [frame_tuple(f.tech, f.type, f.flags, f.phase, f.rate, f.start, f.end, bytes(f.data[:f.len])) for f in buf[:n]]
+    return frames, cout.raw, res
+
+
+def describe(fr):
+    return "tech=%x type=%x flags=%02x phase=%x rate=%d [%d..%d] %s" % (fr[0], fr[1], fr[2], fr[3], fr[4], fr[5], fr[6], fr[7].hex(":"))
