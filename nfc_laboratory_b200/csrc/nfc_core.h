@@ -111,6 +111,7 @@ struct Front
    u32 clk;         // signalClock
    u32 k;           // local step (ring slot label, warm-up gate)
    u32 pulseFilter;
+   u32 closed;      // leaky count of samples with the envelope gate closed (lane retirement only, not in the reference)
    float env, avg, dev, f1;
    float edgePeak;
    u32 edgeTime;
@@ -129,6 +130,7 @@ struct Lane
    u32 lock;      // LOCK_*
    u32 lockRate;  // rate index of the locked modulation
    u32 pulseBits; // NFC-V pulse code: 2 or 8 (decoder->pulse)
+   u32 lockedMask; // techs that were locked at least once during this run (bit t), for the carry dependency check
    u32 warm;      // local steps during which carrier detection is suppressed (cold-started lanes)
    u32 gate;      // local steps during which the detectors are off (reference: signalClock < BUFFER_SIZE)
 };
@@ -341,6 +343,13 @@ struct Machine
          f.cV0 = 0;
 
       float diff = fabsf(x - f.env) / f.env; // NfcTech.cpp:39 (inf / NaN at env == 0 compare false, as there)
+
+      // retirement bookkeeping: while the gate stays closed the envelope is stale and thresholds derived from it
+      // differ from what the screening pass assumes, so such a lane is never dormant
+      if (diff < 0.05f)
+         f.closed = f.closed ? f.closed - 1 : 0;
+      else if (f.closed < 4096)
+         f.closed++;
 
       if (diff < 0.05f || f.pulseFilter > (u32) (P.etu * 10))
       {
@@ -3163,13 +3172,13 @@ struct Machine
             return;
 
          if ((P.enabled & EN_A) && A_detect())
-            return;
-         if ((P.enabled & EN_B) && B_detect())
-            return;
-         if ((P.enabled & EN_F) && F_detect())
-            return;
-         if ((P.enabled & EN_V) && V_detect())
-            return;
+            L.lockedMask |= 1u << TECH_A;
+         else if ((P.enabled & EN_B) && B_detect())
+            L.lockedMask |= 1u << TECH_B;
+         else if ((P.enabled & EN_F) && F_detect())
+            L.lockedMask |= 1u << TECH_F;
+         else if ((P.enabled & EN_V) && V_detect())
+            L.lockedMask |= 1u << TECH_V;
 
          return;
       }
@@ -3219,9 +3228,9 @@ struct Machine
          return false;
       if (m.searchSyncTime && m.searchSyncTime + horizon >= clk)
          return false;
-      if (m.correlatedPeakTime && m.correlatedPeakTime + horizon >= clk)
-         return false;
-      if (m.detectorPeakTime && m.detectorPeakTime + horizon >= clk)
+      // a tracked peak always has a pending action: the "recover status" blocks (NfcA.cpp:268, NfcB.cpp:265,
+      // NfcF.cpp:260, NfcV.cpp:287) clear it one period later, on the next search-mode sample at the latest
+      if (m.correlatedPeakTime || m.detectorPeakTime)
          return false;
       return true;
    }
@@ -3231,6 +3240,9 @@ struct Machine
       if (L.lock != LOCK_NONE)
          return false;
 
+      if (L.fe.closed >= 16) // envelope not settled
+         return false;
+
       const u32 clk = L.fe.clk;
       const u32 horizon = P.V.p0 + 2; // longest recover timeout (NfcV.cpp:287) + margin
 
@@ -3238,8 +3250,16 @@ struct Machine
          if (!mod_dormant(L.c.mA[r], clk, horizon))
             return false;
       for (int r = 0; r < 2; r++)
+      {
          if (!mod_dormant(L.c.mB[r], clk, horizon) || !mod_dormant(L.c.mF[r], clk, horizon))
             return false;
+
+         // a stalled NFC-B SOF search reacts to edges above ITS OWN threshold (NfcB.cpp:313, 327, 366, 380); the
+         // screening kernel only guarantees to flag edges above modMin * envelope, so a more sensitive residue keeps
+         // the lane awake
+         if (L.c.mB[r].symbolStartTime && L.c.mB[r].searchValueThreshold < L.fe.env * P.thr[TECH_B].modMin)
+            return false;
+      }
       return mod_dormant(L.c.mV, clk, horizon);
    }
 
@@ -3277,6 +3297,119 @@ NFC_HD void carry_init(Carry &c, const Params &P)
       c.t[t].fs.frameWaitingTime = def[t][2];
       c.t[t].fs.requestGuardTime = def[t][3];
    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// carry canonical form.  A retired (dormant, unlocked) lane leaves values behind that no later code path can read
+// before overwriting them; zeroing those makes the carries of independent lanes comparable (DESIGN.md "carry groups").
+//   * running sums restart with the rings in the next lane
+//   * a detector whose search state is idle (no times, no peaks) rewrites every other Mod field before reading it:
+//       NFC-B searchValueThreshold is reassigned each sample (NfcB.cpp:280); NFC-F searchLastPhase / LastValue /
+//       Corr0Value / SyncValue are set by the first peak of a new search (NfcF.cpp:286-300, 344) -- but NFC-F's
+//       searchValueThreshold and searchPulseWidth survive the "recover" path (NfcF.cpp:260-271) and ARE read by the
+//       next search (:307-313), so an NFC-F Mod only counts as idle when those are zero too
+//   * NfcFrameStatus: everything except lastCommand is reassigned by process() / detectModulation before use
+//   * carrier times only matter as set / unset once their frame has been emitted (NfcDecoder.cpp:477, 502, 451)
+// ---------------------------------------------------------------------------------------------------------------------
+NFC_HD bool mod_idle(const Mod &m, bool isF)
+{
+   if (m.symbolStartTime | m.symbolEndTime | m.searchStartTime | m.searchEndTime | m.searchSyncTime | m.correlatedPeakTime | m.detectorPeakTime)
+      return false;
+   if (m.correlatedPeakValue != 0 || m.detectorPeakValue != 0)
+      return false;
+   if (isF && (m.searchPulseWidth != 0 || m.searchValueThreshold != 0))
+      return false;
+   return true;
+}
+
+NFC_HD void mod_canon(Mod &m, bool isF)
+{
+   m.filterIntegrate = 0;
+   m.phaseIntegrate = 0;
+
+   if (mod_idle(m, isF))
+   {
+      u32 *raw = (u32 *) &m;
+      for (u32 i = 0; i < sizeof(Mod) / 4; i++)
+         raw[i] = 0;
+   }
+}
+
+NFC_HD void carry_canon(Carry &c)
+{
+   for (int r = 0; r < 3; r++)
+      mod_canon(c.mA[r], false);
+   for (int r = 0; r < 2; r++)
+   {
+      mod_canon(c.mB[r], false);
+      mod_canon(c.mF[r], true);
+   }
+   mod_canon(c.mV, false);
+
+   for (int t = 0; t < 4; t++)
+   {
+      FrameSt &fs = c.t[t].fs;
+      fs.frameType = fs.symbolRate = fs.frameStart = fs.frameEnd = fs.guardEnd = fs.waitingEnd = 0;
+      fs.frameGuardTime = fs.frameWaitingTime = fs.startUpGuardTime = fs.requestGuardTime = 0;
+   }
+
+   c.carrierOn = c.carrierOn ? 1 : 0;
+   c.carrierOff = c.carrierOff ? 1 : 0;
+}
+
+// carry groups: 0..3 detector residue of tech A/B/F/V (always live: the detectors run on every search-mode sample),
+// 4..7 protocol state of tech A/B/F/V (only read or written while that tech is LOCKED), 8 carrier flags
+#define NFCB200_GROUPS 9
+
+NFC_HD void carry_group(Carry &c, int g, u32 *&ptr, u32 &words)
+{
+   switch (g)
+   {
+      case 0:
+         ptr = (u32 *) c.mA;
+         words = 3 * sizeof(Mod) / 4;
+         break;
+      case 1:
+         ptr = (u32 *) c.mB;
+         words = 2 * sizeof(Mod) / 4;
+         break;
+      case 2:
+         ptr = (u32 *) c.mF;
+         words = 2 * sizeof(Mod) / 4;
+         break;
+      case 3:
+         ptr = (u32 *) &c.mV;
+         words = sizeof(Mod) / 4;
+         break;
+      case 8:
+         ptr = &c.carrierOn;
+         words = 2;
+         break;
+      default:
+         ptr = (u32 *) &c.t[g - 4];
+         words = sizeof(TechSt) / 4;
+         break;
+   }
+}
+
+NFC_HD bool group_equal(Carry &a, Carry &b, int g)
+{
+   u32 *pa, *pb, wa, wb;
+   carry_group(a, g, pa, wa);
+   carry_group(b, g, pb, wb);
+   for (u32 i = 0; i < wa; i++)
+      if (pa[i] != pb[i])
+         return false;
+   return true;
+}
+
+NFC_HD void group_copy(Carry &dst, Carry &src, int g)
+{
+   u32 *pd, *ps, wd, ws;
+   carry_group(dst, g, pd, wd);
+   carry_group(src, g, ps, ws);
+   for (u32 i = 0; i < wd; i++)
+      pd[i] = ps[i];
 }
 
 // start a lane at absolute sample index `first` (the first sample it will be fed).  first == 0 is the exact reference

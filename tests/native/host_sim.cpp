@@ -12,7 +12,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "../../nfc_laboratory_b200/csrc/nfc_core.h"
+#include "../../nfc_laboratory_b200/csrc/nfc_chain.h"
 
 using namespace nfcb200;
 
@@ -76,6 +76,17 @@ int hostsim_params(uint32_t sampleRate, uint32_t enabled, Params *P)
    return P->valid;
 }
 
+/* speculative carry of a lane that does not start at sample 0: power-on state, carrier already on */
+void hostsim_default_carry(uint32_t sampleRate, void *out)
+{
+   Params P;
+   hostsim_params(sampleRate, 0xF, &P);
+   Carry c;
+   carry_init(c, P);
+   c.carrierOn = 1;
+   std::memcpy(out, &c, sizeof(Carry));
+}
+
 int hostsim_params_size(void)
 {
    return (int) sizeof(Params);
@@ -83,10 +94,11 @@ int hostsim_params_size(void)
 
 /*
  * Run one lane over mag[first .. n) (mag indexed by absolute sample).  carry_in == NULL: power-on carry.
- * The lane stops at n, or -- when own_end > 0 -- at the first sample >= own_end where it is dormant.
+ * The lane stops at n, or -- when own_end > 0 -- at the first sample >= own_end where it is dormant and outside
+ * every flagged block (flags: one byte per `block` samples, may be NULL).
  */
 long hostsim_run(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t enabled, uint32_t first, uint32_t warm, uint32_t own_end,
-                 const void *carry_in, void *carry_out, sim_frame *out, long cap, sim_result *res)
+                 const void *carry_in, void *carry_out, sim_frame *out, long cap, sim_result *res, const uint8_t *flags, uint32_t block)
 {
    Params P;
    if (!hostsim_params(sampleRate, enabled, &P))
@@ -111,14 +123,19 @@ long hostsim_run(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t ena
 
    for (; pos < n; pos++)
    {
-      if (own_end && pos >= own_end && M.dormant())
+      // a lane retires at the first sample past its own region where nothing is pending and the screen saw nothing
+      if (own_end && pos >= own_end && !(flags && flags[pos / block]) && M.dormant())
          break;
 
       M.step(mag[pos]);
    }
 
    if (carry_out)
-      std::memcpy(carry_out, &L.c, sizeof(Carry));
+   {
+      Carry c = L.c;
+      carry_canon(c);
+      std::memcpy(carry_out, &c, sizeof(Carry));
+   }
 
    if (res)
    {
@@ -129,6 +146,132 @@ long hostsim_run(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t ena
    }
 
    return sink.count;
+}
+
+
+/*
+ * Whole-stream model of the product pipeline: segments from the screening flags (one byte per block, bit 0 = trigger),
+ * one lane per segment, carry chain to the fixed point.  stats: [0] lanes [1] live lanes [2] rounds [3] lane runs
+ * [4] samples stepped [5] active blocks
+ */
+long hostsim_pipeline(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t enabled, uint8_t *flags, uint32_t nb, sim_frame *out, long cap,
+                      uint64_t *stats)
+{
+   Params P;
+   if (!hostsim_params(sampleRate, enabled, &P))
+      return -1;
+
+   blocks_activate(flags, nb);
+
+   uint32_t nseg = blocks_segments(flags, nb, (uint32_t) n, 0, nullptr, 0);
+   std::vector<LaneRec> lanes(nseg);
+   blocks_segments(flags, nb, (uint32_t) n, 0, lanes.data(), nseg);
+
+   for (uint32_t j = 0; j < nseg; j++)
+   {
+      if (lanes[j].first == 0)
+      {
+         carry_init(lanes[j].in, P);
+         carry_canon(lanes[j].in);
+      }
+      else
+         carry_speculate(lanes[j].in, P);
+   }
+
+   std::vector<std::vector<sim_frame>> frames(nseg);
+   std::vector<float> scratch(NFCB200_SCRATCH_FLOATS);
+   std::vector<u8> sb(512);
+
+   uint64_t rounds = 0, runs = 0, work = 0;
+
+   for (;;)
+   {
+      bool any = false;
+
+      for (uint32_t j = 0; j < nseg; j++)
+      {
+         LaneRec &R = lanes[j];
+
+         if (R.dead || !R.dirty)
+            continue;
+
+         any = true;
+
+         std::fill(scratch.begin(), scratch.end(), 0.0f);
+         std::fill(sb.begin(), sb.end(), 0);
+
+         std::vector<sim_frame> buf(4096);
+         Sink sink {buf.data(), (long) buf.size(), 0};
+
+         Lane L;
+         lane_begin(L, P, R.in, R.first, NFCB200_HALO);
+
+         Machine<1, Sink> M(P, L, scratch.data(), sb.data(), sink);
+
+         uint64_t pos = R.first;
+
+         for (; pos < n; pos++)
+         {
+            if (pos >= R.end && !(flags[pos / NFCB200_BLOCK] & SCR_ACTIVE) && M.dormant())
+               break;
+
+            M.step(mag[pos]);
+         }
+
+         R.stop = (uint32_t) pos;
+         R.lockedMask = L.lockedMask;
+         R.out = L.c;
+         carry_canon(R.out);
+         R.gen++;
+         R.dirty = 0;
+         R.nframes = (uint32_t) sink.count;
+         buf.resize(sink.count);
+         frames[j] = buf;
+
+         runs++;
+         work += pos - R.first;
+      }
+
+      if (!any)
+         break;
+
+      rounds++;
+
+      chain_walk(lanes.data(), nseg, P);
+   }
+
+   long count = 0;
+   uint64_t live = 0;
+
+   for (uint32_t j = 0; j < nseg; j++)
+   {
+      if (lanes[j].dead)
+         continue;
+
+      live++;
+
+      for (const sim_frame &f: frames[j])
+      {
+         if (count < cap)
+            out[count] = f;
+         count++;
+      }
+   }
+
+   if (stats)
+   {
+      uint64_t act = 0;
+      for (uint32_t b = 0; b < nb; b++)
+         act += (flags[b] & SCR_ACTIVE) ? 1 : 0;
+      stats[0] = nseg;
+      stats[1] = live;
+      stats[2] = rounds;
+      stats[3] = runs;
+      stats[4] = work;
+      stats[5] = act;
+   }
+
+   return count;
 }
 
 }

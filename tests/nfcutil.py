@@ -121,7 +121,7 @@ def ref_decode(mag, rate=10000000, chunk=65536, enabled=0xF, cap=65536):
 
 def build_hostsim():
     src = os.path.join(ROOT, "tests", "native", "host_sim.cpp")
-    deps = [src, os.path.join(ROOT, "nfc_laboratory_b200", "csrc", "nfc_core.h"), os.path.join(ROOT, "nfc_laboratory_b200", "csrc", "nfc_params.h")]
+    deps = [src] + [os.path.join(ROOT, "nfc_laboratory_b200", "csrc", h) for h in ("nfc_core.h", "nfc_params.h", "nfc_chain.h")]
     if os.path.exists(HOSTSIM_SO) and all(os.path.getmtime(HOSTSIM_SO) >= os.path.getmtime(d) for d in deps):
         return
     os.makedirs(os.path.dirname(HOSTSIM_SO), exist_ok=True)
@@ -139,13 +139,16 @@ def sim_lib():
         lib = C.CDLL(HOSTSIM_SO)
         lib.hostsim_run.restype = C.c_long
         lib.hostsim_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                    C.c_void_p, C.c_void_p, C.POINTER(SimFrame), C.c_long, C.POINTER(SimResult)]
+                                    C.c_void_p, C.c_void_p, C.POINTER(SimFrame), C.c_long, C.POINTER(SimResult), C.c_void_p, C.c_uint32]
         lib.hostsim_carry_size.restype = C.c_int
+        lib.hostsim_pipeline.restype = C.c_long
+        lib.hostsim_pipeline.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(SimFrame), C.c_long,
+                                         C.POINTER(C.c_uint64)]
         _sim = lib
     return _sim
 
 
-def sim_run(mag, rate=10000000, enabled=0xF, first=0, warm=4096, own_end=0, carry_in=None, cap=65536):
+def sim_run(mag, rate=10000000, enabled=0xF, first=0, warm=4096, own_end=0, carry_in=None, cap=65536, flags=None, block=256):
     """host build of the device lane machine; returns (frames, carry_out bytes, SimResult)"""
     lib = sim_lib()
     mag = np.ascontiguousarray(mag, dtype=np.float32)
@@ -154,10 +157,26 @@ def sim_run(mag, rate=10000000, enabled=0xF, first=0, warm=4096, own_end=0, carr
     csz = lib.hostsim_carry_size()
     cout = C.create_string_buffer(csz)
     cin = C.create_string_buffer(carry_in, csz) if carry_in is not None else None
-    n = lib.hostsim_run(mag.ctypes.data, mag.size, rate, enabled, first, warm, own_end, cin, cout, buf, cap, C.byref(res))
+    fl = np.ascontiguousarray(flags, dtype=np.uint8) if flags is not None else None
+    n = lib.hostsim_run(mag.ctypes.data, mag.size, rate, enabled, first, warm, own_end, cin, cout, buf, cap, C.byref(res),
+                        fl.ctypes.data if fl is not None else None, block)
     assert 0 <= n <= cap
     frames = [frame_tuple(f.tech, f.type, f.flags, f.phase, f.rate, f.start, f.end, bytes(f.data[:f.len])) for f in buf[:n]]
     return frames, cout.raw, res
+
+
+def sim_pipeline(mag, trigger_blocks, rate=10000000, enabled=0xF, cap=65536):
+    """segment-speculative pipeline on the host build of the lane machine; trigger_blocks: bool per 256-sample block"""
+    lib = sim_lib()
+    mag = np.ascontiguousarray(mag, dtype=np.float32)
+    flags = np.ascontiguousarray(trigger_blocks, dtype=np.uint8).copy()
+    buf = (SimFrame * cap)()
+    stats = (C.c_uint64 * 8)()
+    n = lib.hostsim_pipeline(mag.ctypes.data, mag.size, rate, enabled, flags.ctypes.data, flags.size, buf, cap, stats)
+    assert 0 <= n <= cap
+    frames = [frame_tuple(f.tech, f.type, f.flags, f.phase, f.rate, f.start, f.end, bytes(f.data[:f.len])) for f in buf[:n]]
+    st = dict(lanes=stats[0], live=stats[1], rounds=stats[2], runs=stats[3], work=stats[4], active_blocks=stats[5])
+    return frames, st
 
 
 def describe(fr):
