@@ -719,7 +719,7 @@ struct Machine
                   {
                      int fsdi = (fb(1, len) >> 4) & 0x0F;
                      fs.lastCommand = b0;
-                     ps.maxFrameSize = (u32) NFC_FDS_TABLE_[fsdi];
+                     ps.maxFrameSize = (u32) nfc_fds_table((int) fsdi);
                      fs.frameWaitingTime = P.fwtActivation;
                      phase = PH_Selection;
                      flags |= !A_crc_ok(len) ? FL_Crc : 0;
@@ -747,8 +747,8 @@ struct Machine
                            sfgi = 0;
                         if (fwi == 15)
                            fwi = 4;
-                        ps.startUpGuardTime = (u32) (int) (P.stu * NFC_XGT_TABLE_[sfgi]);
-                        ps.frameWaitingTime = (u32) (int) (P.stu * NFC_XGT_TABLE_[fwi]);
+                        ps.startUpGuardTime = (u32) (int) (P.stu * nfc_xgt_table((int) sfgi));
+                        ps.frameWaitingTime = (u32) (int) (P.stu * nfc_xgt_table((int) fwi));
                      }
                      else
                      {
@@ -1782,8 +1782,8 @@ struct Machine
          {
             int fdsi = (fb(10, len) >> 4) & 0x0f;
             int fwi = (fb(11, len) >> 4) & 0x0f;
-            ps.maxFrameSize = (u32) NFC_FDS_TABLE_[fdsi];
-            ps.frameWaitingTime = (u32) (int) (P.stu * NFC_XGT_TABLE_[fwi]);
+            ps.maxFrameSize = (u32) nfc_fds_table((int) fdsi);
+            ps.frameWaitingTime = (u32) (int) (P.stu * nfc_xgt_table((int) fwi));
             phase = PH_Selection;
             flags |= !B_crc_ok(len) ? FL_Crc : 0;
             break;
@@ -1798,7 +1798,7 @@ struct Machine
                u32 param1 = fb(5, len), param2 = fb(6, len);
                u32 tr0i = (param1 >> 6) & 0x3;
                u32 fdsi = param2 & 0xf;
-               ps.maxFrameSize = (u32) NFC_FDS_TABLE_[fdsi];
+               ps.maxFrameSize = (u32) nfc_fds_table((int) fdsi);
                if (!tr0i)
                   ps.frameGuardTime = P.B_fgt;
                else

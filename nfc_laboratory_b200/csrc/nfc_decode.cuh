@@ -1,0 +1,466 @@
+/*
+ * nfc_decode.cuh -- K2..K4: segment construction, the exact decoder lanes and the carry chain, on the device.
+ *
+ *   segment_*_kernel : one thread per stream; finishes the screening flags at block granularity (level shifts,
+ *                      carrier on/off band, dilation) and cuts the stream into segments (nfc_chain.h)
+ *   lanes_kernel     : persistent warps; every thread is one lane = one exact per-sample decoder (nfc_core.h) running
+ *                      over one segment.  The 32 lanes of a warp step in lock step and address their history rings with
+ *                      the same relative slot, so ring traffic is fully coalesced (scratch words interleaved by lane).
+ *   chain_kernel     : one thread per stream; chain_walk() -> list of lanes whose speculated carry was wrong
+ *   lane_meta_kernel : compact (generation, dead) per lane for the host-side frame gather
+ *   stream_kernel    : single-lane sequential decode for the streaming entry point (nfcb200_stream_push)
+ *
+ * No kernel here has a counterpart in the reference: the reference runs this logic on one CPU thread per stream.
+ */
+#ifndef NFCB200_DECODE_CUH
+#define NFCB200_DECODE_CUH
+
+#include "nfc_screen.cuh"
+
+namespace nfcb200 {
+
+// decoder parameters travel as a __grid_constant__ kernel argument (constant bank, per launch): handles with different
+// configurations can decode concurrently
+
+// one decoded frame in the device pool (128 bytes); payloads longer than 80 bytes continue in the extension pool
+struct FrameRec
+{
+   u32 lane;  // global lane index
+   u32 gen;   // generation of the lane run that produced it
+   u32 seq;   // order within the run
+   u32 tech, type, flags, phase, rate, start, end, len;
+   u32 ext;   // first 128-byte extension chunk, 0xFFFFFFFF if none
+   u8 data[80];
+};
+
+struct FramePool
+{
+   FrameRec *recs;
+   u32 cap;
+   u32 *count;  // device counter (may exceed cap: overflow is reported, excess frames are dropped)
+   u8 *ext;     // extension chunks of 128 bytes
+   u32 extCap;  // in chunks
+   u32 *extCount;
+};
+
+struct DeviceSink
+{
+   FramePool pool;
+   u32 lane, gen, seq;
+
+   __device__ void frame(const FrameOut &f, const u8 *payload)
+   {
+      u32 idx = atomicAdd(pool.count, 1u);
+      u32 s = seq++;
+
+      if (idx >= pool.cap)
+         return;
+
+      FrameRec &r = pool.recs[idx];
+      r.lane = lane;
+      r.gen = gen;
+      r.seq = s;
+      r.tech = f.tech;
+      r.type = f.type;
+      r.flags = f.flags;
+      r.phase = f.phase;
+      r.rate = f.rate;
+      r.start = f.start;
+      r.end = f.end;
+      r.len = f.len;
+      r.ext = 0xFFFFFFFFu;
+
+      u32 inl = f.len < 80 ? f.len : 80;
+      for (u32 i = 0; i < inl; i++)
+         r.data[i] = payload[i];
+
+      if (f.len > 80)
+      {
+         u32 rest = f.len - 80;
+         u32 chunks = (rest + 127) / 128;
+         u32 e = atomicAdd(pool.extCount, chunks);
+         if (e + chunks <= pool.extCap)
+         {
+            r.ext = e;
+            u8 *dst = pool.ext + (size_t) e * 128;
+            for (u32 i = 0; i < rest; i++)
+               dst[i] = payload[80 + i];
+         }
+         else
+         {
+            r.len = 80; // extension pool exhausted: reported through the counter, payload truncated
+         }
+      }
+   }
+};
+
+__device__ __forceinline__ float load_sample(const void *samples, int sigtype, uint64_t idx)
+{
+   switch (sigtype)
+   {
+      case SIG_IQ_F32:
+      {
+         float2 v = __ldg(((const float2 *) samples) + idx);
+         return sqrtf(v.x * v.x + v.y * v.y);
+      }
+      case SIG_MAG_F32:
+         return __ldg(((const float *) samples) + idx);
+      case SIG_MAG_S16:
+         return (float) __ldg(((const short *) samples) + idx) / 32768.0f;
+      default:
+      {
+         short2 v = __ldg(((const short2 *) samples) + idx);
+         float I = (float) v.x / 32768.0f, Q = (float) v.y / 32768.0f;
+         return sqrtf(I * I + Q * Q);
+      }
+   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// segments
+// ---------------------------------------------------------------------------------------------------------------------
+struct SegmentConfig
+{
+   uint8_t *flags;      // [n_streams][n_blocks]
+   const float *bsum;   // [n_streams][n_blocks]
+   uint32_t n_streams, n_blocks;
+   uint64_t n_samples;
+   uint32_t *counts;    // [n_streams] segments per stream
+   const uint32_t *offsets; // [n_streams] exclusive prefix of counts
+   LaneRec *lanes;
+   uint32_t *queue;     // dirty lane indices
+   float low, high;     // carrier thresholds (NfcDecoder.cpp:328-329)
+   float meanW;         // per-block decay of the carrier average: signalMeanW0 ^ 256
+};
+
+// block-granular part of the screen: level shifts (the reference's gated envelope goes stale, NfcTech.cpp:39-53) and
+// the carrier on/off band (NfcDecoder.cpp:472-523), then dilation; returns the number of segments of the stream
+__global__ void segment_count_kernel(SegmentConfig c)
+{
+   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= c.n_streams)
+      return;
+
+   uint8_t *flags = c.flags + (size_t) s * c.n_blocks;
+   const float *bsum = c.bsum + (size_t) s * c.n_blocks;
+
+   float prev = bsum[0] * (1.0f / NFCB200_BLOCK);
+   float avg = 0;
+
+   for (uint32_t b = 0; b < c.n_blocks; b++)
+   {
+      float mean = bsum[b] * (1.0f / NFCB200_BLOCK);
+      uint8_t f = flags[b];
+
+      // sustained level change between consecutive blocks: the envelope gate of the reference closes (5 %)
+      if (fabsf(mean - prev) > 0.025f * fmaxf(prev, 1e-6f))
+         f |= SCR_TRIGGER;
+
+      // carrier average over the block: avg' ~ meanW * avg + (1 - meanW) * mean; a threshold crossing needs the
+      // average inside the hysteresis band at some point of the block
+      float avgEnd = c.meanW * avg + (1.0f - c.meanW) * mean;
+      float lo = fminf(fminf(avg, avgEnd), mean);
+      float hi = fmaxf(fmaxf(avg, avgEnd), mean);
+      if (lo < 1.2f * c.high && hi > 0.8f * c.low)
+         f |= SCR_TRIGGER;
+
+      flags[b] = f;
+      prev = mean;
+      avg = avgEnd;
+   }
+
+   blocks_activate(flags, c.n_blocks);
+
+   c.counts[s] = blocks_segments(flags, c.n_blocks, (u32) c.n_samples, s, nullptr, 0);
+}
+
+__global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Params dP)
+{
+   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= c.n_streams)
+      return;
+
+   const uint8_t *flags = c.flags + (size_t) s * c.n_blocks;
+   uint32_t off = c.offsets[s];
+   uint32_t n = c.counts[s];
+
+   blocks_segments(flags, c.n_blocks, (u32) c.n_samples, s, c.lanes + off, n);
+
+   Carry spec, pon;
+   carry_speculate(spec, dP);
+   carry_init(pon, dP);
+   carry_canon(pon);
+
+   for (uint32_t j = 0; j < n; j++)
+   {
+      LaneRec &L = c.lanes[off + j];
+      L.in = L.first == 0 ? pon : spec;
+      c.queue[off + j] = off + j; // first round: every lane runs
+   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// lanes
+// ---------------------------------------------------------------------------------------------------------------------
+struct LaneConfig
+{
+   const void *samples;
+   uint64_t n_samples;
+   int sigtype;
+   const uint8_t *flags;
+   uint32_t n_blocks;
+   LaneRec *lanes;
+   const uint32_t *queue;
+   uint32_t queue_count;
+   uint32_t *cursor;         // work-stealing cursor over the queue
+   float *scratch;           // [n_warps][NFCB200_SCRATCH_FLOATS][32]
+   uint8_t *sbuf;            // [n_warps * 32][512]
+   FramePool pool;
+   unsigned long long *work; // samples stepped (statistics)
+};
+
+#define LANE_THREADS 128
+
+__global__ void __launch_bounds__(LANE_THREADS) lanes_kernel(LaneConfig c, const __grid_constant__ Params dP)
+{
+   const uint32_t lane = threadIdx.x & 31;
+   const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+
+   float *rg = c.scratch + (size_t) wg * NFCB200_SCRATCH_FLOATS * 32 + lane;
+   u8 *sb = c.sbuf + ((size_t) wg * 32 + lane) * 512;
+
+   for (;;)
+   {
+      uint32_t base = 0;
+      if (lane == 0)
+         base = atomicAdd(c.cursor, 32u);
+      base = __shfl_sync(0xffffffffu, base, 0);
+
+      if (base >= c.queue_count)
+         break;
+
+      const uint32_t qi = base + lane;
+      const bool have = qi < c.queue_count;
+
+      // correlation rings must read as zero until written (a fresh reference decoder); the sample rings are only read
+      // after 1024 steps (detector gate) and the integration ring only after clear_for_listen(), so they need no wipe
+      for (uint32_t i = NFCB200_OFF_CA; i < NFCB200_SCRATCH_FLOATS; i++)
+         rg[(size_t) i * 32] = 0.0f;
+
+      if (!have)
+         continue;
+
+      const uint32_t li = c.queue[qi];
+      LaneRec &R = c.lanes[li];
+
+      Lane L;
+      lane_begin(L, dP, R.in, R.first, NFCB200_HALO);
+
+      DeviceSink sink;
+      sink.pool = c.pool;
+      sink.lane = li;
+      sink.gen = R.gen + 1;
+      sink.seq = 0;
+
+      Machine<32, DeviceSink> M(dP, L, rg, sb, sink);
+
+      const uint64_t streamBase = (uint64_t) R.stream * c.n_samples;
+      const uint8_t *flags = c.flags + (size_t) R.stream * c.n_blocks;
+      const uint32_t end = R.end;
+      const uint32_t n = (uint32_t) c.n_samples;
+
+      uint32_t pos = R.first;
+
+      for (; pos < n; pos++)
+      {
+         // retire at the first sample past the own region that is outside every active block with nothing pending
+         if (pos >= end && !(flags[pos >> 8] & SCR_ACTIVE) && M.dormant())
+            break;
+
+         M.step(load_sample(c.samples, c.sigtype, streamBase + pos));
+      }
+
+      R.stop = pos;
+      R.lockedMask = L.lockedMask;
+      R.out = L.c;
+      carry_canon(R.out);
+      R.gen = sink.gen;
+      R.dirty = 0;
+      R.nframes = sink.seq;
+
+      atomicAdd(c.work, (unsigned long long) (pos - R.first));
+   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// carry chain
+// ---------------------------------------------------------------------------------------------------------------------
+struct ChainConfig
+{
+   LaneRec *lanes;
+   const uint32_t *offsets;
+   const uint32_t *counts;
+   uint32_t n_streams;
+   uint32_t *queue;
+   uint32_t *queue_count;
+};
+
+__global__ void chain_kernel(ChainConfig c, const __grid_constant__ Params dP)
+{
+   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= c.n_streams)
+      return;
+
+   uint32_t off = c.offsets[s];
+   uint32_t n = c.counts[s];
+
+   if (!chain_walk(c.lanes + off, n, dP))
+      return;
+
+   for (uint32_t j = 0; j < n; j++)
+   {
+      LaneRec &L = c.lanes[off + j];
+      if (L.dirty && !L.dead)
+         c.queue[atomicAdd(c.queue_count, 1u)] = off + j;
+   }
+}
+
+// (generation << 1 | dead) per lane, plus the stream of the lane: what the host needs to gather frames
+__global__ void lane_meta_kernel(const LaneRec *lanes, uint32_t n, uint32_t *meta, uint32_t *streamOf, unsigned long long *liveCount)
+{
+   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n)
+      return;
+   meta[i] = (lanes[i].gen << 1) | (lanes[i].dead ? 1u : 0u);
+   streamOf[i] = lanes[i].stream;
+   if (!lanes[i].dead)
+      atomicAdd(liveCount, 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// streaming: one sequential lane per handle, suspended / resumed across pushes, skipping idle blocks exactly like the
+// batch lanes do (cold start HALO samples before the next active block from the exact carry it retired with)
+// ---------------------------------------------------------------------------------------------------------------------
+struct StreamState
+{
+   Lane L;
+   Carry carry;     // exact canonical carry at `pos` while parked
+   u32 running;     // 1: L is a live lane positioned at `pos`; 0: parked (dormant)
+   u32 contig;      // parked only: L is still positioned exactly at `pos` (it can be resumed instead of cold started)
+   u32 pos;         // absolute index of the next sample to consume
+   u32 seq;
+};
+
+struct StreamConfig
+{
+   const void *samples;   // device buffer holding absolute samples [base, base + count)
+   uint32_t base;
+   uint32_t count;
+   int sigtype;
+   const uint8_t *flags;  // one byte per block, flags[0] is absolute block flagBase
+   uint32_t flagBase;
+   uint32_t flagCount;
+   uint32_t limit;        // process samples < limit (absolute); limit <= base + count
+   uint32_t final;        // end of stream: do not wait for more data
+   StreamState *state;
+   float *scratch;        // NFCB200_SCRATCH_FLOATS floats
+   uint8_t *sbuf;         // 512 bytes
+   FramePool pool;
+};
+
+__global__ void stream_kernel(StreamConfig c, const __grid_constant__ Params dP)
+{
+   if (threadIdx.x != 0 || blockIdx.x != 0)
+      return;
+
+   StreamState &S = *c.state;
+
+   Lane L = S.L;
+
+   DeviceSink sink;
+   sink.pool = c.pool;
+   sink.lane = 0;
+   sink.gen = 1;
+   sink.seq = S.seq;
+
+   Machine<1, DeviceSink> M(dP, L, c.scratch, c.sbuf, sink);
+
+   u32 pos = S.pos;
+   u32 running = S.running;
+   u32 contig = S.contig;
+
+   auto active = [&](u32 p) -> bool {
+      u32 b = p >> 8;
+      if (b < c.flagBase || b - c.flagBase >= c.flagCount)
+         return true; // blocks not screened yet count as active
+      return (c.flags[b - c.flagBase] & SCR_ACTIVE) != 0;
+   };
+
+   while (pos < c.limit)
+   {
+      if (!running)
+      {
+         // parked: next active block at or after pos
+         u32 b = pos >> 8;
+         const u32 lastBlock = (c.limit - 1) >> 8;
+         while (b <= lastBlock && !active(b << 8))
+            b++;
+
+         if (b > lastBlock)
+         {
+            // idle to the end of the known data.  Skip ahead, but never so far that a block turning active later
+            // (the last block is still filling) could not get its full warm-up
+            u32 hold = c.final ? c.limit : ((lastBlock << 8) > NFCB200_HALO ? (lastBlock << 8) - NFCB200_HALO : 0);
+            if (hold > pos)
+            {
+               pos = hold;
+               contig = 0;
+            }
+            break;
+         }
+
+         u32 begin = b << 8;
+         if (begin < pos)
+            begin = pos;
+
+         if (begin >= pos + NFCB200_HALO || !contig)
+         {
+            // cold start HALO samples early from the exact carry (lane_begin restarts front end, rings, running sums)
+            u32 first = begin >= pos + NFCB200_HALO ? begin - NFCB200_HALO : pos;
+            for (u32 i = NFCB200_OFF_CA; i < NFCB200_SCRATCH_FLOATS; i++)
+               c.scratch[i] = 0.0f;
+            lane_begin(L, dP, S.carry, first, first ? NFCB200_HALO : 0);
+            pos = first;
+         }
+         // else: too close for a cold start and the parked machine is still positioned at pos: resume it
+
+         running = 1;
+         contig = 1;
+      }
+
+      while (pos < c.limit)
+      {
+         if (!active(pos) && M.dormant())
+         {
+            S.carry = L.c;
+            carry_canon(S.carry);
+            running = 0;
+            contig = 1;
+            break;
+         }
+
+         M.step(load_sample(c.samples, c.sigtype, (uint64_t) (pos - c.base)));
+         pos++;
+      }
+   }
+
+   S.L = L;
+   S.pos = pos;
+   S.running = running;
+   S.contig = contig;
+   S.seq = sink.seq;
+}
+
+}
+
+#endif

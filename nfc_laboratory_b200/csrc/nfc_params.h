@@ -96,11 +96,40 @@ struct Params
    int valid; // 0 when the sample rate cannot be represented by the scratch layout
 };
 
-// Nfc.h tables
-static const int NFC_FDS_TABLE_[16] = {16, 24, 32, 40, 48, 64, 96, 128, 256, 512, 1024, 2048, 4096, 0, 0, 0};
-static const int NFC_XGT_TABLE_[16] = {4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288, 1048576, 2097152, 4194304, 8388608, 16777216, 33554432, 67108864, 134217728};
+// Nfc.h:45-52 tables (functions, so that device code can index them)
+#if defined(__CUDACC__)
+#define NFC_TAB_HD __host__ __device__ inline
+#else
+#define NFC_TAB_HD inline
+#endif
 
-#ifndef __CUDA_ARCH__
+// NFC_FDS_TABLE: FSDI -> frame size
+NFC_TAB_HD int nfc_fds_table(int i)
+{
+   switch (i & 15)
+   {
+      case 0: return 16;
+      case 1: return 24;
+      case 2: return 32;
+      case 3: return 40;
+      case 4: return 48;
+      case 5: return 64;
+      case 6: return 96;
+      case 7: return 128;
+      case 8: return 256;
+      case 9: return 512;
+      case 10: return 1024;
+      case 11: return 2048;
+      case 12: return 4096;
+      default: return 0;
+   }
+}
+
+// NFC_SFGT_TABLE / NFC_FWT_TABLE: 256 * 16 * 2^i in 1/fc units
+NFC_TAB_HD int nfc_xgt_table(int i)
+{
+   return 4096 << (i & 15);
+}
 
 static inline void rate_fill(RateParams *r, double stu, int shiftBase, int rate, u32 sdd, u32 corrOff)
 {
@@ -219,8 +248,6 @@ static inline void params_defaults(Params *P)
    P->thr[TECH_F] = TechThresholds {0.50f, 0.10f, 0.90f}; // NfcF.cpp:88-94
    P->thr[TECH_V] = TechThresholds {0.50f, 0.90f, 1.00f}; // NfcV.cpp:101-107
 }
-
-#endif // !__CUDA_ARCH__
 
 }
 

@@ -1,0 +1,903 @@
+/*
+ * nfcb200.cu -- C ABI (include/nfcb200.h) and host orchestration of the B200 NFC demodulation path.
+ *
+ * One translation unit: the kernels live in nfc_screen.cuh / nfc_decode.cuh, the exact lane machine in nfc_core.h.
+ * Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+ * (-fmad=false: the reference's x86 build has no FMA, CMakeLists.txt:36-40; lane decisions must be bit-identical).
+ *
+ * There is no CPU fallback in this library: every entry point that decodes requires a CUDA device.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/nfcb200.h"
+#include "nfc_decode.cuh"
+
+using namespace nfcb200;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------------
+static thread_local char g_error[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(g_error, sizeof(g_error), fmt, ap);
+   va_end(ap);
+   return code;
+}
+
+#define CUDA_TRY(expr)                                                                                              \
+   do                                                                                                               \
+   {                                                                                                                \
+      cudaError_t e_ = (expr);                                                                                      \
+      if (e_ != cudaSuccess)                                                                                        \
+         return fail(NFCB200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+   }                                                                                                                \
+   while (0)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// device buffer that only grows
+// ---------------------------------------------------------------------------------------------------------------------
+struct DevBuf
+{
+   void *ptr = nullptr;
+   size_t cap = 0;
+
+   int reserve(size_t bytes)
+   {
+      if (bytes <= cap)
+         return 0;
+      if (ptr)
+         cudaFree(ptr);
+      ptr = nullptr;
+      cap = 0;
+      size_t want = bytes + bytes / 8 + 256;
+      cudaError_t e = cudaMalloc(&ptr, want);
+      if (e != cudaSuccess)
+         return fail(NFCB200_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+      cap = want;
+      return 0;
+   }
+
+   void release()
+   {
+      if (ptr)
+         cudaFree(ptr);
+      ptr = nullptr;
+      cap = 0;
+   }
+
+   template <class T>
+   T *as() const
+   {
+      return (T *) ptr;
+   }
+};
+
+struct Counters
+{
+   u32 poolCount;
+   u32 extCount;
+   u32 queueCount;
+   u32 cursor;
+   unsigned long long work;
+   unsigned long long live;
+};
+
+struct nfcb200_handle
+{
+   nfcb200_config cfg;
+   Params P;
+   u32 paramsRate = 0;
+   int device = 0;
+   int smCount = 148;
+   cudaStream_t stream = nullptr;
+   cudaEvent_t ev[8] = {};
+
+   DevBuf samples, flags, bsum, counts, offsets, lanes, queue, scratch, sbuf, pool, ext, meta, streamOf, counters;
+   nfcb200_stats stats;
+
+   // last batch geometry (for the flag tap)
+   u32 lastStreams = 0, lastBlocks = 0;
+
+   // streaming state
+   DevBuf sState, sScratch, sSbuf, sSamples, sFlags, sBsum, sCounts;
+   std::vector<unsigned char> sHostTail; // samples retained on the host side of the stream buffer
+   u32 sBase = 0;        // absolute index of the first retained sample
+   u32 sCount = 0;       // retained samples
+   u32 sRate = 0;
+   int sSig = 0;
+   bool sInit = false;
+   u32 sEmitted = 0;     // frames already returned
+};
+
+static int setup_params(nfcb200_handle *h, u32 sampleRate)
+{
+   Params &P = h->P;
+   memset(&P, 0, sizeof(P));
+   params_defaults(&P);
+   P.enabled = h->cfg.enabled & 0xF;
+   P.streamTime = h->cfg.stream_time;
+   P.power = h->cfg.power_level_threshold;
+   for (int t = 0; t < 4; t++)
+   {
+      P.thr[t].corr = h->cfg.correlation_threshold[t];
+      P.thr[t].modMin = h->cfg.modulation_min[t];
+      P.thr[t].modMax = h->cfg.modulation_max[t];
+   }
+   params_init(&P, sampleRate);
+
+   if (!P.valid)
+      return fail(NFCB200_ERR_UNSUPPORTED, "sample rate %u is outside the supported range of the device ring layout", sampleRate);
+
+   // the screening tile keeps SCR_HALO samples of history: every correlator tap must fit
+   if (P.V.p1 + 2 > SCR_HALO || P.A[0].p1 + 2 > SCR_HALO || NFCB200_BLOCK * 2 > SCR_HALO)
+      return fail(NFCB200_ERR_UNSUPPORTED, "sample rate %u needs a longer screening halo than %d samples", sampleRate, SCR_HALO);
+
+   h->paramsRate = sampleRate;
+   return 0;
+}
+
+static void fill_screen_config(const nfcb200_handle *h, ScreenConfig &sc)
+{
+   const Params &P = h->P;
+   const float margin = 0.9f;
+   for (int r = 0; r < 3; r++)
+   {
+      sc.p1[r] = P.A[r].p1;
+      sc.p2[r] = P.A[r].p2;
+   }
+   sc.vp1 = P.V.p1;
+   sc.vp2 = P.V.p2;
+   // rate 106 is only used by NFC-A; 212 / 424 by NFC-A and NFC-F; disabled techs still screen (conservative)
+   float cA = P.thr[TECH_A].corr, cF = P.thr[TECH_F].corr;
+   sc.kSD[0] = margin * cA;
+   sc.kSD[1] = margin * std::min(cA, cF);
+   sc.kSD[2] = margin * std::min(cA, cF);
+   sc.kV = margin * P.thr[TECH_V].corr;
+   sc.kB = margin * P.thr[TECH_B].modMin;
+   sc.use_tma = h->cfg.use_tma ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *nfcb200_last_error(void)
+{
+   return g_error;
+}
+
+const char *nfcb200_version(void)
+{
+   return "nfcb200 0.1 sm_100a";
+}
+
+void nfcb200_config_default(nfcb200_config *cfg)
+{
+   memset(cfg, 0, sizeof(*cfg));
+   Params P;
+   params_defaults(&P);
+   cfg->device = 0;
+   cfg->enabled = P.enabled;
+   cfg->power_level_threshold = P.power;
+   for (int t = 0; t < 4; t++)
+   {
+      cfg->correlation_threshold[t] = P.thr[t].corr;
+      cfg->modulation_min[t] = P.thr[t].modMin;
+      cfg->modulation_max[t] = P.thr[t].modMax;
+   }
+   cfg->stream_time = 0;
+   cfg->use_tma = 1;
+   cfg->max_rounds = 0;
+}
+
+int nfcb200_create(const nfcb200_config *cfg, nfcb200_handle **out)
+{
+   if (!out)
+      return fail(NFCB200_ERR_INVALID, "null output handle");
+
+   *out = nullptr;
+
+   int count = 0;
+   cudaError_t e = cudaGetDeviceCount(&count);
+   if (e != cudaSuccess || count == 0)
+      return fail(NFCB200_ERR_NO_DEVICE, "no CUDA device available (%s): this library has no CPU path", e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+
+   nfcb200_config c;
+   if (cfg)
+      c = *cfg;
+   else
+      nfcb200_config_default(&c);
+
+   if (c.device < 0 || c.device >= count)
+      return fail(NFCB200_ERR_INVALID, "device %d out of range (0..%d)", c.device, count - 1);
+
+   CUDA_TRY(cudaSetDevice(c.device));
+
+   nfcb200_handle *h = new nfcb200_handle();
+   h->cfg = c;
+   h->device = c.device;
+   memset(&h->stats, 0, sizeof(h->stats));
+
+   cudaDeviceProp prop;
+   if (cudaGetDeviceProperties(&prop, c.device) == cudaSuccess)
+      h->smCount = prop.multiProcessorCount;
+
+   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+   if (e != cudaSuccess)
+   {
+      delete h;
+      return fail(NFCB200_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+   }
+
+   for (auto &ev: h->ev)
+      cudaEventCreate(&ev);
+
+   cudaFuncSetAttribute(screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem));
+
+   *out = h;
+   return 0;
+}
+
+void nfcb200_destroy(nfcb200_handle *h)
+{
+   if (!h)
+      return;
+   cudaSetDevice(h->device);
+   cudaStreamSynchronize(h->stream);
+   DevBuf *bufs[] = {&h->samples, &h->flags, &h->bsum, &h->counts, &h->offsets, &h->lanes, &h->queue, &h->scratch, &h->sbuf, &h->pool, &h->ext, &h->meta,
+                     &h->streamOf, &h->counters, &h->sState, &h->sScratch, &h->sSbuf, &h->sSamples, &h->sFlags, &h->sBsum, &h->sCounts};
+   for (DevBuf *b: bufs)
+      b->release();
+   for (auto &ev: h->ev)
+      if (ev)
+         cudaEventDestroy(ev);
+   if (h->stream)
+      cudaStreamDestroy(h->stream);
+   delete h;
+}
+
+int nfcb200_configure(nfcb200_handle *h, const nfcb200_config *cfg)
+{
+   if (!h || !cfg)
+      return fail(NFCB200_ERR_INVALID, "null argument");
+   if (cfg->device != h->device)
+      return fail(NFCB200_ERR_INVALID, "the device of a handle cannot change");
+   h->cfg = *cfg;
+   h->paramsRate = 0; // parameters are re-derived at the next decode (NfcDecoder::initialize)
+   return 0;
+}
+
+int nfcb200_get_stats(nfcb200_handle *h, nfcb200_stats *stats)
+{
+   if (!h || !stats)
+      return fail(NFCB200_ERR_INVALID, "null argument");
+   *stats = h->stats;
+   return 0;
+}
+
+int nfcb200_get_block_flags(nfcb200_handle *h, uint8_t *out, uint64_t cap, uint64_t *n_blocks_per_stream)
+{
+   if (!h)
+      return fail(NFCB200_ERR_INVALID, "null handle");
+   if (n_blocks_per_stream)
+      *n_blocks_per_stream = h->lastBlocks;
+   uint64_t total = (uint64_t) h->lastStreams * h->lastBlocks;
+   if (!out)
+      return 0;
+   if (cap < total)
+      return fail(NFCB200_ERR_CAPACITY, "flag buffer too small: need %llu bytes", (unsigned long long) total);
+   CUDA_TRY(cudaSetDevice(h->device));
+   CUDA_TRY(cudaMemcpy(out, h->flags.ptr, total, cudaMemcpyDeviceToHost));
+   return 0;
+}
+
+// convert one pool record to the ABI frame
+static void emit_frame(const nfcb200_handle *h, const FrameRec &r, const std::vector<unsigned char> &ext, u32 stream, u32 sampleRate, nfcb200_frame &o)
+{
+   memset(&o, 0, sizeof(o));
+   o.stream = stream;
+   o.tech_type = r.tech;
+   o.frame_type = r.type;
+   o.frame_flags = r.flags;
+   o.frame_phase = r.phase;
+   o.frame_rate = r.rate;
+   o.sample_start = r.start;
+   o.sample_end = r.end;
+   o.sample_rate = sampleRate;
+   o.time_start = (double) r.start / (double) sampleRate;
+   o.time_end = (double) r.end / (double) sampleRate;
+   o.date_time = (double) h->P.streamTime + o.time_start;
+   u32 len = r.len > 512 ? 512 : r.len;
+   o.length = len;
+   u32 inl = len < 80 ? len : 80;
+   memcpy(o.data, r.data, inl);
+   if (len > 80 && r.ext != 0xFFFFFFFFu && (size_t) r.ext * 128 + (len - 80) <= ext.size())
+      memcpy(o.data + 80, ext.data() + (size_t) r.ext * 128, len - 80);
+}
+
+int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_device, int sigtype, uint32_t n_streams, uint64_t n_samples,
+                         uint32_t sample_rate, nfcb200_frame *out, uint64_t cap, uint64_t *n_out)
+{
+   if (!h)
+      return fail(NFCB200_ERR_INVALID, "null handle");
+   if (n_out)
+      *n_out = 0;
+   if (sigtype < SIG_IQ_F32 || sigtype > SIG_IQ_S16)
+      return fail(NFCB200_ERR_INVALID, "unknown signal type %d", sigtype);
+   if (!samples || n_streams == 0 || n_samples == 0)
+      return fail(NFCB200_ERR_INVALID, "empty batch");
+   if (n_samples >= 0xFFFF0000ull)
+      return fail(NFCB200_ERR_UNSUPPORTED, "streams of 2^32 samples or more exceed the 32-bit sample clock of the frame format (NfcTech.h:338)");
+   if (cap && !out)
+      return fail(NFCB200_ERR_INVALID, "null frame buffer");
+
+   CUDA_TRY(cudaSetDevice(h->device));
+
+   if (h->paramsRate != sample_rate)
+   {
+      int rc = setup_params(h, sample_rate);
+      if (rc)
+         return rc;
+   }
+
+   cudaStream_t st = h->stream;
+   const u32 bs = sig_bytes(sigtype);
+   const uint64_t total = (uint64_t) n_streams * n_samples;
+   const u32 n_blocks = (u32) ((n_samples + NFCB200_BLOCK - 1) / NFCB200_BLOCK);
+   const u32 tiles = (u32) ((n_samples + SCR_TILE - 1) / SCR_TILE);
+   uint64_t launches = 0;
+
+   nfcb200_stats &S = h->stats;
+   memset(&S, 0, sizeof(S));
+   S.samples = total;
+   S.blocks = (uint64_t) n_streams * n_blocks;
+
+   cudaEventRecord(h->ev[0], st);
+
+   // ---- input ---------------------------------------------------------------------------------------------------------
+   const void *dSamples = samples;
+   if (!samples_on_device)
+   {
+      int rc = h->samples.reserve(total * bs + 64);
+      if (rc)
+         return rc;
+      CUDA_TRY(cudaMemcpyAsync(h->samples.ptr, samples, total * bs, cudaMemcpyHostToDevice, st));
+      dSamples = h->samples.ptr;
+   }
+
+   cudaEventRecord(h->ev[1], st);
+
+   // ---- K1: screening -------------------------------------------------------------------------------------------------
+   {
+      int rc = h->flags.reserve((size_t) n_streams * n_blocks);
+      rc = rc ? rc : h->bsum.reserve((size_t) n_streams * n_blocks * sizeof(float));
+      rc = rc ? rc : h->counts.reserve((size_t) n_streams * sizeof(u32));
+      rc = rc ? rc : h->offsets.reserve((size_t) n_streams * sizeof(u32));
+      rc = rc ? rc : h->counters.reserve(sizeof(Counters));
+      if (rc)
+         return rc;
+   }
+
+   ScreenConfig sc;
+   memset(&sc, 0, sizeof(sc));
+   sc.samples = dSamples;
+   sc.n_samples = n_samples;
+   sc.n_streams = n_streams;
+   sc.sigtype = sigtype;
+   sc.n_blocks = n_blocks;
+   sc.tiles_per_stream = tiles;
+   sc.flags = h->flags.as<uint8_t>();
+   sc.bsum = h->bsum.as<float>();
+   fill_screen_config(h, sc);
+   // cp.async.bulk needs 16-byte aligned global addresses: stream pitch and base pointer
+   if ((((uintptr_t) dSamples) & 15) || ((n_samples * bs) & 15))
+      sc.use_tma = 0;
+
+   {
+      uint64_t items = (uint64_t) n_streams * tiles;
+      u32 grid = (u32) std::min<uint64_t>(items, (uint64_t) h->smCount * 2);
+      screen_kernel<<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
+      launches++;
+      CUDA_TRY(cudaGetLastError());
+   }
+
+   cudaEventRecord(h->ev[2], st);
+
+   // ---- segments ------------------------------------------------------------------------------------------------------
+   SegmentConfig sg;
+   memset(&sg, 0, sizeof(sg));
+   sg.flags = h->flags.as<uint8_t>();
+   sg.bsum = h->bsum.as<float>();
+   sg.n_streams = n_streams;
+   sg.n_blocks = n_blocks;
+   sg.n_samples = n_samples;
+   sg.counts = h->counts.as<u32>();
+   sg.offsets = h->offsets.as<u32>();
+   sg.low = h->P.lowThr;
+   sg.high = h->P.highThr;
+   sg.meanW = powf(h->P.meanW0, (float) NFCB200_BLOCK);
+
+   const u32 sgrid = (n_streams + 63) / 64;
+   segment_count_kernel<<<sgrid, 64, 0, st>>>(sg);
+   launches++;
+   CUDA_TRY(cudaGetLastError());
+
+   std::vector<u32> counts(n_streams), offsets(n_streams);
+   CUDA_TRY(cudaMemcpyAsync(counts.data(), h->counts.ptr, n_streams * sizeof(u32), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaStreamSynchronize(st));
+
+   uint64_t nLanes64 = 0;
+   for (u32 s = 0; s < n_streams; s++)
+   {
+      offsets[s] = (u32) nLanes64;
+      nLanes64 += counts[s];
+   }
+   if (nLanes64 >= 0x7FFFFFFFull)
+      return fail(NFCB200_ERR_CAPACITY, "too many segments (%llu)", (unsigned long long) nLanes64);
+   const u32 nLanes = (u32) nLanes64;
+   S.lanes = nLanes;
+
+   {
+      int rc = h->lanes.reserve((size_t) nLanes * sizeof(LaneRec));
+      rc = rc ? rc : h->queue.reserve((size_t) nLanes * sizeof(u32));
+      rc = rc ? rc : h->meta.reserve((size_t) nLanes * sizeof(u32));
+      rc = rc ? rc : h->streamOf.reserve((size_t) nLanes * sizeof(u32));
+      if (rc)
+         return rc;
+   }
+
+   CUDA_TRY(cudaMemcpyAsync(h->offsets.ptr, offsets.data(), n_streams * sizeof(u32), cudaMemcpyHostToDevice, st));
+   sg.lanes = h->lanes.as<LaneRec>();
+   sg.queue = h->queue.as<u32>();
+   segment_fill_kernel<<<sgrid, 64, 0, st>>>(sg, h->P);
+   launches++;
+   CUDA_TRY(cudaGetLastError());
+
+   cudaEventRecord(h->ev[3], st);
+
+   // ---- frame pool ----------------------------------------------------------------------------------------------------
+   u32 poolCap = (u32) std::min<uint64_t>(32u << 20, std::max<uint64_t>(1u << 16, total / 512 + (uint64_t) nLanes * 8));
+   u32 extCap = std::max<u32>(1u << 12, poolCap / 8);
+   {
+      int rc = h->pool.reserve((size_t) poolCap * sizeof(FrameRec));
+      rc = rc ? rc : h->ext.reserve((size_t) extCap * 128);
+      if (rc)
+         return rc;
+   }
+
+   Counters *dC = h->counters.as<Counters>();
+   CUDA_TRY(cudaMemsetAsync(dC, 0, sizeof(Counters), st));
+
+   FramePool pool;
+   pool.recs = h->pool.as<FrameRec>();
+   pool.cap = poolCap;
+   pool.count = &dC->poolCount;
+   pool.ext = h->ext.as<u8>();
+   pool.extCap = extCap;
+   pool.extCount = &dC->extCount;
+
+   // ---- lanes + chain, to the fixed point -----------------------------------------------------------------------------
+   const u32 warpsPerBlock = LANE_THREADS / 32;
+   const u32 maxWarps = (u32) h->smCount * 16;
+
+   LaneConfig lc;
+   memset(&lc, 0, sizeof(lc));
+   lc.samples = dSamples;
+   lc.n_samples = n_samples;
+   lc.sigtype = sigtype;
+   lc.flags = h->flags.as<uint8_t>();
+   lc.n_blocks = n_blocks;
+   lc.lanes = h->lanes.as<LaneRec>();
+   lc.queue = h->queue.as<u32>();
+   lc.cursor = &dC->cursor;
+   lc.pool = pool;
+   lc.work = &dC->work;
+
+   ChainConfig cc;
+   cc.lanes = h->lanes.as<LaneRec>();
+   cc.offsets = h->offsets.as<u32>();
+   cc.counts = h->counts.as<u32>();
+   cc.n_streams = n_streams;
+   cc.queue = h->queue.as<u32>();
+   cc.queue_count = &dC->queueCount;
+
+   u32 queueCount = nLanes;
+   u32 maxRounds = h->cfg.max_rounds ? h->cfg.max_rounds : 4096;
+   u32 rounds = 0;
+
+   while (queueCount > 0)
+   {
+      if (rounds >= maxRounds)
+         return fail(NFCB200_ERR_CAPACITY, "carry chain did not converge in %u rounds", maxRounds);
+
+      u32 warps = std::min(maxWarps, (queueCount + 31) / 32);
+      u32 blocks = (warps + warpsPerBlock - 1) / warpsPerBlock;
+      warps = blocks * warpsPerBlock;
+
+      {
+         int rc = h->scratch.reserve((size_t) warps * NFCB200_SCRATCH_FLOATS * 32 * sizeof(float));
+         rc = rc ? rc : h->sbuf.reserve((size_t) warps * 32 * 512);
+         if (rc)
+            return rc;
+      }
+
+      lc.scratch = h->scratch.as<float>();
+      lc.sbuf = h->sbuf.as<uint8_t>();
+      lc.queue_count = queueCount;
+
+      CUDA_TRY(cudaMemsetAsync(&dC->cursor, 0, sizeof(u32), st));
+      lanes_kernel<<<blocks, LANE_THREADS, 0, st>>>(lc, h->P);
+      launches++;
+      CUDA_TRY(cudaGetLastError());
+
+      S.lane_runs += queueCount;
+      rounds++;
+
+      CUDA_TRY(cudaMemsetAsync(&dC->queueCount, 0, sizeof(u32), st));
+      chain_kernel<<<sgrid, 64, 0, st>>>(cc, h->P);
+      launches++;
+      CUDA_TRY(cudaGetLastError());
+
+      CUDA_TRY(cudaMemcpyAsync(&queueCount, &dC->queueCount, sizeof(u32), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+   }
+
+   S.rounds = rounds;
+
+   cudaEventRecord(h->ev[4], st);
+
+   // ---- gather --------------------------------------------------------------------------------------------------------
+   lane_meta_kernel<<<(nLanes + 255) / 256, 256, 0, st>>>(h->lanes.as<LaneRec>(), nLanes, h->meta.as<u32>(), h->streamOf.as<u32>(), &dC->live);
+   launches++;
+   CUDA_TRY(cudaGetLastError());
+
+   Counters hc;
+   CUDA_TRY(cudaMemcpyAsync(&hc, dC, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaStreamSynchronize(st));
+
+   S.lane_samples = hc.work;
+   S.live_lanes = hc.live;
+
+   if (hc.poolCount > poolCap || hc.extCount > extCap)
+      return fail(NFCB200_ERR_CAPACITY, "frame pool exhausted (%u frames, %u extension chunks)", hc.poolCount, hc.extCount);
+
+   std::vector<FrameRec> recs(hc.poolCount);
+   std::vector<unsigned char> ext((size_t) hc.extCount * 128);
+   std::vector<u32> meta(nLanes), streamOf(nLanes);
+
+   if (hc.poolCount)
+      CUDA_TRY(cudaMemcpyAsync(recs.data(), h->pool.ptr, (size_t) hc.poolCount * sizeof(FrameRec), cudaMemcpyDeviceToHost, st));
+   if (hc.extCount)
+      CUDA_TRY(cudaMemcpyAsync(ext.data(), h->ext.ptr, ext.size(), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaMemcpyAsync(meta.data(), h->meta.ptr, (size_t) nLanes * sizeof(u32), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaMemcpyAsync(streamOf.data(), h->streamOf.ptr, (size_t) nLanes * sizeof(u32), cudaMemcpyDeviceToHost, st));
+
+   cudaEventRecord(h->ev[5], st);
+   CUDA_TRY(cudaStreamSynchronize(st));
+
+   // keep only the frames of the final generation of live lanes; lanes are globally ordered by (stream, time)
+   std::vector<u32> keep;
+   keep.reserve(recs.size());
+   for (u32 i = 0; i < recs.size(); i++)
+   {
+      const FrameRec &r = recs[i];
+      if (r.lane >= nLanes)
+         continue;
+      u32 m = meta[r.lane];
+      if ((m & 1) || (m >> 1) != r.gen)
+         continue;
+      keep.push_back(i);
+   }
+
+   std::sort(keep.begin(), keep.end(), [&](u32 a, u32 b) {
+      const FrameRec &x = recs[a], &y = recs[b];
+      if (x.lane != y.lane)
+         return x.lane < y.lane;
+      return x.seq < y.seq;
+   });
+
+   uint64_t nf = keep.size();
+   for (uint64_t i = 0; i < nf && i < cap; i++)
+      emit_frame(h, recs[keep[i]], ext, streamOf[recs[keep[i]].lane], sample_rate, out[i]);
+
+   if (n_out)
+      *n_out = nf;
+
+   // active blocks (statistics; tiny D2H only when the flag array is small, else estimated from the lanes)
+   S.frames = nf;
+   S.kernel_launches = launches;
+   h->lastStreams = n_streams;
+   h->lastBlocks = n_blocks;
+
+   float ms = 0;
+   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+   S.ms_h2d = samples_on_device ? 0.0f : ms;
+   cudaEventElapsedTime(&S.ms_screen, h->ev[1], h->ev[2]);
+   cudaEventElapsedTime(&S.ms_segment, h->ev[2], h->ev[3]);
+   cudaEventElapsedTime(&S.ms_lanes, h->ev[3], h->ev[4]);
+   cudaEventElapsedTime(&S.ms_gather, h->ev[4], h->ev[5]);
+   cudaEventElapsedTime(&S.ms_total, h->ev[0], h->ev[5]);
+
+   if (nf > cap)
+      return fail(NFCB200_ERR_CAPACITY, "%llu frames decoded but room for %llu only", (unsigned long long) nf, (unsigned long long) cap);
+
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// streaming
+// ---------------------------------------------------------------------------------------------------------------------
+int nfcb200_stream_reset(nfcb200_handle *h)
+{
+   if (!h)
+      return fail(NFCB200_ERR_INVALID, "null handle");
+   h->sInit = false;
+   h->sBase = 0;
+   h->sCount = 0;
+   h->sEmitted = 0;
+   return 0;
+}
+
+int nfcb200_stream_push(nfcb200_handle *h, const void *samples, int sigtype, uint64_t n, uint32_t sample_rate, nfcb200_frame *out, uint64_t cap,
+                        uint64_t *n_out)
+{
+   if (!h)
+      return fail(NFCB200_ERR_INVALID, "null handle");
+   if (n_out)
+      *n_out = 0;
+   if (n && (sigtype < SIG_IQ_F32 || sigtype > SIG_IQ_S16))
+      return fail(NFCB200_ERR_INVALID, "unknown signal type %d", sigtype);
+   if (n && !samples)
+      return fail(NFCB200_ERR_INVALID, "null samples");
+   if (n > (1u << 28))
+      return fail(NFCB200_ERR_INVALID, "push of more than 2^28 samples: use nfcb200_decode_batch");
+
+   CUDA_TRY(cudaSetDevice(h->device));
+   cudaStream_t st = h->stream;
+
+   const bool flush = n == 0;
+
+   if (flush && !h->sInit)
+   {
+      // nextFrames({}) on a decoder that never saw a sample: one carrier-off frame at clock -1 (NfcDecoder.cpp:449-463)
+      if (cap < 1)
+         return fail(NFCB200_ERR_CAPACITY, "room for the flush frame needed");
+      memset(&out[0], 0, sizeof(nfcb200_frame));
+      out[0].tech_type = TT_Any;
+      out[0].frame_type = FT_CarrierOff;
+      out[0].frame_phase = PH_Carrier;
+      out[0].sample_start = out[0].sample_end = 0xFFFFFFFFull;
+      if (n_out)
+         *n_out = 1;
+      return 0;
+   }
+
+   // a sample-rate (or format) change re-initialises the decoder (NfcDecoder.cpp:383-388)
+   if (!flush && (!h->sInit || h->sRate != sample_rate || h->sSig != sigtype))
+   {
+      nfcb200_stream_reset(h);
+      int rc = 0;
+      if (h->paramsRate != sample_rate)
+         rc = setup_params(h, sample_rate);
+      if (rc)
+         return rc;
+
+      rc = h->sState.reserve(sizeof(StreamState));
+      rc = rc ? rc : h->sScratch.reserve(NFCB200_SCRATCH_FLOATS * sizeof(float));
+      rc = rc ? rc : h->sSbuf.reserve(512);
+      rc = rc ? rc : h->counters.reserve(sizeof(Counters));
+      if (rc)
+         return rc;
+
+      StreamState init;
+      memset(&init, 0, sizeof(init));
+      carry_init(init.carry, h->P);
+      carry_canon(init.carry);
+      CUDA_TRY(cudaMemcpyAsync(h->sState.ptr, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemsetAsync(h->sScratch.ptr, 0, NFCB200_SCRATCH_FLOATS * sizeof(float), st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+
+      h->sRate = sample_rate;
+      h->sSig = sigtype;
+      h->sInit = true;
+   }
+   else if (h->paramsRate != h->sRate)
+   {
+      int rc = setup_params(h, h->sRate);
+      if (rc)
+         return rc;
+   }
+
+   const u32 bs = sig_bytes(h->sSig);
+
+   // retained host-side tail + new samples -> device buffer covering absolute samples [sBase, sBase + sCount + n)
+   const u32 newCount = h->sCount + (u32) n;
+   {
+      int rc = h->sSamples.reserve((size_t) newCount * bs + 64);
+      if (rc)
+         return rc;
+   }
+   if (h->sCount)
+      CUDA_TRY(cudaMemcpyAsync(h->sSamples.ptr, h->sHostTail.data(), (size_t) h->sCount * bs, cudaMemcpyHostToDevice, st));
+   if (n)
+      CUDA_TRY(cudaMemcpyAsync((unsigned char *) h->sSamples.ptr + (size_t) h->sCount * bs, samples, (size_t) n * bs, cudaMemcpyHostToDevice, st));
+
+   // host copy of the buffer for the next retention step
+   {
+      std::vector<unsigned char> merged((size_t) newCount * bs);
+      if (h->sCount)
+         memcpy(merged.data(), h->sHostTail.data(), (size_t) h->sCount * bs);
+      if (n)
+         memcpy(merged.data() + (size_t) h->sCount * bs, samples, (size_t) n * bs);
+      h->sHostTail.swap(merged);
+   }
+   h->sCount = newCount;
+
+   // the buffer always starts on a block boundary, so buffer block i is absolute block sBase / 256 + i
+   const u32 n_blocks = (newCount + NFCB200_BLOCK - 1) / NFCB200_BLOCK;
+   const u32 tiles = (newCount + SCR_TILE - 1) / SCR_TILE;
+
+   if (newCount)
+   {
+      int rc = h->sFlags.reserve(n_blocks);
+      rc = rc ? rc : h->sBsum.reserve((size_t) n_blocks * sizeof(float));
+      rc = rc ? rc : h->sCounts.reserve(sizeof(u32) * 2);
+      if (rc)
+         return rc;
+
+      ScreenConfig sc;
+      memset(&sc, 0, sizeof(sc));
+      sc.samples = h->sSamples.ptr;
+      sc.n_samples = newCount;
+      sc.n_streams = 1;
+      sc.sigtype = h->sSig;
+      sc.n_blocks = n_blocks;
+      sc.tiles_per_stream = tiles;
+      sc.flags = h->sFlags.as<uint8_t>();
+      sc.bsum = h->sBsum.as<float>();
+      fill_screen_config(h, sc);
+      if ((((uintptr_t) sc.samples) & 15) || (((uint64_t) newCount * bs) & 15))
+         sc.use_tma = 0;
+
+      screen_kernel<<<std::min<u32>(tiles, (u32) h->smCount * 2), SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, tiles);
+      CUDA_TRY(cudaGetLastError());
+
+      SegmentConfig sg;
+      memset(&sg, 0, sizeof(sg));
+      sg.flags = h->sFlags.as<uint8_t>();
+      sg.bsum = h->sBsum.as<float>();
+      sg.n_streams = 1;
+      sg.n_blocks = n_blocks;
+      sg.n_samples = newCount;
+      sg.counts = h->sCounts.as<u32>();
+      sg.low = h->P.lowThr;
+      sg.high = h->P.highThr;
+      sg.meanW = powf(h->P.meanW0, (float) NFCB200_BLOCK);
+      // note: the stream-start margin of blocks_activate applies to buffer block 0; at the true stream start that is
+      // exactly the reference start, later it only makes a few retained blocks active (harmless)
+      segment_count_kernel<<<1, 64, 0, st>>>(sg);
+      CUDA_TRY(cudaGetLastError());
+   }
+
+   // frame pool for this push
+   const u32 poolCap = 1u << 14, extCap = 1u << 12;
+   {
+      int rc = h->pool.reserve((size_t) poolCap * sizeof(FrameRec));
+      rc = rc ? rc : h->ext.reserve((size_t) extCap * 128);
+      if (rc)
+         return rc;
+   }
+   Counters *dC = h->counters.as<Counters>();
+   CUDA_TRY(cudaMemsetAsync(dC, 0, sizeof(Counters), st));
+
+   StreamConfig cfg;
+   memset(&cfg, 0, sizeof(cfg));
+   cfg.samples = h->sSamples.ptr;
+   cfg.base = h->sBase;
+   cfg.count = newCount;
+   cfg.sigtype = h->sSig;
+   cfg.flags = h->sFlags.as<uint8_t>();
+   cfg.flagBase = h->sBase / NFCB200_BLOCK;
+   cfg.flagCount = n_blocks;
+   cfg.limit = h->sBase + newCount;
+   cfg.final = flush ? 1 : 0;
+   cfg.state = h->sState.as<StreamState>();
+   cfg.scratch = h->sScratch.as<float>();
+   cfg.sbuf = h->sSbuf.as<uint8_t>();
+   cfg.pool.recs = h->pool.as<FrameRec>();
+   cfg.pool.cap = poolCap;
+   cfg.pool.count = &dC->poolCount;
+   cfg.pool.ext = h->ext.as<u8>();
+   cfg.pool.extCap = extCap;
+   cfg.pool.extCount = &dC->extCount;
+
+   stream_kernel<<<1, 32, 0, st>>>(cfg, h->P);
+   CUDA_TRY(cudaGetLastError());
+
+   Counters hc;
+   StreamState hs;
+   CUDA_TRY(cudaMemcpyAsync(&hc, dC, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaMemcpyAsync(&hs, h->sState.ptr, sizeof(StreamState), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaStreamSynchronize(st));
+
+   if (hc.poolCount > poolCap || hc.extCount > extCap)
+      return fail(NFCB200_ERR_CAPACITY, "stream frame pool exhausted");
+
+   std::vector<FrameRec> recs(hc.poolCount);
+   std::vector<unsigned char> ext((size_t) hc.extCount * 128);
+   if (hc.poolCount)
+      CUDA_TRY(cudaMemcpy(recs.data(), h->pool.ptr, (size_t) hc.poolCount * sizeof(FrameRec), cudaMemcpyDeviceToHost));
+   if (hc.extCount)
+      CUDA_TRY(cudaMemcpy(ext.data(), h->ext.ptr, ext.size(), cudaMemcpyDeviceToHost));
+
+   std::sort(recs.begin(), recs.end(), [](const FrameRec &a, const FrameRec &b) { return a.seq < b.seq; });
+
+   uint64_t nf = 0;
+   for (const FrameRec &r: recs)
+   {
+      if (nf < cap)
+         emit_frame(h, r, ext, 0, h->sRate, out[nf]);
+      nf++;
+   }
+
+   if (flush)
+   {
+      // nextFrames({}): one carrier frame at the current clock (NfcDecoder.cpp:449-463)
+      u32 clock = hs.pos - 1;
+      bool on = hs.running ? hs.L.c.carrierOn != 0 : hs.carry.carrierOn != 0;
+      if (nf < cap)
+      {
+         nfcb200_frame &o = out[nf];
+         memset(&o, 0, sizeof(o));
+         o.tech_type = TT_Any;
+         o.frame_type = on ? FT_CarrierOn : FT_CarrierOff;
+         o.frame_phase = PH_Carrier;
+         o.sample_start = o.sample_end = clock;
+         o.sample_rate = h->sRate;
+         o.time_start = o.time_end = (double) clock / (double) h->sRate;
+         o.date_time = (double) h->P.streamTime + o.time_start;
+      }
+      nf++;
+   }
+
+   // retention: keep what the parked / running lane can still need.  A running lane only reads forward (its history is in
+   // its rings); a parked lane may cold start HALO samples before a later active block or be resumed at pos.
+   {
+      u32 keepFrom = hs.pos > NFCB200_HALO + 2 * NFCB200_BLOCK ? hs.pos - NFCB200_HALO - 2 * NFCB200_BLOCK : 0;
+      if (hs.running)
+         keepFrom = hs.pos > SCR_HALO + NFCB200_BLOCK ? hs.pos - SCR_HALO - NFCB200_BLOCK : 0; // screening history only
+      keepFrom &= ~(u32) (NFCB200_BLOCK - 1); // block aligned
+      if (keepFrom < h->sBase)
+         keepFrom = h->sBase;
+      u32 drop = keepFrom - h->sBase;
+      if (drop)
+      {
+         h->sHostTail.erase(h->sHostTail.begin(), h->sHostTail.begin() + (size_t) drop * bs);
+         h->sBase += drop;
+         h->sCount -= drop;
+      }
+   }
+
+   if (n_out)
+      *n_out = nf;
+
+   if (nf > cap)
+      return fail(NFCB200_ERR_CAPACITY, "%llu frames decoded but room for %llu only", (unsigned long long) nf, (unsigned long long) cap);
+
+   return 0;
+}
+
+}

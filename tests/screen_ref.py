@@ -118,3 +118,39 @@ def segments(act, n):
         while b < nb and not act[b]:
             b += 1
     return segs
+
+
+def block_flags_device_model(x, sp):
+    """block trigger flags as csrc/nfc_screen.cuh + segment_count_kernel compute them (float64 model):
+    per-sample correlator / edge tests against the per-block envelope min(mean(block), mean(previous block)), then the
+    block-granular level-shift and carrier-band rules"""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.size
+    nb = (n + BLOCK - 1) // BLOCK
+    f = features(x, sp)
+    xp = np.concatenate([x, np.full(nb * BLOCK - n, x[-1])])
+    means = xp.reshape(nb, BLOCK).mean(axis=1)
+    prev = np.concatenate([[x[0]], means[:-1]])
+    envb = np.maximum(np.minimum(means, prev), 0.0)
+    env = np.repeat(envb, BLOCK)[:n]
+    hit = np.zeros(n, dtype=bool)
+    for r in range(3):
+        hit |= np.abs(f["sd"][r]) > sp.kSD[r] * env
+    hit |= np.abs(f["s0v"]) > sp.kV * env
+    hit |= np.abs(f["w"]) > sp.kB * env
+    pad = np.zeros(nb * BLOCK, dtype=bool)
+    pad[:n] = hit
+    trig = pad.reshape(nb, BLOCK).any(axis=1)
+    meanW = sp.meanW0 ** BLOCK
+    avg = 0.0
+    pm = means[0]
+    for b in range(nb):
+        m = means[b]
+        if abs(m - pm) > 0.025 * max(pm, 1e-6):
+            trig[b] = True
+        avg_end = meanW * avg + (1 - meanW) * m
+        lo, hi = min(avg, avg_end, m), max(avg, avg_end, m)
+        if lo < 1.2 * sp.high and hi > 0.8 * sp.low:
+            trig[b] = True
+        pm, avg = m, avg_end
+    return trig

@@ -1,0 +1,87 @@
+"""CPU checks of the host-side logic and of the lane machine compiled for the host (tests/native/host_sim.cpp).
+
+The product runs the lane machine only inside CUDA kernels; the host build exists so that the decoder logic, the
+segment construction and the carry chain are exercised in the GPU-less container against the reference's outputs.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import nfcutil as U
+import screen_ref as S
+from test_golden_oracle import committed_ref
+
+NAMES = U.fixture_names()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_single_lane_equals_reference(name):
+    """one lane over the whole capture == the reference decoder, frame for frame, carrier frames included"""
+    mag, rate, _ = U.fixture_wav(name)
+    frames, _, _ = U.sim_run(mag, rate)
+    assert frames == committed_ref(name)[0]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_segment_speculation_equals_reference(name):
+    """screen -> segments -> independent cold-started lanes -> carry chain fixed point == the sequential reference"""
+    mag, rate, _ = U.fixture_wav(name)
+    trig = S.block_flags(mag, S.ScreenParams(rate))
+    frames, st = U.sim_pipeline(mag, trig, rate)
+    assert frames == committed_ref(name)[0]
+    assert st["rounds"] <= st["lanes"] + 1
+
+
+def test_screen_is_conservative_on_fixtures():
+    """every frame of the reference starts inside an active block of the numpy screen model"""
+    for name in NAMES:
+        mag, rate, _ = U.fixture_wav(name)
+        act = S.active_blocks(S.block_flags(mag, S.ScreenParams(rate)))
+        for f in committed_ref(name)[0]:
+            if f[1] in (0x102,):
+                assert act[min(f[5] // S.BLOCK, act.size - 1)], (name, f)
+
+
+def test_enable_mask():
+    mag, rate, _ = U.fixture_wav("test_POLL_ABF_001")
+    frames, _, _ = U.sim_run(mag, rate, enabled=0x1)
+    assert frames and all(f[0] in (0x100, 0x101) for f in frames)
+    if U.ref_lib() is not None:
+        assert frames == U.ref_decode(mag, rate, enabled=0x1)
+
+
+def test_all_zero_input_quirk():
+    """all-zero input gives exactly two NfcCarrierOff frames at samples 0 and 1"""
+    frames, _, _ = U.sim_run(np.zeros(50000, dtype=np.float32))
+    assert [(f[1], f[5]) for f in frames] == [(0x100, 0), (0x100, 1)]
+
+
+def test_library_exports_every_declared_symbol():
+    """the C-ABI library loads without a GPU and exports every entry point include/nfcb200.h declares"""
+    import nfc_laboratory_b200 as N
+    header = open(os.path.join(U.ROOT, "include", "nfcb200.h")).read()
+    declared = set(re.findall(r"\b(nfcb200_[a-z_]+)\s*\(", header))
+    assert declared == set(N.binding.EXPORTS)
+    lib = C.CDLL(N.library_path())
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
+def test_no_cpu_fallback():
+    """without a CUDA device the product refuses to decode (there is no CPU path)"""
+    import torch
+    import nfc_laboratory_b200 as N
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(N.NfcB200Error) as e:
+        N.NfcDecoder()
+    assert e.value.code == -1
+
+
+def test_struct_layouts_match_header():
+    import nfc_laboratory_b200.binding as B
+    assert C.sizeof(B.CFrame) == 32 + 24 + 24 + 512
+    assert C.sizeof(B.CConfig) == 4 + 4 + 4 + 48 + 4 * 3 + 20
