@@ -1,0 +1,343 @@
+#!/usr/bin/env python3
+"""Benchmark of the NFC IQ demodulation hot path (BASELINE.json metric: IQ MSamples/s decoded).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--streams S] [--samples n] [--workload nfca106]
+
+One step = one pass of the hot path (IQ -> frames) over one batch of synthetic 10 MS/s IQ streams.  At N = 1 the
+default workload is BASELINE.json configs[1]: NFC-A 106 kbps, 1024 streams x 1 s (1e7 samples) of float2 IQ, resident in
+HBM (81.9 GB) when the timed region starts.  For N > 1 (torchrun) every rank decodes its own batch of the same shape
+(weak scaling, streams are independent) and the frames are gathered to rank 0 over NCCL inside the timed region.
+
+Prints ONE JSON line on rank 0 (contract in the task statement): value = whole-job MSamples/s with device-resident
+input; e2e = the same through the C ABI with host buffers (H2D inside the timed region); roofline = the screening
+kernel against the measured HBM copy bandwidth; cpu_baseline = the reference's own CPU decoder (oracle/_ref) timed on
+this box's cores on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "IQ MSamples/s decoded"
+UNIT = "MSamples/s"
+RATE = 10_000_000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=1024)
+    ap.add_argument("--samples", type=int, default=10_000_000)
+    ap.add_argument("--workload", default="nfca106", choices=["nfca106", "nfcb106", "nfca424", "mixed"])
+    ap.add_argument("--seed", type=int, default=2024)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="small batch for smoke runs (64 streams x 2e6)")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference_run(iq_host, threads):
+    """the reference's own CPU decoder (unmodified sources, oracle/_ref) on iq_host [S, n, 2] float32: one NfcDecoder per
+    host thread, IQ -> magnitude (reference scalar formula) included.  Returns (MSamples/s, frames)."""
+    import nfcutil as U
+    lib = U.ref_lib()
+    if lib is None:
+        return None, None
+    S, n = iq_host.shape[0], iq_host.shape[1]
+    frames = C.c_long(0)
+    sec = lib.nfcref_time_batch(None, iq_host.ctypes.data, n, S, RATE, 65536, threads, C.byref(frames))
+    return S * n / sec / 1e6, int(frames.value)
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the reference CPU implementation of the path on this box's host cores (rank 0 only)"""
+    if rank != 0:
+        return
+    import torch
+    from nfc_laboratory_b200 import synth
+    cores = os.cpu_count() or 1
+    S = max(cores, min(4 * cores, 64))
+    n = min(args.samples, 10_000_000)
+    iq = synth.synth_batch(args.workload, S, n, seed=args.seed, device="cpu").numpy()
+    for _ in range(args.warmup):
+        cpu_reference_run(iq[:cores, : n // 8], cores)
+    t0 = time.perf_counter()
+    frames = 0
+    for _ in range(args.steps):
+        v, fr = cpu_reference_run(iq, cores)
+        if v is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libnfcref.so missing"}))
+            return
+        frames += fr
+    dt = time.perf_counter() - t0
+    value = S * n * args.steps / dt / 1e6
+    sample = "%d streams x %d samples of the %s workload per step, %d host threads, IQ->magnitude included" % (S, n, args.workload, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: synthetic 10 MS/s float2 IQ, bounded sample of the GPU arm's batch" % args.workload, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "frames_per_step": frames // max(1, args.steps),
+    }))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.quick:
+        args.streams, args.samples = 64, 2_000_000
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import nfc_laboratory_b200 as N
+    from nfc_laboratory_b200 import synth, dist as ND
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    S, n = args.streams, args.samples
+    free, total_mem = torch.cuda.mem_get_info()
+    need = S * n * 8
+    if need > 0.8 * free:
+        S = max(1, int(0.8 * free // (n * 8)))
+    bytes_per_step = S * n * 8
+
+    # ---- synthetic batch, generated on the device (seed differs per rank: every rank holds different streams) -----------
+    iq = torch.empty((S, n, 2), dtype=torch.float32, device=dev)
+    synth.synth_batch(args.workload, S, n, seed=args.seed + 1000 * rank, device=dev, out=iq)
+    torch.cuda.synchronize()
+
+    dec = N.NfcDecoder(device=local)
+    cap = max(1 << 16, S * (n // 12000 + 64))
+
+    def step_device():
+        buf, nf = dec.decode_batch_ptr(iq.data_ptr(), True, N.SIG_IQ_F32, S, n, RATE, cap=cap, raw=True)
+        return buf, nf
+
+    def gather(buf, nf):
+        if world == 1:
+            return nf
+        flat = ND.pack_frames(ND.frames_as_array(buf, nf), stream_offset=rank * S)
+        allf = ND.gather_frames(flat, dev)
+        return nf if allf is None else len(allf)
+
+    # ---- parity spot check against the oracle (untimed): first streams, first 2e6 samples ---------------------------------
+    parity = None
+    if rank == 0:
+        import nfcutil as U
+        if U.ref_lib() is not None:
+            ns = min(2, S)
+            m = min(n, 2_000_000)
+            sub = iq[:ns, :m].contiguous()
+            got = dec.decode_batch(sub, N.SIG_IQ_F32, RATE)
+            host = sub.cpu().numpy()
+            parity = True
+            for s in range(ns):
+                mag = np.empty(m, dtype=np.float32)
+                U.ref_lib().nfcref_iq_magnitude(np.ascontiguousarray(host[s]).ctypes.data, m, mag.ctypes.data)
+                ref = U.ref_decode(mag, RATE)
+                if [f.key() for f in got if f.stream == s] != ref:
+                    parity = False
+            if not parity:
+                raise SystemExit("parity check against the reference oracle FAILED: refusing to report a number")
+
+    # ---- warm-up, then the timed region -----------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 0)):
+        buf, nf = step_device()
+        gather(buf, nf)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    stats = []
+    frames_total = 0
+    for _ in range(args.steps):
+        buf, nf = step_device()
+        stats.append(dec.stats())
+        frames_total += gather(buf, nf)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+
+    tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dt = float(tmax.item())
+
+    clocks = sampler.summary() if rank == 0 else None
+
+    value = world * S * n * args.steps / dt / 1e6
+
+    # ---- roofline of the dominant dense kernel (K1 screen): algorithmic bytes = one read of the IQ input ------------------
+    ms_screen = statistics.mean(s["ms_screen"] for s in stats)
+    peak, peak_src = measured_peaks()
+    achieved = bytes_per_step / (ms_screen * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "screen_kernel_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                t = json.load(f)
+            # bytes per sample measured by ncu (dram read + write) scaled to this launch
+            traffic = float(t["dram_bytes_per_sample"]) * S * n
+        except Exception:
+            traffic = None
+
+    # ---- e2e: the same decode through the C ABI with HOST buffers (H2D inside the timed region) ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 32 << 30
+        Se = S
+        while Se > 1 and Se * n * 8 > 0.35 * avail:
+            Se //= 2
+        host = torch.empty((Se, n, 2), dtype=torch.float32, pin_memory=True)
+        host.copy_(iq[:Se])
+        torch.cuda.synchronize()
+        dec.decode_batch_ptr(host.data_ptr(), False, N.SIG_IQ_F32, Se, n, RATE, cap=cap, raw=True)  # warm
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        d2h = 0
+        esteps = max(1, min(args.steps, 2))
+        for _ in range(esteps):
+            buf, nf = dec.decode_batch_ptr(host.data_ptr(), False, N.SIG_IQ_F32, Se, n, RATE, cap=cap, raw=True)
+            d2h = nf * 128 + 8
+            gather(buf, nf)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        de = time.perf_counter() - t1
+        tm = torch.tensor([de], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        de = float(tm.item())
+        e2e = {"value": world * Se * n * esteps / de / 1e6, "unit": UNIT, "h2d_bytes_per_step": Se * n * 8, "d2h_bytes_per_step": int(d2h),
+               "streams": Se, "note": "host-pinned float2 IQ -> nfcb200_decode_batch -> frames in host memory"
+                                      + ("" if Se == S else " (sub-batch of %d streams: host memory bound)" % Se)}
+        del host
+
+    # ---- CPU baseline: the reference decoder on this box's cores, bounded sample of the same batch -------------------------
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        Sc = min(S, max(cores, min(2 * cores, 32)))
+        nc = min(n, 10_000_000)
+        sub = iq[:Sc, :nc].cpu().numpy()
+        v, fr = cpu_reference_run(sub, cores)
+        if v is not None:
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": "%d of the batch's streams x %d samples, one NfcDecoder per host thread on %d threads, IQ->magnitude included" % (Sc, nc, cores)}
+
+    if rank == 0:
+        st = stats[-1]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: %d synthetic 10 MS/s x %.1f s float2 IQ streams per GPU (BASELINE.json configs[1] shape), input %.1f GB per GPU, "
+                                   "larger than L2 (no flush needed)" % (args.workload, S, n / RATE, bytes_per_step / 1e9),
+                       "streams_per_gpu": S, "samples_per_stream": n, "sample_rate": RATE, "sharding": "streams, block partition, NCCL frame gather" if world > 1 else "single GPU"},
+            "e2e": e2e,
+            "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "screen_kernel (K1: IQ->magnitude, prefix-sum moving sums, A/F/V correlators, B edge IIR)", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_step, "ms_per_launch": ms_screen},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "phases_ms": {k: statistics.mean(s[k] for s in stats) for k in ("ms_screen", "ms_segment", "ms_lanes", "ms_gather", "ms_total")},
+            "decode": {"frames_per_step": frames_total // max(1, args.steps), "segments": st["segments"], "lanes": st["lanes"], "rounds": st["rounds"],
+                       "lane_runs": st["lane_runs"], "lane_samples_frac": st["lane_samples"] / max(1, st["samples"])},
+            "parity_spot_check": parity,
+        }
+        print(json.dumps(line))
+
+    dec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -76,7 +76,8 @@ typedef struct nfcb200_config
    uint32_t stream_time;          /* setStreamTime                                                                */
    uint32_t use_tma;              /* 1: stage screening tiles with cp.async.bulk (default); 0: plain loads (debug) */
    uint32_t max_rounds;           /* bound on speculation rounds (0 = default)                                    */
-   uint32_t reserved[5];
+   uint32_t segments_per_lane;    /* 0 = choose from the batch size; >= 1 forces the lane grouping                */
+   uint32_t reserved[4];
 } nfcb200_config;
 
 /* counters and device timings of the last nfcb200_decode_batch call */
@@ -85,7 +86,8 @@ typedef struct nfcb200_stats
    uint64_t samples;          /* n_streams * n_samples                          */
    uint64_t blocks;           /* screening blocks                               */
    uint64_t active_blocks;    /* blocks handed to lanes                         */
-   uint64_t lanes;            /* segments                                       */
+   uint64_t segments;         /* segments found by the screen                   */
+   uint64_t lanes;            /* lanes (groups of consecutive segments)         */
    uint64_t live_lanes;       /* segments not swallowed by a predecessor        */
    uint64_t lane_runs;        /* lane executions over all rounds                */
    uint64_t lane_samples;     /* samples stepped by lanes over all rounds       */

@@ -38,13 +38,14 @@ class CConfig(C.Structure):
     _fields_ = [
         ("device", C.c_int), ("enabled", C.c_uint32), ("power_level_threshold", C.c_float),
         ("correlation_threshold", C.c_float * 4), ("modulation_min", C.c_float * 4), ("modulation_max", C.c_float * 4),
-        ("stream_time", C.c_uint32), ("use_tma", C.c_uint32), ("max_rounds", C.c_uint32), ("reserved", C.c_uint32 * 5),
+        ("stream_time", C.c_uint32), ("use_tma", C.c_uint32), ("max_rounds", C.c_uint32), ("segments_per_lane", C.c_uint32),
+        ("reserved", C.c_uint32 * 4),
     ]
 
 
 class CStats(C.Structure):
     _fields_ = [
-        ("samples", C.c_uint64), ("blocks", C.c_uint64), ("active_blocks", C.c_uint64), ("lanes", C.c_uint64),
+        ("samples", C.c_uint64), ("blocks", C.c_uint64), ("active_blocks", C.c_uint64), ("segments", C.c_uint64), ("lanes", C.c_uint64),
         ("live_lanes", C.c_uint64), ("lane_runs", C.c_uint64), ("lane_samples", C.c_uint64), ("rounds", C.c_uint64),
         ("frames", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("ms_h2d", C.c_float), ("ms_screen", C.c_float), ("ms_segment", C.c_float), ("ms_lanes", C.c_float),
@@ -123,12 +124,13 @@ _SIG_DTYPE = {SIG_IQ_F32: (np.float32, 2), SIG_MAG_F32: (np.float32, 1), SIG_MAG
 class NfcDecoder:
     """GPU decoder handle.  Method names follow lab::NfcDecoder; batch decoding is the B200-native addition."""
 
-    def __init__(self, device=0, use_tma=True):
+    def __init__(self, device=0, use_tma=True, segments_per_lane=0):
         self._lib = load_library()
         self._cfg = CConfig()
         self._lib.nfcb200_config_default(C.byref(self._cfg))
         self._cfg.device = device
         self._cfg.use_tma = 1 if use_tma else 0
+        self._cfg.segments_per_lane = segments_per_lane
         self._h = C.c_void_p()
         _check(self._lib, self._lib.nfcb200_create(C.byref(self._cfg), C.byref(self._h)))
         self._rate = 0

@@ -39,7 +39,11 @@ struct LaneRec
    u32 dirty;      // must (re-)run
    u32 dead;       // swallowed by its predecessor
    u32 nframes;    // frames emitted by the last run
-   u32 pad[2];
+   // what the last run observed of its incoming carry (copied from Lane, see nfc_core.h)
+   u32 lcWritten, lcLive, fZeroed, fThrWritten, fThrRead;
+   u32 fInc0[2];
+   float fThrSync[2];
+   u32 pad;
    Carry in;       // carry the last run started from
    Carry out;      // canonical carry the last run retired with
 };
@@ -70,11 +74,13 @@ NFC_HD void blocks_activate(u8 *flags, u32 nb)
    }
 }
 
-// emit the segments of one stream; returns the number of segments (only `cap` are stored)
-NFC_HD u32 blocks_segments(const u8 *flags, u32 nb, u32 nsamples, u32 stream, LaneRec *out, u32 cap)
+// emit the lanes of one stream: every lane owns `group` consecutive segments (it skips the idle stretches between them
+// itself, re-warming from its own exact carry); returns the number of lanes (only `cap` are stored)
+NFC_HD u32 blocks_segments(const u8 *flags, u32 nb, u32 nsamples, u32 stream, LaneRec *out, u32 cap, u32 group = 1)
 {
    u32 count = 0;
    u32 b = 0;
+   u32 inGroup = 0;
 
    while (b < nb)
    {
@@ -94,28 +100,233 @@ NFC_HD u32 blocks_segments(const u8 *flags, u32 nb, u32 nsamples, u32 stream, La
          e++;
       }
 
-      if (count < cap)
+      u32 segEnd = (last + 1) * NFCB200_BLOCK;
+      if (segEnd > nsamples)
+         segEnd = nsamples;
+
+      if (inGroup == 0)
       {
-         LaneRec &l = out[count];
-         l.stream = stream;
-         l.begin = b * NFCB200_BLOCK;
-         l.end = (last + 1) * NFCB200_BLOCK;
-         if (l.end > nsamples)
-            l.end = nsamples;
-         l.first = l.begin > NFCB200_HALO ? l.begin - NFCB200_HALO : 0;
-         l.stop = 0;
-         l.lockedMask = 0;
-         l.gen = 0;
-         l.dirty = 1;
-         l.dead = 0;
-         l.nframes = 0;
+         if (count < cap)
+         {
+            LaneRec &l = out[count];
+            l.stream = stream;
+            l.begin = b * NFCB200_BLOCK;
+            l.end = segEnd;
+            l.first = l.begin > NFCB200_HALO ? l.begin - NFCB200_HALO : 0;
+            l.stop = 0;
+            l.lockedMask = 0;
+            l.gen = 0;
+            l.dirty = 1;
+            l.dead = 0;
+            l.nframes = 0;
+         }
+         count++;
+      }
+      else if (count - 1 < cap)
+      {
+         out[count - 1].end = segEnd;
       }
 
-      count++;
+      if (++inGroup >= group)
+         inGroup = 0;
+
       b = last + 1;
    }
 
    return count;
+}
+
+/*
+ * Drive one lane from R.first until it retires past R.end (or the stream ends).  Inside its own region the lane skips
+ * idle stretches: when it is dormant outside every active block it jumps to HALO samples before the next active block
+ * and re-warms from its own canonical carry -- exactly what a separate lane with a verified carry would do.
+ *   LOAD(pos)    -> magnitude sample at absolute index pos
+ *   ACTIVE(pos)  -> block of pos is active
+ *   ZERO()       -> wipe the correlation rings of the lane's scratch
+ *   kw           -> warp-uniform iteration counter (ring slot labels), advanced by the caller's loop on the device;
+ *                   the host build passes its own counter
+ * One call = one iteration (at most one sample).  Returns false when the lane has retired.
+ */
+template <class MACH, class LOAD, class ACTIVE, class ZERO>
+NFC_HD bool lane_iterate(MACH &M, Lane &L, const Params &P, u32 &pos, u32 end, u32 n, u32 kw, u32 &stepped, LOAD load, ACTIVE active, ZERO zero)
+{
+   if (pos >= n)
+      return false;
+
+   if (!active(pos) && M.dormant())
+   {
+      if (pos >= end)
+         return false;
+
+      // next active block inside the own region (end is the end of an active block, so one exists)
+      u32 b = pos >> 8;
+      while (((b + 1) << 8) < end && !active(b << 8))
+         b++;
+
+      u32 begin = b << 8;
+
+      if (begin > pos + NFCB200_HALO)
+      {
+         Carry carry = L.c;
+         carry_canon(carry);
+         u32 locked = L.lockedMask;
+         u32 target = begin - NFCB200_HALO;
+         zero();
+         lane_begin(L, P, carry, target, NFCB200_HALO);
+         L.lockedMask = locked;
+         L.fe.kbase = kw;
+         pos = target;
+      }
+   }
+
+   M.step(load(pos));
+   pos++;
+   stepped++;
+   return true;
+}
+
+// copy the outcome of a finished run into its record
+NFC_HD void lane_record(LaneRec &R, const Lane &L, u32 stop, u32 gen, u32 nframes)
+{
+   R.stop = stop;
+   R.lockedMask = L.lockedMask;
+   R.out = L.c;
+   carry_canon(R.out);
+   R.gen = gen;
+   R.dirty = 0;
+   R.nframes = nframes;
+   R.lcWritten = L.lcWritten;
+   R.lcLive = L.lcLive;
+   R.fZeroed = L.fZeroed;
+   R.fThrWritten = L.fThrWritten;
+   R.fThrRead = L.fThrRead;
+   R.fInc0[0] = L.fInc0[0];
+   R.fInc0[1] = L.fInc0[1];
+   R.fThrSync[0] = L.fThrSync[0];
+   R.fThrSync[1] = L.fThrSync[1];
+}
+
+// word offsets inside Mod / TechSt used by the relaxed dependency rules
+#define NFCB200_MOD_WORDS (sizeof(Mod) / 4)
+#define NFCB200_W_PULSE 4 /* Mod::searchPulseWidth     */
+#define NFCB200_W_THR 5   /* Mod::searchValueThreshold */
+
+NFC_HD float u32_as_float(u32 v)
+{
+   union
+   {
+      u32 u;
+      float f;
+   } c;
+   c.u = v;
+   return c.f;
+}
+
+/*
+ * Did the last run of L observe anything of carry group g that differs between the carry it assumed (L.in) and the
+ * true carry `cur`?  Plain word equality, except for three values whose only reads are known:
+ *   - frameStatus.lastCommand (word 0 of the protocol groups): read only by the listen-frame classifiers; a run whose
+ *     first classified listen frame followed an assignment in the same run never saw the carried value (lcLive)
+ *   - NFC-F searchPulseWidth: read only by `searchPulseWidth++ < 94` (NfcF.cpp:307, 844); until its first reset the run
+ *     executed fInc0 such tests, all with the same outcome under both carries iff both stay below / above 94 throughout
+ *   - NFC-F searchValueThreshold: until its first assignment it is compared once, against fThrSync (NfcF.cpp:313, 331)
+ */
+NFC_HD bool group_observed_equal(LaneRec &L, Carry &cur, int g)
+{
+   u32 *pa, *pb, wa, wb;
+   carry_group(L.in, g, pa, wa);
+   carry_group(cur, g, pb, wb);
+
+   for (u32 w = 0; w < wa; w++)
+   {
+      if (pa[w] == pb[w])
+         continue;
+
+      if (g >= 4 && g < 8 && w == 0)
+      {
+         if (!((L.lcLive >> (g - 4)) & 1))
+            continue;
+         return false;
+      }
+
+      if (g == 2)
+      {
+         u32 r = w / NFCB200_MOD_WORDS, f = w % NFCB200_MOD_WORDS;
+
+         if (f == NFCB200_W_PULSE)
+         {
+            u32 n = L.fInc0[r];
+            u32 hi = pa[w] > pb[w] ? pa[w] : pb[w];
+            u32 lo = pa[w] > pb[w] ? pb[w] : pa[w];
+            if (n == 0 || hi + n <= 94 || lo >= 94)
+               continue;
+            return false;
+         }
+
+         if (f == NFCB200_W_THR)
+         {
+            if (!((L.fThrRead >> r) & 1))
+               continue;
+            float sv = L.fThrSync[r], a = u32_as_float(pa[w]), t = u32_as_float(pb[w]);
+            if ((sv < a) == (sv < t) && (sv > a) == (sv > t))
+               continue;
+            return false;
+         }
+      }
+
+      return false;
+   }
+
+   return true;
+}
+
+// carry after the last run of L, given the true carry `cur` before it (exact when the run is valid, a prediction else)
+NFC_HD void carry_compose(LaneRec &L, Carry &cur, Carry &next, u32 touched)
+{
+   next = cur;
+
+   for (int g = 0; g < NFCB200_GROUPS; g++)
+   {
+      if (!((touched >> g) & 1))
+         continue;
+
+      u32 *pn, *po, *pi, wn, wo, wi;
+      carry_group(next, g, pn, wn);
+      carry_group(L.out, g, po, wo);
+      carry_group(L.in, g, pi, wi);
+
+      for (u32 w = 0; w < wn; w++)
+      {
+         if (g >= 4 && g < 8 && w == 0)
+         {
+            if ((L.lcWritten >> (g - 4)) & 1)
+               pn[w] = po[w];
+            continue;
+         }
+
+         if (g == 2)
+         {
+            u32 r = w / NFCB200_MOD_WORDS, f = w % NFCB200_MOD_WORDS;
+
+            if (f == NFCB200_W_PULSE)
+            {
+               pn[w] = ((L.fZeroed >> r) & 1) ? po[w] : pn[w] + (po[w] - pi[w]);
+               continue;
+            }
+
+            if (f == NFCB200_W_THR)
+            {
+               if ((L.fThrWritten >> r) & 1)
+                  pn[w] = po[w];
+               continue;
+            }
+         }
+
+         // a word the run left unchanged passes the (corrected) incoming value through, any other keeps the run's value
+         if (po[w] != pi[w])
+            pn[w] = po[w];
+      }
+   }
 }
 
 // speculated carry of a lane that does not start at sample 0: power-on state with the carrier already detected
@@ -181,7 +392,7 @@ NFC_HD u32 chain_walk(LaneRec *lanes, u32 n, const Params &P)
       {
          for (int g = 0; g < NFCB200_GROUPS; g++)
             if ((touched >> g) & 1)
-               if (!group_equal(L.in, cur, g))
+               if (!group_observed_equal(L, cur, g))
                {
                   ok = false;
 #ifdef NFCB200_CHAIN_DEBUG
@@ -200,33 +411,7 @@ NFC_HD u32 chain_walk(LaneRec *lanes, u32 n, const Params &P)
       Carry next = cur;
 
       if (ran)
-      {
-         // per-word prediction: a word the last run left unchanged is assumed to pass the corrected value through, any
-         // other word keeps the value the run produced.  The NFC-F pulse counters (searchPulseWidth) accumulate across
-         // lanes (NfcF.cpp:307 increments, the recover path :260-271 does not clear), so they are predicted by delta.
-         for (int g = 0; g < NFCB200_GROUPS; g++)
-         {
-            if (!((touched >> g) & 1))
-               continue;
-
-            u32 *pn, *po, *pi, wn, wo, wi;
-            carry_group(next, g, pn, wn);
-            carry_group(L.out, g, po, wo);
-            carry_group(L.in, g, pi, wi);
-
-            for (u32 w = 0; w < wn; w++)
-            {
-               if (po[w] == pi[w])
-                  continue;
-
-               const u32 pulseWord = 4; // offset of Mod::searchPulseWidth
-               if (g == 2 && (w % (sizeof(Mod) / 4)) == pulseWord)
-                  pn[w] = pn[w] + (po[w] - pi[w]);
-               else
-                  pn[w] = po[w];
-            }
-         }
-      }
+         carry_compose(L, cur, next, touched);
 
       if (!ok)
       {

@@ -109,7 +109,8 @@ struct Carry
 struct Front
 {
    u32 clk;         // signalClock
-   u32 k;           // local step (ring slot label, warm-up gate)
+   u32 k;           // local step since the (re)start of the lane: warm-up gate, detector gate
+   u32 kbase;       // k + kbase labels the ring slots: equal in all lanes of a warp -> coalesced ring traffic
    u32 pulseFilter;
    u32 closed;      // leaky count of samples with the envelope gate closed (lane retirement only, not in the reference)
    float env, avg, dev, f1;
@@ -131,6 +132,14 @@ struct Lane
    u32 lockRate;  // rate index of the locked modulation
    u32 pulseBits; // NFC-V pulse code: 2 or 8 (decoder->pulse)
    u32 lockedMask; // techs that were locked at least once during this run (bit t), for the carry dependency check
+   // finer dependency tracking of the run on its incoming carry (nfc_chain.h chain_walk):
+   u32 lcWritten;  // bit t: frameStatus.lastCommand of tech t was assigned during this run
+   u32 lcLive;     // bit t: ... and was read by a listen frame before any assignment (the run depends on the carry value)
+   u32 fZeroed;    // bit r: NFC-F rate r searchPulseWidth was reset during this run (restart / reset / listen clear)
+   u32 fThrWritten;// bit r: NFC-F rate r searchValueThreshold was assigned during this run
+   u32 fThrRead;   // bit r: ... and was compared before any assignment, against fThrSync[r]
+   u32 fInc0[2];   // `searchPulseWidth++ < 94` tests executed before the first reset (NfcF.cpp:307)
+   float fThrSync[2];
    u32 warm;      // local steps during which carrier detection is suppressed (cold-started lanes)
    u32 gate;      // local steps during which the detectors are off (reference: signalClock < BUFFER_SIZE)
 };
@@ -200,7 +209,7 @@ struct Machine
    }
 
 #define RG(off, i) rg[((off) + (i)) * STRIDE]
-#define SMP(off, delay) RG(off, (L.fe.k - (delay)) & (NFCB200_RING - 1))
+#define SMP(off, delay) RG(off, (L.fe.k + L.fe.kbase - (delay)) & (NFCB200_RING - 1))
 
    NFC_HD static void zero_mod(Mod &m)
    {
@@ -636,6 +645,9 @@ struct Machine
    // NfcA::Impl::process and the processXXX chain, NfcA.cpp:1480-1973
    NFC_HD void A_process(u32 type, u32 len, u32 &flags, u32 &phase)
    {
+      if (type != FT_Poll && !((L.lcWritten >> TECH_A) & 1))
+         L.lcLive |= 1u << TECH_A; // a listen frame classified with the lastCommand this lane started from
+
       TechSt &t = L.c.t[TECH_A];
       FrameSt &fs = t.fs;
       Proto &ps = t.ps;
@@ -663,6 +675,7 @@ struct Machine
          {
             phase = PH_Selection;
             fs.lastCommand = b0;
+            L.lcWritten |= 1u << TECH_A;
             A_default_protocol(ps);
             fs.frameGuardTime = P.A_fgt;
             fs.frameWaitingTime = P.A_fwtAtqa;
@@ -682,6 +695,7 @@ struct Machine
          phase = PH_Selection;
          flags |= !A_crc_ok(len) ? FL_Crc : 0;
          fs.lastCommand = b0;
+            L.lcWritten |= 1u << TECH_A;
          A_default_protocol(ps);
          t.chained = 0;
          A_reset();
@@ -701,6 +715,7 @@ struct Machine
                   {
                      phase = PH_Selection;
                      fs.lastCommand = b0;
+            L.lcWritten |= 1u << TECH_A;
                      fs.frameGuardTime = P.A_fgt;
                      fs.frameWaitingTime = P.A_fwtAtqa;
                      break;
@@ -719,6 +734,7 @@ struct Machine
                   {
                      int fsdi = (fb(1, len) >> 4) & 0x0F;
                      fs.lastCommand = b0;
+            L.lcWritten |= 1u << TECH_A;
                      ps.maxFrameSize = (u32) nfc_fds_table((int) fsdi);
                      fs.frameWaitingTime = P.fwtActivation;
                      phase = PH_Selection;
@@ -768,6 +784,7 @@ struct Machine
                   if ((b0 & 0xF0) == 0xD0)
                   {
                      fs.lastCommand = b0 & 0xF0;
+            L.lcWritten |= 1u << TECH_A;
                      phase = PH_Selection;
                      flags |= !A_crc_ok(len) ? FL_Crc : 0;
                      break;
@@ -786,6 +803,7 @@ struct Machine
                   if (b0 == 0x60 || b0 == 0x61)
                   {
                      fs.lastCommand = b0;
+            L.lcWritten |= 1u << TECH_A;
                      phase = PH_Application;
                      flags |= !A_crc_ok(len) ? FL_Crc : 0;
                      break;
@@ -804,6 +822,7 @@ struct Machine
                   if ((b0 & 0xE2) == 0x02 && len > 4)
                   {
                      fs.lastCommand = b0 & 0xE2;
+            L.lcWritten |= 1u << TECH_A;
                      phase = PH_Application;
                      flags |= !A_crc_ok(len) ? FL_Crc : 0;
                      break;
@@ -822,6 +841,7 @@ struct Machine
                   if ((b0 & 0xE6) == 0xA2 && len == 3)
                   {
                      fs.lastCommand = b0 & 0xE6;
+            L.lcWritten |= 1u << TECH_A;
                      phase = PH_Application;
                      flags |= !A_crc_ok(len) ? FL_Crc : 0;
                      break;
@@ -840,6 +860,7 @@ struct Machine
                   if ((b0 & 0xC7) == 0xC0 && len == 4)
                   {
                      fs.lastCommand = b0 & 0xC7;
+            L.lcWritten |= 1u << TECH_A;
                      phase = PH_Application;
                      flags |= !A_crc_ok(len) ? FL_Crc : 0;
                      break;
@@ -883,6 +904,7 @@ struct Machine
             fs.guardEnd = fs.frameEnd + fs.frameGuardTime + P.A[L.lockRate].sdd;
          fs.frameType = 0;
          fs.lastCommand = 0;
+         L.lcWritten |= 1u << TECH_A;
       }
 
       fs.frameStart = 0;
@@ -1739,6 +1761,9 @@ struct Machine
    // NfcB::Impl::process, NfcB.cpp:1074-1267
    NFC_HD void B_process(u32 type, u32 len, u32 &flags, u32 &phase)
    {
+      if (type != FT_Poll && !((L.lcWritten >> TECH_B) & 1))
+         L.lcLive |= 1u << TECH_B; // a listen frame classified with the lastCommand this lane started from
+
       TechSt &t = L.c.t[TECH_B];
       FrameSt &fs = t.fs;
       Proto &ps = t.ps;
@@ -1765,6 +1790,7 @@ struct Machine
             if (b0 == 0x05 && len == 5)
             {
                fs.lastCommand = b0;
+            L.lcWritten |= 1u << TECH_B;
                ps.maxFrameSize = 256;
                ps.startUpGuardTime = P.B_sfgt;
                ps.frameGuardTime = P.B_fgt;
@@ -1795,6 +1821,7 @@ struct Machine
             if (b0 == 0x1d && len > 10)
             {
                fs.lastCommand = b0;
+            L.lcWritten |= 1u << TECH_B;
                u32 param1 = fb(5, len), param2 = fb(6, len);
                u32 tr0i = (param1 >> 6) & 0x3;
                u32 fdsi = param2 & 0xf;
@@ -1840,6 +1867,7 @@ struct Machine
             fs.guardEnd = fs.frameEnd + fs.frameGuardTime + P.B[L.lockRate].sdd;
          fs.frameType = 0;
          fs.lastCommand = 0;
+         L.lcWritten |= 1u << TECH_B;
       }
 
       fs.frameStart = 0;
@@ -2164,6 +2192,8 @@ struct Machine
    // NfcF::Impl::resetModulation, NfcF.cpp:1047-1071
    NFC_HD void F_reset()
    {
+      L.fZeroed |= 3;
+      L.fThrWritten |= 3;
       for (int r = 0; r < 2; r++)
       {
          zero_mod(L.c.mF[r]);
@@ -2175,6 +2205,13 @@ struct Machine
       L.c.t[TECH_F].fs.frameStart = 0;
       L.c.t[TECH_F].fs.frameEnd = 0;
       L.lock = LOCK_NONE;
+   }
+
+   NFC_HD void F_note_zeroed(const Mod &m)
+   {
+      u32 bit = (&m == &L.c.mF[1]) ? 2u : 1u;
+      L.fZeroed |= bit;
+      L.fThrWritten |= bit;
    }
 
    NFC_HD static void F_restart_search(Mod &m)
@@ -2226,17 +2263,29 @@ struct Machine
       if (clk != m.searchEndTime)
          return false;
 
+      // dependency bookkeeping (not in the reference): which incoming values did this run actually observe
+      const u32 fr = (&m == &L.c.mF[1]) ? 1u : 0u;
+      if (!((L.fZeroed >> fr) & 1))
+         L.fInc0[fr]++;
+      if (!((L.fThrWritten >> fr) & 1) && !((L.fThrRead >> fr) & 1))
+      {
+         L.fThrRead |= 1u << fr;
+         L.fThrSync[fr] = m.searchSyncValue;
+      }
+
       if (m.searchPulseWidth++ < 94)
       {
          if (m.correlatedPeakTime == 0 || m.searchSyncValue < m.searchValueThreshold)
          {
             F_restart_search(m);
+            F_note_zeroed(m);
             return false;
          }
       }
 
       if (m.searchSyncValue > m.searchValueThreshold)
       {
+         L.fThrWritten |= 1u << fr;
          if (!m.symbolStartTime)
             m.symbolStartTime = m.correlatedPeakTime - b.p2;
 
@@ -2261,6 +2310,7 @@ struct Machine
       if (preambleLength < preambleMinLength || preambleLength > preambleMaxLength)
       {
          F_restart_search(m);
+         F_note_zeroed(m);
          return false;
       }
 
@@ -2351,6 +2401,9 @@ struct Machine
    // NfcF::Impl::process, NfcF.cpp:1076-1210.  d = payload after the sync bytes
    NFC_HD void F_process(u32 type, const u8 *d, u32 len, u32 &flags, u32 &phase)
    {
+      if (type != FT_Poll && !((L.lcWritten >> TECH_F) & 1))
+         L.lcLive |= 1u << TECH_F; // a listen frame classified with the lastCommand this lane started from
+
       TechSt &t = L.c.t[TECH_F];
       FrameSt &fs = t.fs;
       Proto &ps = t.ps;
@@ -2378,6 +2431,7 @@ struct Machine
          if (b1 == 0x00)
          {
             fs.lastCommand = b1;
+            L.lcWritten |= 1u << TECH_F;
             int tsn = (int) (5 < len ? d[5] : 0);
             ps.maxFrameSize = 256;
             ps.startUpGuardTime = P.F_sfgt;
@@ -2423,6 +2477,7 @@ struct Machine
             fs.guardEnd = fs.frameEnd + fs.frameGuardTime + P.F[L.lockRate].sdd;
          fs.frameType = 0;
          fs.lastCommand = 0;
+         L.lcWritten |= 1u << TECH_F;
       }
 
       fs.frameStart = 0;
@@ -2525,7 +2580,10 @@ struct Machine
                clear_bits();
 
                if (L.lock == LOCK_F)
+               {
                   clear_for_listen(L.c.mF[L.lockRate - 1], P.F[L.lockRate].corr, P.F[L.lockRate].p1);
+                  F_note_zeroed(L.c.mF[L.lockRate - 1]);
+               }
 
                return;
             }
@@ -2778,6 +2836,9 @@ struct Machine
    // NfcV::Impl::process, NfcV.cpp:1108-1189
    NFC_HD void V_process(u32 type, u32 len, u32 &flags, u32 &phase)
    {
+      if (type != FT_Poll && !((L.lcWritten >> TECH_V) & 1))
+         L.lcLive |= 1u << TECH_V; // a listen frame classified with the lastCommand this lane started from
+
       TechSt &t = L.c.t[TECH_V];
       FrameSt &fs = t.fs;
       const bool poll = type == FT_Poll;
@@ -2811,6 +2872,7 @@ struct Machine
             fs.guardEnd = fs.frameEnd + fs.frameGuardTime + P.V.sdd;
          fs.frameType = 0;
          fs.lastCommand = 0;
+         L.lcWritten |= 1u << TECH_V;
       }
 
       fs.frameStart = 0;

@@ -131,6 +131,8 @@ struct SegmentConfig
    uint32_t *queue;     // dirty lane indices
    float low, high;     // carrier thresholds (NfcDecoder.cpp:328-329)
    float meanW;         // per-block decay of the carrier average: signalMeanW0 ^ 256
+   uint32_t group;      // segments per lane
+   uint32_t *segTotal;  // total number of segments (statistics / group sizing)
 };
 
 // block-granular part of the screen: level shifts (the reference's gated envelope goes stale, NfcTech.cpp:39-53) and
@@ -171,7 +173,18 @@ __global__ void segment_count_kernel(SegmentConfig c)
 
    blocks_activate(flags, c.n_blocks);
 
-   c.counts[s] = blocks_segments(flags, c.n_blocks, (u32) c.n_samples, s, nullptr, 0);
+   u32 nseg = blocks_segments(flags, c.n_blocks, (u32) c.n_samples, s, nullptr, 0, 1);
+   c.counts[s] = nseg;
+   atomicAdd(c.segTotal, nseg);
+}
+
+// lanes per stream for the chosen group size
+__global__ void segment_group_kernel(SegmentConfig c)
+{
+   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= c.n_streams)
+      return;
+   c.counts[s] = (c.counts[s] + c.group - 1) / c.group;
 }
 
 __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Params dP)
@@ -184,7 +197,7 @@ __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Par
    uint32_t off = c.offsets[s];
    uint32_t n = c.counts[s];
 
-   blocks_segments(flags, c.n_blocks, (u32) c.n_samples, s, c.lanes + off, n);
+   blocks_segments(flags, c.n_blocks, (u32) c.n_samples, s, c.lanes + off, n, c.group);
 
    Carry spec, pon;
    carry_speculate(spec, dP);
@@ -247,48 +260,49 @@ __global__ void __launch_bounds__(LANE_THREADS) lanes_kernel(LaneConfig c, const
       for (uint32_t i = NFCB200_OFF_CA; i < NFCB200_SCRATCH_FLOATS; i++)
          rg[(size_t) i * 32] = 0.0f;
 
-      if (!have)
-         continue;
-
-      const uint32_t li = c.queue[qi];
+      const uint32_t li = have ? c.queue[qi] : 0;
       LaneRec &R = c.lanes[li];
 
       Lane L;
-      lane_begin(L, dP, R.in, R.first, NFCB200_HALO);
-
       DeviceSink sink;
       sink.pool = c.pool;
       sink.lane = li;
-      sink.gen = R.gen + 1;
+      sink.gen = have ? R.gen + 1 : 0;
       sink.seq = 0;
+
+      if (have)
+         lane_begin(L, dP, R.in, R.first, NFCB200_HALO);
 
       Machine<32, DeviceSink> M(dP, L, rg, sb, sink);
 
-      const uint64_t streamBase = (uint64_t) R.stream * c.n_samples;
-      const uint8_t *flags = c.flags + (size_t) R.stream * c.n_blocks;
-      const uint32_t end = R.end;
+      const uint64_t streamBase = have ? (uint64_t) R.stream * c.n_samples : 0;
+      const uint8_t *flags = c.flags + (have ? (size_t) R.stream * c.n_blocks : 0);
+      const uint32_t end = have ? R.end : 0;
       const uint32_t n = (uint32_t) c.n_samples;
 
-      uint32_t pos = R.first;
+      uint32_t pos = have ? R.first : 0;
+      uint32_t stepped = 0;
+      bool running = have;
 
-      for (; pos < n; pos++)
+      auto load = [&](uint32_t p) { return load_sample(c.samples, c.sigtype, streamBase + p); };
+      auto active = [&](uint32_t p) { return (flags[p >> 8] & SCR_ACTIVE) != 0; };
+      auto zero = [&]() {
+         for (uint32_t i = NFCB200_OFF_CA; i < NFCB200_SCRATCH_FLOATS; i++)
+            rg[(size_t) i * 32] = 0.0f;
+      };
+
+      // warp-synchronous stepping: kw is the same in all lanes, so is every ring slot label (k + kbase == kw + 1)
+      for (uint32_t kw = 0; __any_sync(0xffffffffu, running); kw++)
       {
-         // retire at the first sample past the own region that is outside every active block with nothing pending
-         if (pos >= end && !(flags[pos >> 8] & SCR_ACTIVE) && M.dormant())
-            break;
-
-         M.step(load_sample(c.samples, c.sigtype, streamBase + pos));
+         if (running)
+            running = lane_iterate(M, L, dP, pos, end, n, kw, stepped, load, active, zero);
       }
 
-      R.stop = pos;
-      R.lockedMask = L.lockedMask;
-      R.out = L.c;
-      carry_canon(R.out);
-      R.gen = sink.gen;
-      R.dirty = 0;
-      R.nframes = sink.seq;
-
-      atomicAdd(c.work, (unsigned long long) (pos - R.first));
+      if (have)
+      {
+         lane_record(R, L, pos, sink.gen, sink.seq);
+         atomicAdd(c.work, (unsigned long long) stepped);
+      }
    }
 }
 

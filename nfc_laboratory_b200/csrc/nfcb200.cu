@@ -92,6 +92,8 @@ struct Counters
    u32 cursor;
    unsigned long long work;
    unsigned long long live;
+   u32 segTotal;
+   u32 pad;
 };
 
 struct nfcb200_handle
@@ -430,10 +432,34 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
    sg.high = h->P.highThr;
    sg.meanW = powf(h->P.meanW0, (float) NFCB200_BLOCK);
 
+   Counters *dC = h->counters.as<Counters>();
+   CUDA_TRY(cudaMemsetAsync(dC, 0, sizeof(Counters), st));
+   sg.segTotal = &dC->segTotal;
+   sg.group = 1;
+
    const u32 sgrid = (n_streams + 63) / 64;
    segment_count_kernel<<<sgrid, 64, 0, st>>>(sg);
    launches++;
    CUDA_TRY(cudaGetLastError());
+
+   // segments per lane: enough lanes to fill the machine a few times over, no more (every lane pays a warm-up halo and
+   // longer lanes keep more of the carry chain inside one sequential run)
+   u32 segTotal = 0;
+   CUDA_TRY(cudaMemcpyAsync(&segTotal, &dC->segTotal, sizeof(u32), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaStreamSynchronize(st));
+   {
+      const uint64_t residentLanes = (uint64_t) h->smCount * 8 * 32;
+      const uint64_t target = residentLanes * 2;
+      u32 group = h->cfg.segments_per_lane ? h->cfg.segments_per_lane : (u32) std::max<uint64_t>(1, segTotal / std::max<uint64_t>(1, target));
+      sg.group = std::min<u32>(group, 64);
+      if (sg.group > 1)
+      {
+         segment_group_kernel<<<sgrid, 64, 0, st>>>(sg);
+         launches++;
+         CUDA_TRY(cudaGetLastError());
+      }
+   }
+   S.segments = segTotal;
 
    std::vector<u32> counts(n_streams), offsets(n_streams);
    CUDA_TRY(cudaMemcpyAsync(counts.data(), h->counts.ptr, n_streams * sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -478,9 +504,6 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
          return rc;
    }
 
-   Counters *dC = h->counters.as<Counters>();
-   CUDA_TRY(cudaMemsetAsync(dC, 0, sizeof(Counters), st));
-
    FramePool pool;
    pool.recs = h->pool.as<FrameRec>();
    pool.cap = poolCap;
@@ -491,7 +514,7 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
 
    // ---- lanes + chain, to the fixed point -----------------------------------------------------------------------------
    const u32 warpsPerBlock = LANE_THREADS / 32;
-   const u32 maxWarps = (u32) h->smCount * 16;
+   const u32 maxWarps = (u32) h->smCount * 8; // 255 registers per lane thread: 8 resident warps per SM
 
    LaneConfig lc;
    memset(&lc, 0, sizeof(lc));

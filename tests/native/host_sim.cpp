@@ -155,7 +155,7 @@ long hostsim_run(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t ena
  * [4] samples stepped [5] active blocks
  */
 long hostsim_pipeline(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t enabled, uint8_t *flags, uint32_t nb, sim_frame *out, long cap,
-                      uint64_t *stats)
+                      uint64_t *stats, uint32_t group)
 {
    Params P;
    if (!hostsim_params(sampleRate, enabled, &P))
@@ -163,9 +163,12 @@ long hostsim_pipeline(const float *mag, uint64_t n, uint32_t sampleRate, uint32_
 
    blocks_activate(flags, nb);
 
-   uint32_t nseg = blocks_segments(flags, nb, (uint32_t) n, 0, nullptr, 0);
+   if (group < 1)
+      group = 1;
+
+   uint32_t nseg = blocks_segments(flags, nb, (uint32_t) n, 0, nullptr, 0, group);
    std::vector<LaneRec> lanes(nseg);
-   blocks_segments(flags, nb, (uint32_t) n, 0, lanes.data(), nseg);
+   blocks_segments(flags, nb, (uint32_t) n, 0, lanes.data(), nseg, group);
 
    for (uint32_t j = 0; j < nseg; j++)
    {
@@ -208,28 +211,21 @@ long hostsim_pipeline(const float *mag, uint64_t n, uint32_t sampleRate, uint32_
 
          Machine<1, Sink> M(P, L, scratch.data(), sb.data(), sink);
 
-         uint64_t pos = R.first;
+         uint32_t pos = R.first, kw = 0, stepped = 0;
 
-         for (; pos < n; pos++)
-         {
-            if (pos >= R.end && !(flags[pos / NFCB200_BLOCK] & SCR_ACTIVE) && M.dormant())
-               break;
+         auto load = [&](uint32_t p) { return mag[p]; };
+         auto active = [&](uint32_t p) { return (flags[p / NFCB200_BLOCK] & SCR_ACTIVE) != 0; };
+         auto zero = [&]() { std::fill(scratch.begin() + NFCB200_OFF_CA, scratch.end(), 0.0f); };
 
-            M.step(mag[pos]);
-         }
+         while (lane_iterate(M, L, P, pos, R.end, (uint32_t) n, kw, stepped, load, active, zero))
+            kw++;
 
-         R.stop = (uint32_t) pos;
-         R.lockedMask = L.lockedMask;
-         R.out = L.c;
-         carry_canon(R.out);
-         R.gen++;
-         R.dirty = 0;
-         R.nframes = (uint32_t) sink.count;
+         lane_record(R, L, pos, R.gen + 1, (uint32_t) sink.count);
          buf.resize(sink.count);
          frames[j] = buf;
 
          runs++;
-         work += pos - R.first;
+         work += stepped;
       }
 
       if (!any)
