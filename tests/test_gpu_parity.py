@@ -132,3 +132,21 @@ def test_empty_and_invalid_arguments(decoder):
     # a short, ragged stream still decodes (two carrier-off frames)
     frames = decoder.decode_batch(np.zeros((1, 1001), dtype=np.float32), N.SIG_MAG_F32, 10_000_000)
     assert [(f.frame_type, f.sample_start) for f in frames] == [(0x100, 0), (0x100, 1)]
+
+
+def test_reference_regression_tool_links_against_the_b200_decoder(tmp_path):
+    """the reference's UNMODIFIED test-sdr (main.cpp) linked against the lab::NfcDecoder shim + libnfcb200.so prints PASS
+    for all 19 captures (built in the container by nfc_laboratory_b200/shim/Makefile, travels as build/dropin/)"""
+    import lzma
+    import os
+    import shutil
+    import subprocess
+    exe = os.path.join(U.ROOT, "build", "dropin", "test-sdr-b200")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in harness not built (needs the reference tree)")
+    for name in NAMES:
+        with lzma.open(os.path.join(U.GOLDEN, name + ".wav.xz"), "rb") as f, open(tmp_path / (name + ".wav"), "wb") as g:
+            g.write(f.read())
+        shutil.copyfile(os.path.join(U.GOLDEN, name + ".json"), tmp_path / (name + ".json"))
+    out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=900).stdout
+    assert out.count("PASS") == 19 and "FAIL" not in out and "UPDATED" not in out, out
