@@ -153,7 +153,8 @@ NFC_HD bool lane_iterate(MACH &M, Lane &L, const Params &P, u32 &pos, u32 end, u
    if (pos >= n)
       return false;
 
-   if (!active(pos) && M.dormant())
+   // retirement / skip-ahead is only examined every 32 samples (it costs a walk over all detector states)
+   if ((pos & 31) == 0 && !active(pos) && M.dormant())
    {
       if (pos >= end)
          return false;

@@ -351,16 +351,26 @@ struct Machine
       if (++f.cV0 == P.V.p0)
          f.cV0 = 0;
 
-      float diff = fabsf(x - f.env) / f.env; // NfcTech.cpp:39 (inf / NaN at env == 0 compare false, as there)
+      // NfcTech.cpp:39-42: signalDiff = abs(x - env) / env; gate = signalDiff < 0.05f.  The IEEE division is only
+      // executed when the quotient is within 2 % of the threshold; outside that band the comparison is decided by
+      // a / env <= 0.049 (1 + ulp) < 0.05 resp. >= 0.051 (1 - ulp) > 0.05 (inf / NaN at env == 0 compare false, as there)
+      const float adiff = fabsf(x - f.env);
+      bool open;
+      if (adiff < 0.049f * f.env)
+         open = true;
+      else if (adiff > 0.051f * f.env)
+         open = false;
+      else
+         open = (adiff / f.env) < 0.05f;
 
       // retirement bookkeeping: while the gate stays closed the envelope is stale and thresholds derived from it
       // differ from what the screening pass assumes, so such a lane is never dormant
-      if (diff < 0.05f)
+      if (open)
          f.closed = f.closed ? f.closed - 1 : 0;
       else if (f.closed < 4096)
          f.closed++;
 
-      if (diff < 0.05f || f.pulseFilter > (u32) (P.etu * 10))
+      if (open || f.pulseFilter > (u32) (P.etu * 10))
       {
          f.pulseFilter = 0;
          f.env = f.env * P.envW0 + x * P.envW1;
@@ -377,12 +387,12 @@ struct Machine
       f.dev = f.dev * P.mdevW0 + fabsf(w) * P.mdevW1; // :65
       f.avg = f.avg * P.meanW0 + x * P.meanW1;        // :68
 
-      float clamped = x < 0.0f ? 0.0f : (f.env < x ? f.env : x); // std::clamp(x, 0, env), :74
-
+      // the ring keeps the envelope instead of modulateDepth (:74): the depth is only read on detector triggers and
+      // in listen mode, and depth_at() evaluates the reference expression from the stored x and envelope when it is
       SMP(NFCB200_OFF_X, 0) = x;
       SMP(NFCB200_OFF_W, 0) = w;
       SMP(NFCB200_OFF_D, 0) = f.dev;
-      SMP(NFCB200_OFF_M, 0) = (f.env - clamped) / f.env;
+      SMP(NFCB200_OFF_M, 0) = f.env;
 
       float rect = fabsf(w); // :77-92
 
@@ -398,6 +408,15 @@ struct Machine
       {
          f.edgePeak = 0;
       }
+   }
+
+   // sample[..].modulateDepth of `delay` samples ago: (env - clamp(x, 0, env)) / env, NfcTech.cpp:74
+   NFC_HD float depth_at(u32 delay)
+   {
+      float x = SMP(NFCB200_OFF_X, delay);
+      float env = SMP(NFCB200_OFF_M, delay);
+      float clamped = x < 0.0f ? 0.0f : (env < x ? env : x);
+      return (env - clamped) / env;
    }
 
    // NfcDecoder::Impl::detectCarrier, NfcDecoder.cpp:472-523
@@ -482,6 +501,13 @@ struct Machine
          // :253-255
          float s0 = m.filterIntegrate - RG(b.corr, fp2);
          float s1 = RG(b.corr, fp2) - RG(b.corr, fp3);
+
+         // idle fast path (not in the reference): with no search state pending, the rest of this iteration only acts when
+         // correlatedSD < -minimumCorrelationValue (:291).  (s0 - s1) / p2 < -T needs s0 - s1 < -T p2 (1 - ulp): anything
+         // above half of that cannot trigger, so the IEEE division and the state tests are skipped
+         if ((m.symbolStartTime | m.searchStartTime | m.searchEndTime | m.correlatedPeakTime) == 0 && (s0 - s1) > -0.5f * minimumCorrelationValue * (float) b.p2)
+            continue;
+
          float sd = (s0 - s1) / (float) b.p2;
 
          // :268-279 recover status from previous partial search
@@ -503,7 +529,7 @@ struct Machine
 
          if (!m.symbolStartTime) // :285-306
          {
-            float deep = SMP(NFCB200_OFF_M, b.sdd + b.p8);
+            float deep = depth_at(b.sdd + b.p8);
 
             if (sd < -minimumCorrelationValue)
             {
@@ -1122,7 +1148,7 @@ struct Machine
       float s0, s1;
       A_listen_ask_integrate(b, m, s0, s1);
 
-      float deep = SMP(NFCB200_OFF_M, 0); // futureIndex
+      float deep = depth_at(0); // futureIndex
 
       if (clk < fs.guardEnd)
          return A_Invalid;
@@ -1287,7 +1313,7 @@ struct Machine
 
       float data = SMP(NFCB200_OFF_W, b.sdd);
       float delay1 = SMP(NFCB200_OFF_W, b.sdd + b.p1);
-      float deep = SMP(NFCB200_OFF_M, 0);
+      float deep = depth_at(0);
 
       float v = data * delay1 * 10;
       SMP(NFCB200_OFF_I, b.sdd) = v;
@@ -1617,7 +1643,13 @@ struct Machine
          Mod &m = L.c.mB[rate];
 
          float edge = SMP(NFCB200_OFF_W, b.sdd);
-         float deep = SMP(NFCB200_OFF_M, b.sdd);
+
+         // idle fast path (not in the reference): with no SOF search pending the iteration only acts on a falling edge
+         // below -envelope * minimumModulationDeep (:283); the per-sample rewrite of searchValueThreshold (:280) is dead
+         if ((m.symbolStartTime | m.searchEndTime | m.detectorPeakTime) == 0 && !(edge < -(env * P.thr[TECH_B].modMin)))
+            continue;
+
+         float deep = depth_at(b.sdd);
 
          // :265-274
          if (deep > P.thr[TECH_B].modMax || (m.detectorPeakTime && clk > m.detectorPeakTime + b.p1))
@@ -1882,7 +1914,7 @@ struct Machine
       const u32 clk = L.fe.clk;
 
       float edge = SMP(NFCB200_OFF_W, b.sdd);
-      float deep = SMP(NFCB200_OFF_M, b.sdd);
+      float deep = depth_at(b.sdd);
 
       if (clk > m.searchStartTime && clk < m.searchEndTime)
       {
@@ -1998,7 +2030,7 @@ struct Machine
 
       float data = SMP(NFCB200_OFF_W, b.sdd);
       float delay1 = SMP(NFCB200_OFF_W, b.sdd + b.p1);
-      float deep = SMP(NFCB200_OFF_M, 0);
+      float deep = depth_at(0);
 
       float v = data * delay1 * 10;
       SMP(NFCB200_OFF_I, b.sdd) = v;
@@ -2344,10 +2376,25 @@ struct Machine
          const RateParams &b = P.F[rate];
          Mod &m = L.c.mF[rate - 1];
 
-         float deep = SMP(NFCB200_OFF_M, b.sdd);
-
          m.filterIntegrate += SMP(NFCB200_OFF_X, b.sdd);
          m.filterIntegrate -= SMP(NFCB200_OFF_X, b.sdd + b.p2);
+
+         // idle fast path (not in the reference): with no search window pending (the residual pulse counter / threshold
+         // only matter at a window end) the iteration only acts when correlatedSD > minimumCorrelationValue (:277); the
+         // "recover" block (:260-271) rewrites zeros.  |s0 - s1| below half of T p2 cannot reach the threshold.
+         if ((m.symbolStartTime | m.symbolEndTime | m.searchStartTime | m.searchEndTime | m.searchSyncTime | m.correlatedPeakTime) == 0)
+         {
+            u32 fq2, fq3;
+            const u32 fq1 = L.fe.cF[rate - 1];
+            corr_points(fq1, b.p1, b.p2, fq2, fq3);
+            RG(b.corr, fq1) = m.filterIntegrate;
+            float q0 = m.filterIntegrate - RG(b.corr, fq2);
+            float q1 = RG(b.corr, fq2) - RG(b.corr, fq3);
+            if (fabsf(q0 - q1) < 0.5f * minimumCorrelationValue * (float) b.p2)
+               continue;
+         }
+
+         float deep = depth_at(b.sdd);
 
          float s0, s1, sd;
          F_correlate(b, m, L.fe.cF[rate - 1], s0, s1, sd);
@@ -2729,7 +2776,12 @@ struct Machine
 
       float signalData;
       float s0 = V_pulse_corr(m, signalData);
-      float deep = SMP(NFCB200_OFF_M, b.sdd + b.p8);
+
+      // idle fast path (not in the reference): nothing pending and the pulse correlation far below the trigger (:305)
+      if ((m.searchStartTime | m.searchEndTime | m.correlatedPeakTime) == 0 && !(s0 > minimumCorrelationValue))
+         return false;
+
+      float deep = depth_at(b.sdd + b.p8);
 
       if (m.correlatedPeakTime && clk > m.correlatedPeakTime + b.p0) // :287-298
       {
@@ -3041,7 +3093,7 @@ struct Machine
       const u32 clk = L.fe.clk;
 
       float s0 = V_listen_corr(m);
-      float deep = SMP(NFCB200_OFF_M, 0);
+      float deep = depth_at(0);
 
       if (clk < fs.guardEnd)
          return V_Invalid;
@@ -3506,7 +3558,10 @@ NFC_HD void lane_begin(Lane &L, const Params &P, const Carry &carry, u32 first, 
    L.fe.cV0 = P.V.c0 ? P.V.c0 - 1 : P.V.p0 - 1;
 
    L.warm = first ? warm : 0;
-   L.gate = NFCB200_RING;
+   // detectors stay off for the first 1024 samples of a stream like in the reference (signalClock < BUFFER_SIZE); a
+   // cold-started lane keeps them off until 512 samples before its own region: enough to refill the correlation rings
+   // (longest period 378), while the front end alone converges over the rest of the halo
+   L.gate = (first && warm > NFCB200_RING + 512) ? warm - 512 : NFCB200_RING;
 }
 
 }
