@@ -3270,6 +3270,74 @@ struct Machine
    }
 
    // ------------------------------------------------------------------------------------------------------------------
+   // software prefetch of the ring taps the detectors will read NFCB200_PF steps from now.  Every tap is at least 12
+   // samples old when it is read (smallest delay: period2 of the 424k detectors), so the slots already hold their final
+   // value; a lone lane (warp) is otherwise bound by one L2 round trip per dependent tap.  Device only, no semantics.
+   // ------------------------------------------------------------------------------------------------------------------
+#define NFCB200_PF 8
+
+   NFC_HD void prefetch_slot(u32 off, u32 index)
+   {
+#if defined(__CUDA_ARCH__)
+      const float *ptr = &RG(off, index);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+#else
+      (void) off;
+      (void) index;
+#endif
+   }
+
+   NFC_HD void prefetch_sample(u32 off, u32 delay)
+   {
+      if (delay > NFCB200_PF)
+         prefetch_slot(off, (L.fe.k + L.fe.kbase + NFCB200_PF - delay) & (NFCB200_RING - 1));
+   }
+
+   NFC_HD void prefetch_corr(const RateParams &b, u32 c, u32 period, u32 shift)
+   {
+      // slot (c + PF + shift) mod period, the one correlated against PF steps from now
+      u32 slot = c + NFCB200_PF + shift;
+      while (slot >= period)
+         slot -= period;
+      prefetch_slot(b.corr, slot);
+   }
+
+   NFC_HD void prefetch_taps()
+   {
+#if defined(__CUDA_ARCH__)
+      if (L.lock == LOCK_NONE)
+      {
+         for (int r = 0; r < 3; r++)
+         {
+            prefetch_sample(NFCB200_OFF_X, P.A[r].sdd);
+            prefetch_sample(NFCB200_OFF_X, P.A[r].sdd + P.A[r].p2);
+            prefetch_corr(P.A[r], L.fe.cA[r], P.A[r].p1, P.A[r].p2);
+         }
+         prefetch_sample(NFCB200_OFF_W, P.B[1].sdd);
+         for (int r = 1; r <= 2; r++)
+         {
+            prefetch_sample(NFCB200_OFF_X, P.F[r].p2);
+            prefetch_corr(P.F[r], L.fe.cF[r - 1], P.F[r].p1, P.F[r].p2);
+         }
+         prefetch_sample(NFCB200_OFF_X, P.V.sdd);
+         prefetch_sample(NFCB200_OFF_X, P.V.sdd + P.V.p2);
+         prefetch_corr(P.V, L.fe.cV1, P.V.p1, P.V.p2);
+      }
+      else
+      {
+         const RateParams &b = locked_rate();
+         prefetch_sample(NFCB200_OFF_X, b.sdd);
+         prefetch_sample(NFCB200_OFF_X, b.sdd + b.p2);
+         prefetch_sample(NFCB200_OFF_W, b.sdd);
+         prefetch_sample(NFCB200_OFF_W, b.sdd + b.p1);
+         prefetch_sample(NFCB200_OFF_I, b.sdd + b.p2);
+         prefetch_sample(NFCB200_OFF_I, b.sdd + b.p4);
+         prefetch_sample(NFCB200_OFF_I, b.sdd + b.p1);
+      }
+#endif
+   }
+
+   // ------------------------------------------------------------------------------------------------------------------
    // dispatch: NfcDecoder::Impl::nextFrames inner loops, NfcDecoder.cpp:393-442, one sample per call
    // ------------------------------------------------------------------------------------------------------------------
    NFC_HD void step(float x)

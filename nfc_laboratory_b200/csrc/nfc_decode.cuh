@@ -234,7 +234,7 @@ struct LaneConfig
 
 #define LANE_THREADS 128
 
-__global__ void __launch_bounds__(LANE_THREADS) lanes_kernel(LaneConfig c, const __grid_constant__ Params dP)
+__global__ void __launch_bounds__(LANE_THREADS, 4) lanes_kernel(LaneConfig c, const __grid_constant__ Params dP)
 {
    const uint32_t lane = threadIdx.x & 31;
    const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -448,7 +448,7 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
    CUDA_TRY(cudaMemcpyAsync(&segTotal, &dC->segTotal, sizeof(u32), cudaMemcpyDeviceToHost, st));
    CUDA_TRY(cudaStreamSynchronize(st));
    {
-      const uint64_t residentLanes = (uint64_t) h->smCount * 8 * 32;
+      const uint64_t residentLanes = (uint64_t) h->smCount * 16 * 32;
       const uint64_t target = residentLanes * 2;
       u32 group = h->cfg.segments_per_lane ? h->cfg.segments_per_lane : (u32) std::max<uint64_t>(1, segTotal / std::max<uint64_t>(1, target));
       sg.group = std::min<u32>(group, 64);
@@ -514,7 +514,7 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
 
    // ---- lanes + chain, to the fixed point -----------------------------------------------------------------------------
    const u32 warpsPerBlock = LANE_THREADS / 32;
-   const u32 maxWarps = (u32) h->smCount * 8; // 255 registers per lane thread: 8 resident warps per SM
+   const u32 maxWarps = (u32) h->smCount * 16; // 128 registers per lane thread: 16 resident warps per SM
 
    LaneConfig lc;
    memset(&lc, 0, sizeof(lc));
