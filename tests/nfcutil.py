@@ -119,6 +119,35 @@ def ref_decode(mag, rate=10000000, chunk=65536, enabled=0xF, cap=65536):
                         bytes(f.data[:f.length])) for f in buf[:n]]
 
 
+_port = None
+
+
+def port_lib():
+    """the plain-C restatement oracle/nfc_oracle.c (built by oracle/Makefile `port`)"""
+    global _port
+    if _port is None:
+        src = os.path.join(ORACLE, "nfc_oracle.c")
+        if not os.path.exists(PORT_SO) or os.path.getmtime(PORT_SO) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", ORACLE, "port"])
+        lib = C.CDLL(PORT_SO)
+        lib.nfcoracle_decode.restype = C.c_long
+        lib.nfcoracle_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint, C.POINTER(RefFrame), C.c_long]
+        lib.nfcoracle_iq_magnitude.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        _port = lib
+    return _port
+
+
+def port_decode(mag, rate=10000000, enabled=0xF, cap=65536):
+    """all frames of the plain-C restatement (same record layout as the compiled reference wrapper)"""
+    lib = port_lib()
+    mag = np.ascontiguousarray(mag, dtype=np.float32)
+    buf = (RefFrame * cap)()
+    n = lib.nfcoracle_decode(mag.ctypes.data, mag.size, rate, enabled, buf, cap)
+    assert 0 <= n <= cap
+    return [frame_tuple(f.tech_type, f.frame_type, f.frame_flags, f.frame_phase, f.frame_rate, f.sample_start, f.sample_end,
+                        bytes(f.data[:f.length])) for f in buf[:n]]
+
+
 def build_hostsim():
     src = os.path.join(ROOT, "tests", "native", "host_sim.cpp")
     deps = [src] + [os.path.join(ROOT, "nfc_laboratory_b200", "csrc", h) for h in ("nfc_core.h", "nfc_params.h", "nfc_chain.h")]

@@ -43,3 +43,26 @@ def test_reference_chunk_invariance():
     a = U.ref_decode(mag, rate, chunk=65536)
     assert a == U.ref_decode(mag, rate, chunk=1000)
     assert a == U.ref_decode(mag, rate, chunk=7)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_c_restatement_matches_golden_and_reference(name):
+    """oracle/nfc_oracle.c (plain-C restatement) is pinned against the reference's golden vectors and, frame for frame
+    (carrier frames included), against the recorded output of the compiled reference"""
+    mag, rate, _ = U.fixture_wav(name)
+    frames = U.port_decode(mag, rate)
+    assert [f for f in frames if f[1] in (0x102, 0x103)] == U.fixture_golden(name)
+    assert frames == committed_ref(name)[0]
+
+
+def test_c_restatement_iq_magnitude_and_masks():
+    import numpy as np
+    rng = np.random.default_rng(5)
+    iq = rng.normal(0, 0.3, (1000, 2)).astype(np.float32)
+    mag = np.empty(1000, dtype=np.float32)
+    U.port_lib().nfcoracle_iq_magnitude(iq.ctypes.data, 1000, mag.ctypes.data)
+    assert np.array_equal(mag, np.sqrt((iq[:, 0] * iq[:, 0] + iq[:, 1] * iq[:, 1]).astype(np.float32)).astype(np.float32))
+    x, rate, _ = U.fixture_wav("test_POLL_ABF_001")
+    only_b = U.port_decode(x, rate, enabled=0x2)
+    assert only_b and all(f[0] in (0x100, 0x102) for f in only_b)
+    assert U.port_decode(np.zeros(5000, np.float32)) == [(0x100, 0x100, 0, 0x101, 0, 0, 0, b""), (0x100, 0x100, 0, 0x101, 0, 1, 1, b"")]
