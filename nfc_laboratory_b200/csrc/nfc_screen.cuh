@@ -61,6 +61,32 @@ __device__ __forceinline__ float sample_from_raw(const void *tile, int sigtype, 
    }
 }
 
+// magnitude for SCREENING only: approximate reciprocal square root (2 ulp) instead of the IEEE sqrt sequence; the exact
+// decoder lanes recompute the magnitude with sample_from_raw / load_sample
+__device__ __forceinline__ float screen_mag(const void *tile, int sigtype, uint32_t i)
+{
+   switch (sigtype)
+   {
+      case SIG_IQ_F32:
+      {
+         float2 v = ((const float2 *) tile)[i];
+         float p = v.x * v.x + v.y * v.y;
+         return p * rsqrtf(fmaxf(p, 1e-30f));
+      }
+      case SIG_MAG_F32:
+         return ((const float *) tile)[i];
+      case SIG_MAG_S16:
+         return (float) ((const short *) tile)[i] * (1.0f / 32768.0f);
+      default:
+      {
+         short2 v = ((const short2 *) tile)[i];
+         float I = (float) v.x * (1.0f / 32768.0f), Q = (float) v.y * (1.0f / 32768.0f);
+         float p = I * I + Q * Q;
+         return p * rsqrtf(fmaxf(p, 1e-30f));
+      }
+   }
+}
+
 #define SCR_THREADS 256
 #define SCR_PER_THREAD 17
 #define SCR_SPAN (SCR_THREADS * SCR_PER_THREAD)   /* 4352 samples staged per tile            */
@@ -81,9 +107,9 @@ struct ScreenConfig
    // correlator geometry (samples): A/F rates 106, 212, 424 and NFC-V
    uint32_t p1[3], p2[3];
    uint32_t vp1, vp2;
-   float kSD[3];           // |SD_r| > kSD[r] * envelope  (0.9 x min detector threshold of the techs using rate r)
-   float kV;               // |S0_V| > kV * envelope
-   float kB;               // |w|    > kB * envelope
+   float thrA[3];          // |C[t] - C[t-q]| > thrA[r] * envelope flags rate r (see the derivation in the kernel)
+   float thrV;             // same for the NFC-V pulse correlator
+   float kB;               // |w| > kB * envelope flags an NFC-B edge
    int use_tma;
 };
 
@@ -133,7 +159,6 @@ struct ScreenSmem
    // raw staging, two stages, 16-byte aligned; sized for the widest format (float2)
    unsigned char raw[2][SCR_SPAN * 8];
    float P[SCR_SPAN + 1];   // mean-removed inclusive prefix sum, P[0] = 0
-   float W[SCR_SPAN];       // DC-removed edge signal
    float warpAgg[8];        // cross-warp scan scratch (prefix)
    float warpA[8], warpB[8];// cross-warp scan scratch (affine)
    float lastX[8];          // last magnitude of every warp (x[n-1] of the next warp's first sample)
@@ -246,27 +271,37 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
       __syncthreads();
 
       // ---- per-thread chunk: magnitude, local prefix, local IIR ------------------------------------------------------
-      const int64_t validLo = g.lo - g.base; // slots below hold no data (stream start): replicate the first sample
-      const int64_t validHi = g.hi - g.base; // slots at / above hold no data (stream end): replicate the last sample
+      const int validLo = (int) (g.lo - g.base); // slots below hold no data (stream start): replicate the first sample
+      const int validHi = (int) (g.hi - g.base); // slots at / above hold no data (stream end): replicate the last sample
       const void *raw = s.raw[stage];
+      const bool whole = validLo == 0 && validHi == SCR_SPAN;
 
       float xs[SCR_PER_THREAD];
       const int first = tid * SCR_PER_THREAD;
 
       // reference level for the mean-removed prefix: the first valid sample of the staged span
-      const float mu = sample_from_raw(raw, c.sigtype, (uint32_t) validLo);
+      const float mu = screen_mag(raw, c.sigtype, (uint32_t) validLo);
 
-#pragma unroll
-      for (int i = 0; i < SCR_PER_THREAD; i++)
+      if (whole)
       {
-         int64_t slot = first + i;
-         int64_t sslot = slot < validLo ? validLo : (slot >= validHi ? validHi - 1 : slot);
-         xs[i] = sample_from_raw(raw, c.sigtype, (uint32_t) sslot);
+#pragma unroll
+         for (int i = 0; i < SCR_PER_THREAD; i++)
+            xs[i] = screen_mag(raw, c.sigtype, (uint32_t) (first + i));
+      }
+      else
+      {
+#pragma unroll
+         for (int i = 0; i < SCR_PER_THREAD; i++)
+         {
+            int slot = first + i;
+            slot = slot < validLo ? validLo : (slot >= validHi ? validHi - 1 : slot);
+            xs[i] = screen_mag(raw, c.sigtype, (uint32_t) slot);
+         }
       }
 
-      // additive scan of (x - mu)
-      float run = 0;
+      // additive scan of (x - mu): thread-local inclusive prefix, then warp shuffle scan of the chunk totals
       float loc[SCR_PER_THREAD];
+      float run = 0;
 #pragma unroll
       for (int i = 0; i < SCR_PER_THREAD; i++)
       {
@@ -283,19 +318,20 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
             incl += o;
       }
       if (lane == 31)
+      {
          s.warpAgg[warp] = incl;
-
-      // affine scan of w[n] = 0.9 w[n-1] + (x[n] - x[n-1]); thread-local with zero carry first
-      float prevx = __shfl_up_sync(0xffffffffu, xs[SCR_PER_THREAD - 1], 1);
-      float A = 1.0f, B = 0.0f;
-      float wl[SCR_PER_THREAD];
-      // x[n-1] for the first sample of the chunk comes from the previous thread (or the previous warp via smem)
-      if (lane == 31)
          s.lastX[warp] = xs[SCR_PER_THREAD - 1];
+      }
+
+      // affine scan of w[n] = 0.9 w[n-1] + (x[n] - x[n-1]); thread-local with zero carry first.  x[n-1] of the first
+      // sample of a chunk comes from the previous thread (previous warp through shared memory)
+      float prevx = __shfl_up_sync(0xffffffffu, xs[SCR_PER_THREAD - 1], 1);
       __syncthreads();
       if (lane == 0)
          prevx = warp ? s.lastX[warp - 1] : xs[0];
 
+      float wl[SCR_PER_THREAD];
+      float A = 1.0f, B;
       {
          float w = 0, px = prevx;
 #pragma unroll
@@ -309,7 +345,7 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
          B = w;
       }
 
-      // warp-level inclusive scan of the affine maps (A, B): compose(earlier, later) = (Ae*Al, Al*Be + Bl)
+      // warp-level inclusive scan of the affine maps (A, B): compose(earlier, later) = (Ae * Al, Al * Be + Bl)
       float sA = A, sB = B;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1)
@@ -337,28 +373,22 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
          wCarryWarp = s.warpA[v] * wCarryWarp + s.warpB[v];
       }
 
-      float exclPref = prefBase + (incl - run);
-      // carry into this thread = state after the previous thread
-      float eA = __shfl_up_sync(0xffffffffu, sA, 1);
-      float eB = __shfl_up_sync(0xffffffffu, sB, 1);
-      float wCarry = lane ? (eA * wCarryWarp + eB) : wCarryWarp;
+      const float exclPref = prefBase + (incl - run);
+      const float eA = __shfl_up_sync(0xffffffffu, sA, 1);
+      const float eB = __shfl_up_sync(0xffffffffu, sB, 1);
+      const float wCarry = lane ? (eA * wCarryWarp + eB) : wCarryWarp; // IIR state entering this thread's chunk
 
-      {
-         float a = 1.0f;
 #pragma unroll
-         for (int i = 0; i < SCR_PER_THREAD; i++)
-         {
-            a *= 0.9f;
-            s.P[first + i + 1] = exclPref + loc[i];
-            s.W[first + i] = wl[i] + a * wCarry;
-         }
-      }
+      for (int i = 0; i < SCR_PER_THREAD; i++)
+         s.P[first + i + 1] = exclPref + loc[i];
       if (tid == 0)
          s.P[0] = 0;
 
+      if (tid < SCR_TILE_BLOCKS)
+         s.blockHit[tid] = 0;
+
       __syncthreads();
 
-      // ---- correlators and trigger tests on the tile's own samples ---------------------------------------------------
       // envelope reference per block: min(mean of this block, mean of the previous block) -- in idle both equal the
       // reference's envelope EMA to within the noise; during a pause the smaller one only makes the test stricter
       if (tid < SCR_TILE_BLOCKS)
@@ -372,41 +402,49 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
 
       __syncthreads();
 
+      // ---- correlators and trigger tests on the tile's own samples ---------------------------------------------------
+      // With C[t] = P[t] - P[t - p2] (half-symbol moving sum) the reference's correlator is
+      //    S0 - S1 = (C[t] - C[t - q]) - (C[t - q] - C[t - 1]) = 2 (C[t] - C[t - q]) - (x[t] - x[t - p2])
+      // so  |S0 - S1| <= 2 |C[t] - C[t - q]| + xmax, and a detector needing |S0 - S1| / p2 > T env cannot trigger while
+      //    |C[t] - C[t - q]| <= thr env,   thr = min(0.9 T p2, T p2 - 1.25) / 2          (xmax <= 1.25 env)
+      // One difference of two moving sums (3 shared-memory taps) per rate and sample.  The long windows change slowly
+      // (by at most 2 xmax per sample), so the 106k correlator is evaluated on every 2nd sample and the NFC-V one on
+      // every 4th with the threshold lowered by the possible change in between.
+      if (first + SCR_PER_THREAD > SCR_HALO)
       {
-         // own samples are slots [SCR_HALO, SCR_SPAN); thread t tests those of its 17 slots that are own samples.
-         // thresholds are pre-multiplied by the window length so the tests need no division:
-         //    |S0 - S1| / p2 > k * env   <=>   |C[t] - 2 C[t-q] + C[t-1]| > (k * p2) * env
-         const float tA0 = c.kSD[0] * (float) c.p2[0], tA1 = c.kSD[1] * (float) c.p2[1], tA2 = c.kSD[2] * (float) c.p2[2];
-         const float tV = c.kV * (float) c.vp2;
          const int p20 = (int) c.p2[0], q0 = (int) (c.p1[0] - c.p2[0]);
          const int p21 = (int) c.p2[1], q1 = (int) (c.p1[1] - c.p2[1]);
          const int p22 = (int) c.p2[2], q2 = (int) (c.p1[2] - c.p2[2]);
          const int pv = (int) c.vp2, qv = (int) (c.vp1 - c.vp2);
+         const float t0 = c.thrA[0], t1 = c.thrA[1], t2 = c.thrA[2], tv = c.thrV, tb = c.kB;
+         const int ownEnd = (int) ((int64_t) c.n_samples - g.base); // first slot past the stream
+
+         float a = 1.0f;
 
 #pragma unroll
          for (int i = 0; i < SCR_PER_THREAD; i++)
          {
-            int slot = first + i;
-            if (slot < SCR_HALO)
-               continue;
-            if (g.base + slot >= (int64_t) c.n_samples)
+            a *= 0.9f;
+
+            const int slot = first + i;
+            if (slot < SCR_HALO || slot >= ownEnd)
                continue;
 
             const int blk = (slot - SCR_HALO) >> 8;
             const float env = s.envB[blk];
             const int t = slot + 1; // P index of the inclusive prefix at this sample
-            const float Pt = s.P[t], Pt1 = s.P[t - 1];
+            const float Pt = exclPref + loc[i];
 
-            float d0 = (Pt - s.P[t - p20]) - 2.0f * (s.P[t - q0] - s.P[t - q0 - p20]) + (Pt1 - s.P[t - 1 - p20]);
-            float d1 = (Pt - s.P[t - p21]) - 2.0f * (s.P[t - q1] - s.P[t - q1 - p21]) + (Pt1 - s.P[t - 1 - p21]);
-            float d2 = (Pt - s.P[t - p22]) - 2.0f * (s.P[t - q2] - s.P[t - q2 - p22]) + (Pt1 - s.P[t - 1 - p22]);
-            float dv = (s.P[t - qv] - s.P[t - qv - pv]) - (Pt - s.P[t - pv]);
+            bool hit = fabsf(wl[i] + a * wCarry) > tb * env;
 
-            bool hit = fabsf(d0) > tA0 * env;
-            hit |= fabsf(d1) > tA1 * env;
-            hit |= fabsf(d2) > tA2 * env;
-            hit |= fabsf(dv) > tV * env;
-            hit |= fabsf(s.W[slot]) > c.kB * env;
+            hit |= fabsf((Pt - s.P[t - p21]) - (s.P[t - q1] - s.P[t - q1 - p21])) > t1 * env;
+            hit |= fabsf((Pt - s.P[t - p22]) - (s.P[t - q2] - s.P[t - q2 - p22])) > t2 * env;
+
+            if ((slot & 1) == 0)
+               hit |= fabsf((Pt - s.P[t - p20]) - (s.P[t - q0] - s.P[t - q0 - p20])) > t0 * env;
+
+            if ((slot & 3) == 0)
+               hit |= fabsf((Pt - s.P[t - pv]) - (s.P[t - qv] - s.P[t - qv - pv])) > tv * env;
 
             if (hit)
                s.blockHit[blk] = 1; // benign race: all writers store 1

@@ -161,12 +161,24 @@ static void fill_screen_config(const nfcb200_handle *h, ScreenConfig &sc)
    }
    sc.vp1 = P.V.p1;
    sc.vp2 = P.V.p2;
-   // rate 106 is only used by NFC-A; 212 / 424 by NFC-A and NFC-F; disabled techs still screen (conservative)
-   float cA = P.thr[TECH_A].corr, cF = P.thr[TECH_F].corr;
-   sc.kSD[0] = margin * cA;
-   sc.kSD[1] = margin * std::min(cA, cF);
-   sc.kSD[2] = margin * std::min(cA, cF);
-   sc.kV = margin * P.thr[TECH_V].corr;
+   // rate 106 is only used by NFC-A; 212 / 424 by NFC-A and NFC-F; disabled techs still screen (conservative).
+   // thr = min(0.9 T p2, T p2 - 1.25) / 2, lowered by the change the decimated evaluation can miss (nfc_screen.cuh)
+   const float cA = P.thr[TECH_A].corr, cF = P.thr[TECH_F].corr, cV = P.thr[TECH_V].corr;
+   const float T[3] = {cA, std::min(cA, cF), std::min(cA, cF)};
+   for (int r = 0; r < 3; r++)
+   {
+      float p2 = (float) P.A[r].p2;
+      sc.thrA[r] = std::min(margin * T[r] * p2, T[r] * p2 - 1.25f) * 0.5f;
+   }
+   sc.thrA[0] -= 2.5f;       // evaluated on every 2nd sample: |C[t] - C[t-q]| moves by at most 2 xmax = 2.5 env per sample
+   {
+      float p2 = (float) P.V.p2;
+      // NFC-V: S0 = (C[t-q] - C[t]) / p2 > T env (NfcV.cpp:274, 305); evaluated on every 4th sample
+      sc.thrV = std::min(margin * cV * p2, cV * p2 - 1.25f) - 3 * 2.5f;
+   }
+   for (int r = 0; r < 3; r++)
+      sc.thrA[r] = std::max(sc.thrA[r], 0.25f);
+   sc.thrV = std::max(sc.thrV, 0.25f);
    sc.kB = margin * P.thr[TECH_B].modMin;
    sc.use_tma = h->cfg.use_tma ? 1 : 0;
 }

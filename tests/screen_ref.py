@@ -26,6 +26,10 @@ class ScreenParams:
         self.v = (int(round(stu * 256)), int(round(stu * 128)))
         self.kSD = [margin * corrA, margin * min(corrA, corrF), margin * min(corrA, corrF)]
         self.kV = margin * corrV
+        # device rule (csrc/nfc_screen.cuh): |C[t] - C[t-q]| > thr * env, thr = min(0.9 T p2, T p2 - 1.25) / 2
+        T = [corrA, min(corrA, corrF), min(corrA, corrF)]
+        self.thrA = [max(0.25, min(margin * T[r] * self.periods[r][1], T[r] * self.periods[r][1] - 1.25) * 0.5 - (2.5 if r == 0 else 0.0)) for r in range(3)]
+        self.thrV = max(0.25, min(margin * corrV * self.v[1], corrV * self.v[1] - 1.25) - 7.5)
         self.kB = margin * modMinB
         self.low = power / 1.25
         self.high = power * 1.25
@@ -57,13 +61,15 @@ def features(x, sp):
         return P[hi] - P[lo]
 
     sd = []
+    dc = []
     for (p1, p2) in sp.periods:
         q = p1 - p2
         c0, cq, c1 = win(0, p2), win(q, p2), win(1, p2)
         sd.append((c0 - 2 * cq + c1) / p2)
+        dc.append(c0 - cq)
     p1, p2 = sp.v
     s0v = (win(p1 - p2, p2) - win(0, p2)) / p2
-    return dict(x=x, envf=envf, envs=envs, avg=avg, w=w, sd=sd, s0v=s0v)
+    return dict(x=x, envf=envf, envs=envs, avg=avg, w=w, sd=sd, s0v=s0v, dc=dc, dcv=win(0, p2) - win(p1 - p2, p2))
 
 
 def sample_flags(x, sp):
@@ -134,9 +140,11 @@ def block_flags_device_model(x, sp):
     envb = np.maximum(np.minimum(means, prev), 0.0)
     env = np.repeat(envb, BLOCK)[:n]
     hit = np.zeros(n, dtype=bool)
-    for r in range(3):
-        hit |= np.abs(f["sd"][r]) > sp.kSD[r] * env
-    hit |= np.abs(f["s0v"]) > sp.kV * env
+    idx = np.arange(n)
+    hit |= (np.abs(f["dc"][0]) > sp.thrA[0] * env) & ((idx & 1) == 0)
+    hit |= np.abs(f["dc"][1]) > sp.thrA[1] * env
+    hit |= np.abs(f["dc"][2]) > sp.thrA[2] * env
+    hit |= (np.abs(f["dcv"]) > sp.thrV * env) & ((idx & 3) == 0)
     hit |= np.abs(f["w"]) > sp.kB * env
     pad = np.zeros(nb * BLOCK, dtype=bool)
     pad[:n] = hit
