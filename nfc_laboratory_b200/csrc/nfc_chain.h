@@ -25,7 +25,7 @@ namespace nfcb200 {
 #define NFCB200_START_BLOCKS 8  /* the stream start is always a segment                           */
 
 // screening flag bits (one byte per block)
-enum { SCR_TRIGGER = 1, SCR_ACTIVE = 2 };
+enum { SCR_TRIGGER = 1, SCR_ACTIVE = 2, SCR_START = 4 };
 
 struct LaneRec
 {

@@ -135,47 +135,89 @@ struct SegmentConfig
    uint32_t *segTotal;  // total number of segments (statistics / group sizing)
 };
 
-// block-granular part of the screen: level shifts (the reference's gated envelope goes stale, NfcTech.cpp:39-53) and
-// the carrier on/off band (NfcDecoder.cpp:472-523), then dilation; returns the number of segments of the stream
-__global__ void segment_count_kernel(SegmentConfig c)
+// ---- block-granular part of the screen, parallel over all blocks ---------------------------------------------------------
+// level shifts (the reference's gated envelope goes stale, NfcTech.cpp:39-53) and the carrier on/off band
+// (NfcDecoder.cpp:472-523).  The carrier average entering a block is the exponentially weighted sum of the previous block
+// means; with meanW = signalMeanW0^256 = 0.277 eight terms reproduce the recursion to 3e-5, far inside the band margins.
+__global__ void segment_flags_kernel(SegmentConfig c)
 {
-   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-   if (s >= c.n_streams)
+   const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+   const uint64_t total = (uint64_t) c.n_streams * c.n_blocks;
+   if (i >= total)
       return;
 
-   uint8_t *flags = c.flags + (size_t) s * c.n_blocks;
-   const float *bsum = c.bsum + (size_t) s * c.n_blocks;
+   const uint32_t b = (uint32_t) (i % c.n_blocks);
+   const float *bsum = c.bsum + (i - b);
+   const float inv = 1.0f / NFCB200_BLOCK;
 
-   float prev = bsum[0] * (1.0f / NFCB200_BLOCK);
-   float avg = 0;
+   const float mean = bsum[b] * inv;
+   const float prev = (b ? bsum[b - 1] : bsum[0]) * inv;
 
-   for (uint32_t b = 0; b < c.n_blocks; b++)
+   uint8_t f = c.flags[i] & SCR_TRIGGER;
+
+   if (fabsf(mean - prev) > 0.025f * fmaxf(prev, 1e-6f))
+      f |= SCR_TRIGGER;
+
+   float avg = 0, wgt = 1.0f - c.meanW;
+   for (uint32_t j = 1; j <= 8 && j <= b; j++)
    {
-      float mean = bsum[b] * (1.0f / NFCB200_BLOCK);
-      uint8_t f = flags[b];
-
-      // sustained level change between consecutive blocks: the envelope gate of the reference closes (5 %)
-      if (fabsf(mean - prev) > 0.025f * fmaxf(prev, 1e-6f))
-         f |= SCR_TRIGGER;
-
-      // carrier average over the block: avg' ~ meanW * avg + (1 - meanW) * mean; a threshold crossing needs the
-      // average inside the hysteresis band at some point of the block
-      float avgEnd = c.meanW * avg + (1.0f - c.meanW) * mean;
-      float lo = fminf(fminf(avg, avgEnd), mean);
-      float hi = fmaxf(fmaxf(avg, avgEnd), mean);
-      if (lo < 1.2f * c.high && hi > 0.8f * c.low)
-         f |= SCR_TRIGGER;
-
-      flags[b] = f;
-      prev = mean;
-      avg = avgEnd;
+      avg += wgt * (bsum[b - j] * inv);
+      wgt *= c.meanW;
    }
 
-   blocks_activate(flags, c.n_blocks);
+   const float avgEnd = c.meanW * avg + (1.0f - c.meanW) * mean;
+   const float lo = fminf(fminf(avg, avgEnd), mean);
+   const float hi = fmaxf(fmaxf(avg, avgEnd), mean);
+   if (lo < 1.2f * c.high && hi > 0.8f * c.low)
+      f |= SCR_TRIGGER;
 
-   u32 nseg = blocks_segments(flags, c.n_blocks, (u32) c.n_samples, s, nullptr, 0, 1);
-   c.counts[s] = nseg;
-   atomicAdd(c.segTotal, nseg);
+   c.flags[i] = f;
+}
+
+// dilation: a block is active when a trigger lies within [b - POST, b + PRE], or at the stream start (nfc_chain.h)
+__global__ void segment_activate_kernel(SegmentConfig c)
+{
+   const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+   const uint64_t total = (uint64_t) c.n_streams * c.n_blocks;
+   if (i >= total)
+      return;
+
+   const uint32_t b = (uint32_t) (i % c.n_blocks);
+   const uint8_t *flags = c.flags + (i - b);
+
+   bool act = b < NFCB200_START_BLOCKS;
+   const uint32_t lo = b > NFCB200_POST_BLOCKS ? b - NFCB200_POST_BLOCKS : 0;
+   const uint32_t hi = b + NFCB200_PRE_BLOCKS < c.n_blocks ? b + NFCB200_PRE_BLOCKS : c.n_blocks - 1;
+   for (uint32_t k = lo; k <= hi && !act; k++)
+      act = (flags[k] & SCR_TRIGGER) != 0;
+
+   if (act)
+      c.flags[i] |= SCR_ACTIVE; // other threads only read the trigger bit of this byte
+}
+
+// a segment starts at an active block with no active block among the previous GAP - 1 blocks (blocks_segments())
+__global__ void segment_starts_kernel(SegmentConfig c)
+{
+   const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+   const uint64_t total = (uint64_t) c.n_streams * c.n_blocks;
+   if (i >= total)
+      return;
+
+   const uint32_t b = (uint32_t) (i % c.n_blocks);
+   const uint32_t s = (uint32_t) (i / c.n_blocks);
+   const uint8_t *flags = c.flags + (i - b);
+
+   if (!(flags[b] & SCR_ACTIVE))
+      return;
+
+   const uint32_t lo = b >= NFCB200_GAP_BLOCKS - 1 ? b - (NFCB200_GAP_BLOCKS - 1) : 0;
+   for (uint32_t k = lo; k < b; k++)
+      if (flags[k] & SCR_ACTIVE)
+         return;
+
+   c.flags[i] |= SCR_START;
+   atomicAdd(&c.counts[s], 1u);
+   atomicAdd(c.segTotal, 1u);
 }
 
 // lanes per stream for the chosen group size
@@ -187,28 +229,93 @@ __global__ void segment_group_kernel(SegmentConfig c)
    c.counts[s] = (c.counts[s] + c.group - 1) / c.group;
 }
 
+// one warp per stream: walk the start / active bits 32 blocks at a time and emit the lane records in time order
 __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Params dP)
 {
-   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+   const uint32_t s = blockIdx.x;
+   const uint32_t lane = threadIdx.x;
    if (s >= c.n_streams)
       return;
 
    const uint8_t *flags = c.flags + (size_t) s * c.n_blocks;
-   uint32_t off = c.offsets[s];
-   uint32_t n = c.counts[s];
+   const uint32_t off = c.offsets[s];
+   const uint32_t nLanes = c.counts[s];
+   const uint32_t nsamples = (uint32_t) c.n_samples;
 
-   blocks_segments(flags, c.n_blocks, (u32) c.n_samples, s, c.lanes + off, n, c.group);
+   uint32_t laneIdx = 0;     // next lane record of this stream
+   uint32_t inGroup = 0;     // segments already in the open lane
+   uint32_t lastActive = 0;  // highest active block seen so far
+   bool open = false;
 
-   Carry spec, pon;
-   carry_speculate(spec, dP);
-   carry_init(pon, dP);
-   carry_canon(pon);
-
-   for (uint32_t j = 0; j < n; j++)
+   for (uint32_t base = 0; base < c.n_blocks; base += 32)
    {
-      LaneRec &L = c.lanes[off + j];
-      L.in = L.first == 0 ? pon : spec;
-      c.queue[off + j] = off + j; // first round: every lane runs
+      const uint32_t b = base + lane;
+      const uint8_t f = b < c.n_blocks ? flags[b] : 0;
+      uint32_t startMask = __ballot_sync(0xffffffffu, (f & SCR_START) != 0);
+      const uint32_t actMask = __ballot_sync(0xffffffffu, (f & SCR_ACTIVE) != 0);
+
+      if (lane == 0)
+      {
+         while (startMask)
+         {
+            const uint32_t p = __ffs(startMask) - 1;
+            startMask &= startMask - 1;
+
+            const uint32_t lower = actMask & ((1u << p) - 1u);
+            if (lower)
+               lastActive = base + 31 - __clz(lower);
+
+            if (open)
+            {
+               uint32_t e = (lastActive + 1) * NFCB200_BLOCK;
+               c.lanes[off + laneIdx - 1].end = e > nsamples ? nsamples : e;
+            }
+
+            if (inGroup == 0 && laneIdx < nLanes)
+            {
+               LaneRec &l = c.lanes[off + laneIdx];
+               l.stream = s;
+               l.begin = (base + p) * NFCB200_BLOCK;
+               l.end = l.begin;
+               l.first = l.begin > NFCB200_HALO ? l.begin - NFCB200_HALO : 0;
+               l.stop = 0;
+               l.lockedMask = 0;
+               l.gen = 0;
+               l.dirty = 1;
+               l.dead = 0;
+               l.nframes = 0;
+               laneIdx++;
+            }
+
+            open = true;
+            if (++inGroup >= c.group)
+               inGroup = 0;
+         }
+
+         if (actMask)
+            lastActive = base + 31 - __clz(actMask);
+      }
+   }
+
+   if (lane == 0)
+   {
+      if (open && laneIdx > 0)
+      {
+         uint32_t e = (lastActive + 1) * NFCB200_BLOCK;
+         c.lanes[off + laneIdx - 1].end = e > nsamples ? nsamples : e;
+      }
+
+      Carry spec, pon;
+      carry_speculate(spec, dP);
+      carry_init(pon, dP);
+      carry_canon(pon);
+
+      for (uint32_t j = 0; j < nLanes; j++)
+      {
+         LaneRec &L = c.lanes[off + j];
+         L.in = L.first == 0 ? pon : spec;
+         c.queue[off + j] = off + j; // first round: every lane runs
+      }
    }
 }
 

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/nfcb200.h"
@@ -104,6 +105,8 @@ struct nfcb200_handle
    int device = 0;
    int smCount = 148;
    cudaStream_t stream = nullptr;
+   cudaStream_t copyStream = nullptr;
+   cudaEvent_t copied[2] = {};
    cudaEvent_t ev[8] = {};
 
    DevBuf samples, flags, bsum, counts, offsets, lanes, queue, scratch, sbuf, pool, ext, meta, streamOf, counters;
@@ -278,6 +281,11 @@ void nfcb200_destroy(nfcb200_handle *h)
    for (auto &ev: h->ev)
       if (ev)
          cudaEventDestroy(ev);
+   for (auto &ev: h->copied)
+      if (ev)
+         cudaEventDestroy(ev);
+   if (h->copyStream)
+      cudaStreamDestroy(h->copyStream);
    if (h->stream)
       cudaStreamDestroy(h->stream);
    delete h;
@@ -342,31 +350,11 @@ static void emit_frame(const nfcb200_handle *h, const FrameRec &r, const std::ve
       memcpy(o.data + 80, ext.data() + (size_t) r.ext * 128, len - 80);
 }
 
-int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_device, int sigtype, uint32_t n_streams, uint64_t n_samples,
-                         uint32_t sample_rate, nfcb200_frame *out, uint64_t cap, uint64_t *n_out)
+// decode one device-resident batch [n_streams][n_samples]; frames are written to out[outOffset ...) (bounded by cap) with
+// stream indices offset by streamBase; statistics are ACCUMULATED into h->stats
+static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype, uint32_t n_streams, uint64_t n_samples, uint32_t sample_rate,
+                           uint32_t streamBase, nfcb200_frame *out, uint64_t cap, uint64_t outOffset, uint64_t *produced)
 {
-   if (!h)
-      return fail(NFCB200_ERR_INVALID, "null handle");
-   if (n_out)
-      *n_out = 0;
-   if (sigtype < SIG_IQ_F32 || sigtype > SIG_IQ_S16)
-      return fail(NFCB200_ERR_INVALID, "unknown signal type %d", sigtype);
-   if (!samples || n_streams == 0 || n_samples == 0)
-      return fail(NFCB200_ERR_INVALID, "empty batch");
-   if (n_samples >= 0xFFFF0000ull)
-      return fail(NFCB200_ERR_UNSUPPORTED, "streams of 2^32 samples or more exceed the 32-bit sample clock of the frame format (NfcTech.h:338)");
-   if (cap && !out)
-      return fail(NFCB200_ERR_INVALID, "null frame buffer");
-
-   CUDA_TRY(cudaSetDevice(h->device));
-
-   if (h->paramsRate != sample_rate)
-   {
-      int rc = setup_params(h, sample_rate);
-      if (rc)
-         return rc;
-   }
-
    cudaStream_t st = h->stream;
    const u32 bs = sig_bytes(sigtype);
    const uint64_t total = (uint64_t) n_streams * n_samples;
@@ -375,22 +363,10 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
    uint64_t launches = 0;
 
    nfcb200_stats &S = h->stats;
-   memset(&S, 0, sizeof(S));
-   S.samples = total;
-   S.blocks = (uint64_t) n_streams * n_blocks;
-
-   cudaEventRecord(h->ev[0], st);
-
-   // ---- input ---------------------------------------------------------------------------------------------------------
-   const void *dSamples = samples;
-   if (!samples_on_device)
-   {
-      int rc = h->samples.reserve(total * bs + 64);
-      if (rc)
-         return rc;
-      CUDA_TRY(cudaMemcpyAsync(h->samples.ptr, samples, total * bs, cudaMemcpyHostToDevice, st));
-      dSamples = h->samples.ptr;
-   }
+   nfcb200_stats prev = S;
+   S.lane_runs = 0;
+   S.samples += total;
+   S.blocks += (uint64_t) n_streams * n_blocks;
 
    cudaEventRecord(h->ev[1], st);
 
@@ -450,9 +426,16 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
    sg.group = 1;
 
    const u32 sgrid = (n_streams + 63) / 64;
-   segment_count_kernel<<<sgrid, 64, 0, st>>>(sg);
-   launches++;
-   CUDA_TRY(cudaGetLastError());
+   {
+      CUDA_TRY(cudaMemsetAsync(h->counts.ptr, 0, (size_t) n_streams * sizeof(u32), st));
+      const uint64_t nb = (uint64_t) n_streams * n_blocks;
+      const u32 bgrid = (u32) ((nb + 255) / 256);
+      segment_flags_kernel<<<bgrid, 256, 0, st>>>(sg);
+      segment_activate_kernel<<<bgrid, 256, 0, st>>>(sg);
+      segment_starts_kernel<<<bgrid, 256, 0, st>>>(sg);
+      launches += 3;
+      CUDA_TRY(cudaGetLastError());
+   }
 
    // segments per lane: enough lanes to fill the machine a few times over, no more (every lane pays a warm-up halo and
    // longer lanes keep more of the carry chain inside one sequential run)
@@ -486,7 +469,7 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
    if (nLanes64 >= 0x7FFFFFFFull)
       return fail(NFCB200_ERR_CAPACITY, "too many segments (%llu)", (unsigned long long) nLanes64);
    const u32 nLanes = (u32) nLanes64;
-   S.lanes = nLanes;
+   S.lanes = nLanes;   // this chunk; accumulated with the previous chunks at the end
 
    {
       int rc = h->lanes.reserve((size_t) nLanes * sizeof(LaneRec));
@@ -500,7 +483,7 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
    CUDA_TRY(cudaMemcpyAsync(h->offsets.ptr, offsets.data(), n_streams * sizeof(u32), cudaMemcpyHostToDevice, st));
    sg.lanes = h->lanes.as<LaneRec>();
    sg.queue = h->queue.as<u32>();
-   segment_fill_kernel<<<sgrid, 64, 0, st>>>(sg, h->P);
+   segment_fill_kernel<<<n_streams, 32, 0, st>>>(sg, h->P);
    launches++;
    CUDA_TRY(cudaGetLastError());
 
@@ -623,9 +606,23 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
    cudaEventRecord(h->ev[5], st);
    CUDA_TRY(cudaStreamSynchronize(st));
 
-   // keep only the frames of the final generation of live lanes; lanes are globally ordered by (stream, time)
-   std::vector<u32> keep;
-   keep.reserve(recs.size());
+   // keep only the frames of the final generation of live lanes.  Lanes are globally ordered by (stream, time) and a
+   // run numbers its frames 0 .. nframes-1, so the output position of a frame is a counting sort: offset[lane] + seq
+   std::vector<u32> laneCount(nLanes + 1, 0);
+   for (const FrameRec &r: recs)
+   {
+      if (r.lane >= nLanes)
+         continue;
+      u32 m = meta[r.lane];
+      if ((m & 1) || (m >> 1) != r.gen)
+         continue;
+      laneCount[r.lane + 1]++;
+   }
+   for (u32 i = 0; i < nLanes; i++)
+      laneCount[i + 1] += laneCount[i];
+
+   const uint64_t nf = laneCount[nLanes];
+   std::vector<u32> order(nf);
    for (u32 i = 0; i < recs.size(); i++)
    {
       const FrameRec &r = recs[i];
@@ -634,37 +631,175 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
       u32 m = meta[r.lane];
       if ((m & 1) || (m >> 1) != r.gen)
          continue;
-      keep.push_back(i);
+      uint64_t pos = (uint64_t) laneCount[r.lane] + r.seq;
+      if (pos < (uint64_t) laneCount[r.lane + 1])
+         order[pos] = i;
    }
 
-   std::sort(keep.begin(), keep.end(), [&](u32 a, u32 b) {
-      const FrameRec &x = recs[a], &y = recs[b];
-      if (x.lane != y.lane)
-         return x.lane < y.lane;
-      return x.seq < y.seq;
-   });
+   {
+      const uint64_t count = outOffset >= cap ? 0 : std::min<uint64_t>(nf, cap - outOffset);
+      const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(16, count / 4096));
+      auto work = [&](uint64_t lo, uint64_t hi) {
+         for (uint64_t i = lo; i < hi; i++)
+            emit_frame(h, recs[order[i]], ext, streamBase + streamOf[recs[order[i]].lane], sample_rate, out[outOffset + i]);
+      };
+      if (workers <= 1)
+         work(0, count);
+      else
+      {
+         std::vector<std::thread> pool;
+         const uint64_t step = (count + workers - 1) / workers;
+         for (unsigned w = 0; w < workers; w++)
+            pool.emplace_back(work, std::min(count, w * step), std::min(count, (w + 1) * step));
+         for (auto &t: pool)
+            t.join();
+      }
+   }
 
-   uint64_t nf = keep.size();
-   for (uint64_t i = 0; i < nf && i < cap; i++)
-      emit_frame(h, recs[keep[i]], ext, streamOf[recs[keep[i]].lane], sample_rate, out[i]);
+   *produced = nf;
 
-   if (n_out)
-      *n_out = nf;
-
-   // active blocks (statistics; tiny D2H only when the flag array is small, else estimated from the lanes)
-   S.frames = nf;
-   S.kernel_launches = launches;
    h->lastStreams = n_streams;
    h->lastBlocks = n_blocks;
 
-   float ms = 0;
-   cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-   S.ms_h2d = samples_on_device ? 0.0f : ms;
-   cudaEventElapsedTime(&S.ms_screen, h->ev[1], h->ev[2]);
-   cudaEventElapsedTime(&S.ms_segment, h->ev[2], h->ev[3]);
-   cudaEventElapsedTime(&S.ms_lanes, h->ev[3], h->ev[4]);
-   cudaEventElapsedTime(&S.ms_gather, h->ev[4], h->ev[5]);
+   // accumulate the statistics over the chunks of one call
+   float msScreen = 0, msSeg = 0, msLanes = 0, msGather = 0;
+   cudaEventElapsedTime(&msScreen, h->ev[1], h->ev[2]);
+   cudaEventElapsedTime(&msSeg, h->ev[2], h->ev[3]);
+   cudaEventElapsedTime(&msLanes, h->ev[3], h->ev[4]);
+   cudaEventElapsedTime(&msGather, h->ev[4], h->ev[5]);
+   S.ms_screen = prev.ms_screen + msScreen;
+   S.ms_segment = prev.ms_segment + msSeg;
+   S.ms_lanes = prev.ms_lanes + msLanes;
+   S.ms_gather = prev.ms_gather + msGather;
+   S.segments += prev.segments;
+   S.lanes += prev.lanes;
+   S.live_lanes += prev.live_lanes;
+   S.lane_runs += prev.lane_runs;
+   S.lane_samples += prev.lane_samples;
+   S.rounds = std::max(S.rounds, prev.rounds);
+   S.frames = prev.frames + nf;
+   S.kernel_launches = prev.kernel_launches + launches;
+   (void) bs;
+   return 0;
+}
+
+int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_device, int sigtype, uint32_t n_streams, uint64_t n_samples,
+                         uint32_t sample_rate, nfcb200_frame *out, uint64_t cap, uint64_t *n_out)
+{
+
+   if (!h)
+      return fail(NFCB200_ERR_INVALID, "null handle");
+   if (n_out)
+      *n_out = 0;
+   if (sigtype < SIG_IQ_F32 || sigtype > SIG_IQ_S16)
+      return fail(NFCB200_ERR_INVALID, "unknown signal type %d", sigtype);
+   if (!samples || n_streams == 0 || n_samples == 0)
+      return fail(NFCB200_ERR_INVALID, "empty batch");
+   if (n_samples >= 0xFFFF0000ull)
+      return fail(NFCB200_ERR_UNSUPPORTED, "streams of 2^32 samples or more exceed the 32-bit sample clock of the frame format (NfcTech.h:338)");
+   if (cap && !out)
+      return fail(NFCB200_ERR_INVALID, "null frame buffer");
+
+   CUDA_TRY(cudaSetDevice(h->device));
+
+   if (h->paramsRate != sample_rate)
+   {
+      int rc = setup_params(h, sample_rate);
+      if (rc)
+         return rc;
+   }
+
+   cudaStream_t st = h->stream;
+   const u32 bs = sig_bytes(sigtype);
+   const uint64_t total = (uint64_t) n_streams * n_samples;
+
+   memset(&h->stats, 0, sizeof(h->stats));
+   nfcb200_stats &S = h->stats;
+
+   cudaEventRecord(h->ev[0], st);
+
+   uint64_t nf = 0;
+
+   if (samples_on_device)
+   {
+      int rc = decode_resident(h, samples, sigtype, n_streams, n_samples, sample_rate, 0, out, cap, 0, &nf);
+      if (rc)
+         return rc;
+   }
+   else
+   {
+      // host input: the batch is cut into stream chunks and the copy of chunk i + 1 (second CUDA stream, double-buffered
+      // device staging) overlaps the decode of chunk i, so that a large batch runs at the host link's speed
+      const uint64_t streamBytes = n_samples * bs;
+      uint32_t chunkStreams = n_streams;
+      if (total * bs > (1ull << 30) && n_streams >= 16)
+      {
+         chunkStreams = (n_streams + 7) / 8;
+         while (chunkStreams > 1 && (uint64_t) chunkStreams * streamBytes > (12ull << 30))
+            chunkStreams = (chunkStreams + 1) / 2;
+      }
+      const uint64_t chunkBytes = (((uint64_t) chunkStreams * streamBytes) + 255) & ~255ull;
+      const uint32_t nChunks = (n_streams + chunkStreams - 1) / chunkStreams;
+
+      int rc = h->samples.reserve((nChunks > 1 ? 2 : 1) * chunkBytes + 64);
+      if (rc)
+         return rc;
+
+      if (!h->copyStream)
+      {
+         CUDA_TRY(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+         CUDA_TRY(cudaEventCreateWithFlags(&h->copied[0], cudaEventDisableTiming));
+         CUDA_TRY(cudaEventCreateWithFlags(&h->copied[1], cudaEventDisableTiming));
+      }
+
+      auto issue = [&](uint32_t c) -> cudaError_t {
+         const uint32_t s0 = c * chunkStreams;
+         const uint32_t sc = std::min(chunkStreams, n_streams - s0);
+         unsigned char *dst = (unsigned char *) h->samples.ptr + (c & 1) * chunkBytes;
+         cudaError_t e = cudaMemcpyAsync(dst, (const unsigned char *) samples + (uint64_t) s0 * streamBytes, (uint64_t) sc * streamBytes, cudaMemcpyHostToDevice,
+                                         h->copyStream);
+         if (e != cudaSuccess)
+            return e;
+         return cudaEventRecord(h->copied[c & 1], h->copyStream);
+      };
+
+      CUDA_TRY(issue(0));
+
+      float msCopyWait = 0;
+
+      for (uint32_t c = 0; c < nChunks; c++)
+      {
+         const uint32_t s0 = c * chunkStreams;
+         const uint32_t sc = std::min(chunkStreams, n_streams - s0);
+
+         cudaEventRecord(h->ev[6], st);
+         CUDA_TRY(cudaStreamWaitEvent(st, h->copied[c & 1], 0));
+         cudaEventRecord(h->ev[7], st);
+
+         // the other staging buffer is free (its decode returned): start the next copy before decoding this chunk
+         if (c + 1 < nChunks)
+            CUDA_TRY(issue(c + 1));
+
+         uint64_t got = 0;
+         rc = decode_resident(h, (unsigned char *) h->samples.ptr + (c & 1) * chunkBytes, sigtype, sc, n_samples, sample_rate, s0, out, cap, nf, &got);
+         if (rc)
+            return rc;
+         nf += got;
+
+         float w = 0;
+         cudaEventElapsedTime(&w, h->ev[6], h->ev[7]);
+         msCopyWait += w;
+      }
+
+      S.ms_h2d = msCopyWait; // time the decode stream spent waiting for input
+   }
+
+   cudaEventRecord(h->ev[5], st);
+   CUDA_TRY(cudaStreamSynchronize(st));
    cudaEventElapsedTime(&S.ms_total, h->ev[0], h->ev[5]);
+
+   if (n_out)
+      *n_out = nf;
 
    if (nf > cap)
       return fail(NFCB200_ERR_CAPACITY, "%llu frames decoded but room for %llu only", (unsigned long long) nf, (unsigned long long) cap);
@@ -823,7 +958,10 @@ int nfcb200_stream_push(nfcb200_handle *h, const void *samples, int sigtype, uin
       sg.meanW = powf(h->P.meanW0, (float) NFCB200_BLOCK);
       // note: the stream-start margin of blocks_activate applies to buffer block 0; at the true stream start that is
       // exactly the reference start, later it only makes a few retained blocks active (harmless)
-      segment_count_kernel<<<1, 64, 0, st>>>(sg);
+      sg.segTotal = &h->counters.as<Counters>()->segTotal;
+      const u32 bgrid = (n_blocks + 255) / 256;
+      segment_flags_kernel<<<bgrid, 256, 0, st>>>(sg);
+      segment_activate_kernel<<<bgrid, 256, 0, st>>>(sg);
       CUDA_TRY(cudaGetLastError());
    }
 
