@@ -167,6 +167,72 @@ struct ScreenSmem
    uint64_t bar[2];
 };
 
+struct ScreenTaps
+{
+   int p20, q0, p21, q1, p22, q2, pv, qv;
+   float t0, t1, t2, tv, tb;
+};
+
+// 0.9^(i + 1): decay of the IIR state entering a chunk at its i-th sample
+__device__ __forceinline__ constexpr float pow09(int n)
+{
+   return n <= 0 ? 1.0f : 0.9f * pow09(n - 1);
+}
+
+/*
+ * Trigger tests of one thread's 17 consecutive own samples, branch-free.  PH = slot & 7 of the first sample.
+ * Evaluation density: 424k window every sample, 212k every 2nd, 106k every 4th, NFC-V every 8th -- the thresholds were
+ * lowered on the host by the change |C[t] - C[t - q]| can undergo between evaluations (2 xmax per sample).
+ * The chunk spans at most two screening blocks: their envelope-scaled thresholds are formed once and selected per sample.
+ */
+template <int PH>
+__device__ __forceinline__ void screen_tests(ScreenSmem &s, const ScreenTaps &tp, int first, float exclPref, float wCarry, const float (&loc)[SCR_PER_THREAD],
+                                             const float (&wl)[SCR_PER_THREAD])
+{
+   const int blkA = (first - SCR_HALO) >> 8;
+   const int blkB = (first + SCR_PER_THREAD - 1 - SCR_HALO) >> 8;
+   const int split = SCR_HALO + (blkB << 8) - first; // samples i < split belong to blkA (split >= 17 when blkA == blkB)
+   const float envA = s.envB[blkA], envB = s.envB[blkB];
+
+   const float bA = tp.tb * envA, bB = tp.tb * envB;
+   const float a2A = tp.t2 * envA, a2B = tp.t2 * envB;
+   const float a1A = tp.t1 * envA, a1B = tp.t1 * envB;
+   const float a0A = tp.t0 * envA, a0B = tp.t0 * envB;
+   const float avA = tp.tv * envA, avB = tp.tv * envB;
+
+   const float *P = s.P + first + 1; // P[i] = inclusive prefix at the chunk's i-th sample
+
+   bool hitA = false, hitB = false;
+
+#pragma unroll
+   for (int i = 0; i < SCR_PER_THREAD; i++)
+   {
+      const bool inA = i < split;
+      const float Pt = exclPref + loc[i];
+
+      bool hit = fabsf(wl[i] + pow09(i + 1) * wCarry) > (inA ? bA : bB);
+
+      hit |= fabsf((Pt - P[i - tp.p22]) - (P[i - tp.q2] - P[i - tp.q2 - tp.p22])) > (inA ? a2A : a2B);
+
+      if (((PH + i) & 1) == 0)
+         hit |= fabsf((Pt - P[i - tp.p21]) - (P[i - tp.q1] - P[i - tp.q1 - tp.p21])) > (inA ? a1A : a1B);
+
+      if (((PH + i) & 3) == 0)
+         hit |= fabsf((Pt - P[i - tp.p20]) - (P[i - tp.q0] - P[i - tp.q0 - tp.p20])) > (inA ? a0A : a0B);
+
+      if (((PH + i) & 7) == 0)
+         hit |= fabsf((Pt - P[i - tp.pv]) - (P[i - tp.qv] - P[i - tp.qv - tp.pv])) > (inA ? avA : avB);
+
+      hitA |= hit && inA;
+      hitB |= hit && !inA;
+   }
+
+   if (hitA)
+      s.blockHit[blkA] = 1; // benign race: all writers store 1
+   if (hitB)
+      s.blockHit[blkB] = 1;
+}
+
 // work item -> (stream, tile); staged range in samples [lo, hi) clipped to the stream, `base` = index of smem slot 0
 struct TileGeom
 {
@@ -408,46 +474,65 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
       // so  |S0 - S1| <= 2 |C[t] - C[t - q]| + xmax, and a detector needing |S0 - S1| / p2 > T env cannot trigger while
       //    |C[t] - C[t - q]| <= thr env,   thr = min(0.9 T p2, T p2 - 1.25) / 2          (xmax <= 1.25 env)
       // One difference of two moving sums (3 shared-memory taps) per rate and sample.  The long windows change slowly
-      // (by at most 2 xmax per sample), so the 106k correlator is evaluated on every 2nd sample and the NFC-V one on
-      // every 4th with the threshold lowered by the possible change in between.
-      if (first + SCR_PER_THREAD > SCR_HALO)
+      // (by at most 2 xmax per sample), so the 212k correlator is evaluated on every 2nd sample, the 106k one on every
+      // 4th and the NFC-V one on every 8th, with the thresholds lowered by the possible change in between.
       {
-         const int p20 = (int) c.p2[0], q0 = (int) (c.p1[0] - c.p2[0]);
-         const int p21 = (int) c.p2[1], q1 = (int) (c.p1[1] - c.p2[1]);
-         const int p22 = (int) c.p2[2], q2 = (int) (c.p1[2] - c.p2[2]);
-         const int pv = (int) c.vp2, qv = (int) (c.vp1 - c.vp2);
-         const float t0 = c.thrA[0], t1 = c.thrA[1], t2 = c.thrA[2], tv = c.thrV, tb = c.kB;
+         ScreenTaps tp;
+         tp.p20 = (int) c.p2[0];
+         tp.q0 = (int) (c.p1[0] - c.p2[0]);
+         tp.p21 = (int) c.p2[1];
+         tp.q1 = (int) (c.p1[1] - c.p2[1]);
+         tp.p22 = (int) c.p2[2];
+         tp.q2 = (int) (c.p1[2] - c.p2[2]);
+         tp.pv = (int) c.vp2;
+         tp.qv = (int) (c.vp1 - c.vp2);
+         tp.t0 = c.thrA[0];
+         tp.t1 = c.thrA[1];
+         tp.t2 = c.thrA[2];
+         tp.tv = c.thrV;
+         tp.tb = c.kB;
+
          const int ownEnd = (int) ((int64_t) c.n_samples - g.base); // first slot past the stream
+         const int lastSlot = first + SCR_PER_THREAD - 1;
 
-         float a = 1.0f;
-
-#pragma unroll
-         for (int i = 0; i < SCR_PER_THREAD; i++)
+         if (first >= SCR_HALO && lastSlot < ownEnd)
          {
-            a *= 0.9f;
-
-            const int slot = first + i;
-            if (slot < SCR_HALO || slot >= ownEnd)
-               continue;
-
-            const int blk = (slot - SCR_HALO) >> 8;
-            const float env = s.envB[blk];
-            const int t = slot + 1; // P index of the inclusive prefix at this sample
-            const float Pt = exclPref + loc[i];
-
-            bool hit = fabsf(wl[i] + a * wCarry) > tb * env;
-
-            hit |= fabsf((Pt - s.P[t - p21]) - (s.P[t - q1] - s.P[t - q1 - p21])) > t1 * env;
-            hit |= fabsf((Pt - s.P[t - p22]) - (s.P[t - q2] - s.P[t - q2 - p22])) > t2 * env;
-
-            if ((slot & 1) == 0)
-               hit |= fabsf((Pt - s.P[t - p20]) - (s.P[t - q0] - s.P[t - q0 - p20])) > t0 * env;
-
-            if ((slot & 3) == 0)
-               hit |= fabsf((Pt - s.P[t - pv]) - (s.P[t - qv] - s.P[t - qv - pv])) > tv * env;
-
-            if (hit)
-               s.blockHit[blk] = 1; // benign race: all writers store 1
+            // whole chunk inside the tile's own samples: branch-free tests, decimation phases resolved at compile time
+            // (17 = 1 mod 8, so slot & 7 == (tid + i) & 7)
+            switch (tid & 7)
+            {
+               case 0: screen_tests<0>(s, tp, first, exclPref, wCarry, loc, wl); break;
+               case 1: screen_tests<1>(s, tp, first, exclPref, wCarry, loc, wl); break;
+               case 2: screen_tests<2>(s, tp, first, exclPref, wCarry, loc, wl); break;
+               case 3: screen_tests<3>(s, tp, first, exclPref, wCarry, loc, wl); break;
+               case 4: screen_tests<4>(s, tp, first, exclPref, wCarry, loc, wl); break;
+               case 5: screen_tests<5>(s, tp, first, exclPref, wCarry, loc, wl); break;
+               case 6: screen_tests<6>(s, tp, first, exclPref, wCarry, loc, wl); break;
+               default: screen_tests<7>(s, tp, first, exclPref, wCarry, loc, wl); break;
+            }
+         }
+         else if (lastSlot >= SCR_HALO && first < ownEnd)
+         {
+            // chunk straddling the halo boundary or the end of the stream: same tests, checked per sample, no decimation
+            float a = 1.0f;
+            for (int i = 0; i < SCR_PER_THREAD; i++)
+            {
+               a *= 0.9f;
+               const int slot = first + i;
+               if (slot < SCR_HALO || slot >= ownEnd)
+                  continue;
+               const int blk = (slot - SCR_HALO) >> 8;
+               const float env = s.envB[blk];
+               const int t = slot + 1;
+               const float Pt = s.P[t];
+               bool hit = fabsf(wl[i] + a * wCarry) > tp.tb * env;
+               hit |= fabsf((Pt - s.P[t - tp.p20]) - (s.P[t - tp.q0] - s.P[t - tp.q0 - tp.p20])) > tp.t0 * env;
+               hit |= fabsf((Pt - s.P[t - tp.p21]) - (s.P[t - tp.q1] - s.P[t - tp.q1 - tp.p21])) > tp.t1 * env;
+               hit |= fabsf((Pt - s.P[t - tp.p22]) - (s.P[t - tp.q2] - s.P[t - tp.q2 - tp.p22])) > tp.t2 * env;
+               hit |= fabsf((Pt - s.P[t - tp.pv]) - (s.P[t - tp.qv] - s.P[t - tp.qv - tp.pv])) > tp.tv * env;
+               if (hit)
+                  s.blockHit[blk] = 1;
+            }
          }
       }
 

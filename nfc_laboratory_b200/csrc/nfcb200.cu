@@ -173,11 +173,13 @@ static void fill_screen_config(const nfcb200_handle *h, ScreenConfig &sc)
       float p2 = (float) P.A[r].p2;
       sc.thrA[r] = std::min(margin * T[r] * p2, T[r] * p2 - 1.25f) * 0.5f;
    }
-   sc.thrA[0] -= 2.5f;       // evaluated on every 2nd sample: |C[t] - C[t-q]| moves by at most 2 xmax = 2.5 env per sample
+   // decimated evaluation: |C[t] - C[t-q]| moves by at most 2 xmax = 2.5 env per sample
+   sc.thrA[1] -= 1 * 2.5f;   // 212k: every 2nd sample
+   sc.thrA[0] -= 3 * 2.5f;   // 106k: every 4th sample
    {
       float p2 = (float) P.V.p2;
-      // NFC-V: S0 = (C[t-q] - C[t]) / p2 > T env (NfcV.cpp:274, 305); evaluated on every 4th sample
-      sc.thrV = std::min(margin * cV * p2, cV * p2 - 1.25f) - 3 * 2.5f;
+      // NFC-V: S0 = (C[t-q] - C[t]) / p2 > T env (NfcV.cpp:274, 305); every 8th sample
+      sc.thrV = std::min(margin * cV * p2, cV * p2 - 1.25f) - 7 * 2.5f;
    }
    for (int r = 0; r < 3; r++)
       sc.thrA[r] = std::max(sc.thrA[r], 0.25f);

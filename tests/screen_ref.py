@@ -28,8 +28,8 @@ class ScreenParams:
         self.kV = margin * corrV
         # device rule (csrc/nfc_screen.cuh): |C[t] - C[t-q]| > thr * env, thr = min(0.9 T p2, T p2 - 1.25) / 2
         T = [corrA, min(corrA, corrF), min(corrA, corrF)]
-        self.thrA = [max(0.25, min(margin * T[r] * self.periods[r][1], T[r] * self.periods[r][1] - 1.25) * 0.5 - (2.5 if r == 0 else 0.0)) for r in range(3)]
-        self.thrV = max(0.25, min(margin * corrV * self.v[1], corrV * self.v[1] - 1.25) - 7.5)
+        self.thrA = [max(0.25, min(margin * T[r] * self.periods[r][1], T[r] * self.periods[r][1] - 1.25) * 0.5 - (7.5, 2.5, 0.0)[r]) for r in range(3)]
+        self.thrV = max(0.25, min(margin * corrV * self.v[1], corrV * self.v[1] - 1.25) - 17.5)
         self.kB = margin * modMinB
         self.low = power / 1.25
         self.high = power * 1.25
@@ -141,10 +141,10 @@ def block_flags_device_model(x, sp):
     env = np.repeat(envb, BLOCK)[:n]
     hit = np.zeros(n, dtype=bool)
     idx = np.arange(n)
-    hit |= (np.abs(f["dc"][0]) > sp.thrA[0] * env) & ((idx & 1) == 0)
-    hit |= np.abs(f["dc"][1]) > sp.thrA[1] * env
+    hit |= (np.abs(f["dc"][0]) > sp.thrA[0] * env) & ((idx & 3) == 0)
+    hit |= (np.abs(f["dc"][1]) > sp.thrA[1] * env) & ((idx & 1) == 0)
     hit |= np.abs(f["dc"][2]) > sp.thrA[2] * env
-    hit |= (np.abs(f["dcv"]) > sp.thrV * env) & ((idx & 3) == 0)
+    hit |= (np.abs(f["dcv"]) > sp.thrV * env) & ((idx & 7) == 0)
     hit |= np.abs(f["w"]) > sp.kB * env
     pad = np.zeros(nb * BLOCK, dtype=bool)
     pad[:n] = hit
