@@ -180,12 +180,12 @@ __device__ __forceinline__ constexpr float pow09(int n)
 }
 
 /*
- * Trigger tests of one thread's 17 consecutive own samples, branch-free.  PH = slot & 7 of the first sample.
- * Evaluation density: 424k window every sample, 212k every 2nd, 106k every 4th, NFC-V every 8th -- the thresholds were
- * lowered on the host by the change |C[t] - C[t - q]| can undergo between evaluations (2 xmax per sample).
+ * Trigger tests of one thread's 17 consecutive own samples, branch-free.
+ * Evaluation density: 424k window every sample, 212k at chunk offsets 0, 2, .., 16, 106k at 0, 4, .., 16, NFC-V at 0, 8,
+ * 16 (the gap to the next chunk's offset 0 is one sample) -- the thresholds were lowered on the host by the change
+ * |C[t] - C[t - q]| can undergo between evaluations (2 xmax per sample).  Chunk-relative phases keep every warp uniform.
  * The chunk spans at most two screening blocks: their envelope-scaled thresholds are formed once and selected per sample.
  */
-template <int PH>
 __device__ __forceinline__ void screen_tests(ScreenSmem &s, const ScreenTaps &tp, int first, float exclPref, float wCarry, const float (&loc)[SCR_PER_THREAD],
                                              const float (&wl)[SCR_PER_THREAD])
 {
@@ -214,13 +214,13 @@ __device__ __forceinline__ void screen_tests(ScreenSmem &s, const ScreenTaps &tp
 
       hit |= fabsf((Pt - P[i - tp.p22]) - (P[i - tp.q2] - P[i - tp.q2 - tp.p22])) > (inA ? a2A : a2B);
 
-      if (((PH + i) & 1) == 0)
+      if ((i & 1) == 0)
          hit |= fabsf((Pt - P[i - tp.p21]) - (P[i - tp.q1] - P[i - tp.q1 - tp.p21])) > (inA ? a1A : a1B);
 
-      if (((PH + i) & 3) == 0)
+      if ((i & 3) == 0)
          hit |= fabsf((Pt - P[i - tp.p20]) - (P[i - tp.q0] - P[i - tp.q0 - tp.p20])) > (inA ? a0A : a0B);
 
-      if (((PH + i) & 7) == 0)
+      if ((i & 7) == 0)
          hit |= fabsf((Pt - P[i - tp.pv]) - (P[i - tp.qv] - P[i - tp.qv - tp.pv])) > (inA ? avA : avB);
 
       hitA |= hit && inA;
@@ -497,19 +497,8 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
 
          if (first >= SCR_HALO && lastSlot < ownEnd)
          {
-            // whole chunk inside the tile's own samples: branch-free tests, decimation phases resolved at compile time
-            // (17 = 1 mod 8, so slot & 7 == (tid + i) & 7)
-            switch (tid & 7)
-            {
-               case 0: screen_tests<0>(s, tp, first, exclPref, wCarry, loc, wl); break;
-               case 1: screen_tests<1>(s, tp, first, exclPref, wCarry, loc, wl); break;
-               case 2: screen_tests<2>(s, tp, first, exclPref, wCarry, loc, wl); break;
-               case 3: screen_tests<3>(s, tp, first, exclPref, wCarry, loc, wl); break;
-               case 4: screen_tests<4>(s, tp, first, exclPref, wCarry, loc, wl); break;
-               case 5: screen_tests<5>(s, tp, first, exclPref, wCarry, loc, wl); break;
-               case 6: screen_tests<6>(s, tp, first, exclPref, wCarry, loc, wl); break;
-               default: screen_tests<7>(s, tp, first, exclPref, wCarry, loc, wl); break;
-            }
+            // whole chunk inside the tile's own samples: branch-free tests
+            screen_tests(s, tp, first, exclPref, wCarry, loc, wl);
          }
          else if (lastSlot >= SCR_HALO && first < ownEnd)
          {

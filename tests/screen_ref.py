@@ -141,10 +141,12 @@ def block_flags_device_model(x, sp):
     env = np.repeat(envb, BLOCK)[:n]
     hit = np.zeros(n, dtype=bool)
     idx = np.arange(n)
-    hit |= (np.abs(f["dc"][0]) > sp.thrA[0] * env) & ((idx & 3) == 0)
-    hit |= (np.abs(f["dc"][1]) > sp.thrA[1] * env) & ((idx & 1) == 0)
+    # decimated evaluation at chunk-relative offsets (17-sample thread chunks of 3840-sample tiles with a 512-sample halo)
+    ci = (idx - (idx // 3840) * 3840 + 512) % 17
+    hit |= (np.abs(f["dc"][0]) > sp.thrA[0] * env) & ((ci & 3) == 0)
+    hit |= (np.abs(f["dc"][1]) > sp.thrA[1] * env) & ((ci & 1) == 0)
     hit |= np.abs(f["dc"][2]) > sp.thrA[2] * env
-    hit |= (np.abs(f["dcv"]) > sp.thrV * env) & ((idx & 7) == 0)
+    hit |= (np.abs(f["dcv"]) > sp.thrV * env) & ((ci & 7) == 0)
     hit |= np.abs(f["w"]) > sp.kB * env
     pad = np.zeros(nb * BLOCK, dtype=bool)
     pad[:n] = hit
