@@ -173,12 +173,6 @@ struct ScreenTaps
    float t0, t1, t2, tv, tb;
 };
 
-// 0.9^(i + 1): decay of the IIR state entering a chunk at its i-th sample
-__device__ __forceinline__ constexpr float pow09(int n)
-{
-   return n <= 0 ? 1.0f : 0.9f * pow09(n - 1);
-}
-
 /*
  * Trigger tests of one thread's 17 consecutive own samples, branch-free.
  * Evaluation density: 424k window every sample, 212k at chunk offsets 0, 2, .., 16, 106k at 0, 4, .., 16, NFC-V at 0, 8,
@@ -203,6 +197,7 @@ __device__ __forceinline__ void screen_tests(ScreenSmem &s, const ScreenTaps &tp
    const float *P = s.P + first + 1; // P[i] = inclusive prefix at the chunk's i-th sample
 
    bool hitA = false, hitB = false;
+   float decay = 1.0f; // 0.9^(i + 1): what is left of the IIR state that entered the chunk
 
 #pragma unroll
    for (int i = 0; i < SCR_PER_THREAD; i++)
@@ -210,7 +205,8 @@ __device__ __forceinline__ void screen_tests(ScreenSmem &s, const ScreenTaps &tp
       const bool inA = i < split;
       const float Pt = exclPref + loc[i];
 
-      bool hit = fabsf(wl[i] + pow09(i + 1) * wCarry) > (inA ? bA : bB);
+      decay *= 0.9f;
+      bool hit = fabsf(wl[i] + decay * wCarry) > (inA ? bA : bB);
 
       hit |= fabsf((Pt - P[i - tp.p22]) - (P[i - tp.q2] - P[i - tp.q2 - tp.p22])) > (inA ? a2A : a2B);
 
@@ -504,6 +500,7 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
          {
             // chunk straddling the halo boundary or the end of the stream: same tests, checked per sample, no decimation
             float a = 1.0f;
+#pragma unroll
             for (int i = 0; i < SCR_PER_THREAD; i++)
             {
                a *= 0.9f;
