@@ -446,6 +446,15 @@ __global__ void chain_kernel(ChainConfig c, const __grid_constant__ Params dP)
    }
 }
 
+// length of every lane's own region + halo (the host orders the first-round queue by it: lanes of similar length share a
+// warp, long lanes start first)
+__global__ void lane_length_kernel(const LaneRec *lanes, uint32_t n, uint32_t *length)
+{
+   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n)
+      length[i] = lanes[i].end - lanes[i].first;
+}
+
 // (generation << 1 | dead) per lane, plus the stream of the lane: what the host needs to gather frames
 __global__ void lane_meta_kernel(const LaneRec *lanes, uint32_t n, uint32_t *meta, uint32_t *streamOf, unsigned long long *liveCount)
 {

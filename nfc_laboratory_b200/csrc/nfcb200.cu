@@ -489,6 +489,27 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    launches++;
    CUDA_TRY(cudaGetLastError());
 
+   // first-round queue ordered by decreasing lane length (counting sort on the host: the lengths are 4 bytes per lane)
+   if (nLanes > 64)
+   {
+      lane_length_kernel<<<(nLanes + 255) / 256, 256, 0, st>>>(h->lanes.as<LaneRec>(), nLanes, h->meta.as<u32>());
+      launches++;
+      std::vector<u32> len(nLanes), order(nLanes);
+      CUDA_TRY(cudaMemcpyAsync(len.data(), h->meta.ptr, (size_t) nLanes * sizeof(u32), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      const u32 shift = 8, buckets = 1u << 16;
+      std::vector<u32> hist(buckets + 1, 0);
+      auto key = [&](u32 v) { u32 k = v >> shift; return k >= buckets ? 0u : buckets - 1 - k; }; // descending
+      for (u32 i = 0; i < nLanes; i++)
+         hist[key(len[i]) + 1]++;
+      for (u32 b = 0; b < buckets; b++)
+         hist[b + 1] += hist[b];
+      for (u32 i = 0; i < nLanes; i++)
+         order[hist[key(len[i])]++] = i;
+      CUDA_TRY(cudaMemcpyAsync(h->queue.ptr, order.data(), (size_t) nLanes * sizeof(u32), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+   }
+
    cudaEventRecord(h->ev[3], st);
 
    // ---- frame pool ----------------------------------------------------------------------------------------------------
