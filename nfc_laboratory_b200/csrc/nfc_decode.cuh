@@ -518,6 +518,7 @@ __global__ void stream_kernel(StreamConfig c, const __grid_constant__ Params dP)
    u32 pos = S.pos;
    u32 running = S.running;
    u32 contig = S.contig;
+   u32 noParkBefore = 0; // a resumed lane steps through the idle samples up to the next active block without re-parking
 
    auto active = [&](u32 p) -> bool {
       u32 b = p >> 8;
@@ -564,13 +565,14 @@ __global__ void stream_kernel(StreamConfig c, const __grid_constant__ Params dP)
          }
          // else: too close for a cold start and the parked machine is still positioned at pos: resume it
 
+         noParkBefore = begin;
          running = 1;
          contig = 1;
       }
 
       while (pos < c.limit)
       {
-         if (!active(pos) && M.dormant())
+         if (pos >= noParkBefore && !active(pos) && M.dormant())
          {
             S.carry = L.c;
             carry_canon(S.carry);
