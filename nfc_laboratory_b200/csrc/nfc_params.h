@@ -191,6 +191,8 @@ static inline void params_init(Params *P, u32 sampleRate)
    // NFC-V: single rate, delay = period0 (NfcV.cpp:154-173)
    rate_fill(&P->V, stu, 512, 0, 0, NFCB200_OFF_CV);
    P->V.sdd = P->V.p0;
+   if (!P->V.p1 || !P->V.p0 || P->V.sdd >= NFCB200_RING)
+      return; // sample rate far outside the range the reference supports
    P->V.c1 = (NFCB200_RING - P->V.sdd) % P->V.p1;
    P->V.c0 = (NFCB200_RING - P->V.sdd) % P->V.p0;
    P->V.sps = (u32) (int) roundf(NFC_FC / 256);

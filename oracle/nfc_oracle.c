@@ -232,6 +232,8 @@ static void params_init(Params *p, u32 sampleRate)
    }
    rate_fill(&p->V, stu, 512, 0, 0, NFCB200_OFF_CV);                  /* NfcV.cpp:154-173 */
    p->V.sdd = p->V.p0;
+   if (!p->V.p1 || !p->V.p0 || p->V.sdd >= NFCB200_RING)
+      return;
    p->V.c1 = (NFCB200_RING - p->V.sdd) % p->V.p1;
    p->V.c0 = (NFCB200_RING - p->V.sdd) % p->V.p0;
    p->V.sps = (u32) (int) roundf(NFC_FC / 256);
