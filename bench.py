@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle spot check (profiling runs)")
     ap.add_argument("--quick", action="store_true", help="small batch for smoke runs (64 streams x 2e6)")
     return ap.parse_args()
 
@@ -191,11 +192,11 @@ def main():
             return nf
         flat = ND.pack_frames(ND.frames_as_array(buf, nf), stream_offset=rank * S)
         allf = ND.gather_frames(flat, dev)
-        return nf if allf is None else len(allf)
+        return nf if allf is None else ND.count_frames(allf)
 
     # ---- parity spot check against the oracle (untimed): first streams, first 2e6 samples ---------------------------------
     parity = None
-    if rank == 0:
+    if rank == 0 and not args.no_parity:
         import nfcutil as U
         if U.ref_lib() is not None:
             ns = min(2, S)
@@ -270,7 +271,7 @@ def main():
         except Exception:
             avail = 32 << 30
         Se = S
-        while Se > 1 and Se * n * 8 > 0.35 * avail:
+        while Se > 1 and Se * n * 8 > min(0.25 * avail / world, 24 << 30):  # every rank pins its own copy; bounded host footprint
             Se //= 2
         host = torch.empty((Se, n, 2), dtype=torch.float32, pin_memory=True)
         host.copy_(iq[:Se])
@@ -301,7 +302,7 @@ def main():
 
     # ---- CPU baseline: the reference decoder on this box's cores, bounded sample of the same batch -------------------------
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         Sc = min(S, max(cores, min(2 * cores, 32)))
         nc = min(n, 10_000_000)
@@ -327,7 +328,7 @@ def main():
                          "algorithmic_bytes_per_launch": bytes_per_step, "ms_per_launch": ms_screen},
             "cpu_baseline": cpu,
             "clocks": clocks,
-            "phases_ms": {k: statistics.mean(s[k] for s in stats) for k in ("ms_screen", "ms_segment", "ms_lanes", "ms_gather", "ms_total")},
+            "phases_ms": {k: statistics.mean(s[k] for s in stats) for k in ("ms_screen", "ms_segment", "ms_lanes", "ms_gather", "ms_total", "ms_wall")},
             "decode": {"frames_per_step": frames_total // max(1, args.steps), "segments": st["segments"], "lanes": st["lanes"], "rounds": st["rounds"],
                        "lane_runs": st["lane_runs"], "lane_samples_frac": st["lane_samples"] / max(1, st["samples"])},
             "parity_spot_check": parity,

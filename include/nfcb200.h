@@ -100,6 +100,7 @@ typedef struct nfcb200_stats
    float ms_lanes;            /* all lane + chain kernels                       */
    float ms_gather;           /* frame gather incl. device -> host copy         */
    float ms_total;            /* whole call, device events                      */
+   float ms_wall;             /* whole call, host clock                         */
 } nfcb200_stats;
 
 void nfcb200_config_default(nfcb200_config *cfg);
@@ -142,6 +143,13 @@ int nfcb200_get_stats(nfcb200_handle *h, nfcb200_stats *stats);
 
 /* debug tap: per-block screening flags of the last batch, [n_streams][n_blocks] bytes (bit0 trigger, bit1 active) */
 int nfcb200_get_block_flags(nfcb200_handle *h, uint8_t *out, uint64_t cap, uint64_t *n_blocks_per_stream);
+
+/*
+ * Wire format of the multi-GPU frame gather (no reference counterpart: the reference is one decoder per process).
+ * Writes [u64 count][count x 80-byte frame headers, stream index raised by stream_offset][payload bytes back to back]
+ * to `out`; *n_bytes is the size needed (call with out == NULL to size the buffer).  Host-only, no CUDA call.
+ */
+int nfcb200_pack_frames(const nfcb200_frame *frames, uint64_t n, uint32_t stream_offset, uint8_t *out, uint64_t cap, uint64_t *n_bytes);
 
 const char *nfcb200_last_error(void);
 

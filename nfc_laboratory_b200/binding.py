@@ -49,7 +49,7 @@ class CStats(C.Structure):
         ("live_lanes", C.c_uint64), ("lane_runs", C.c_uint64), ("lane_samples", C.c_uint64), ("rounds", C.c_uint64),
         ("frames", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("ms_h2d", C.c_float), ("ms_screen", C.c_float), ("ms_segment", C.c_float), ("ms_lanes", C.c_float),
-        ("ms_gather", C.c_float), ("ms_total", C.c_float),
+        ("ms_gather", C.c_float), ("ms_total", C.c_float), ("ms_wall", C.c_float),
     ]
 
 
@@ -74,8 +74,8 @@ class Frame(tuple):
 
 EXPORTS = [
     "nfcb200_config_default", "nfcb200_create", "nfcb200_destroy", "nfcb200_configure", "nfcb200_decode_batch",
-    "nfcb200_stream_push", "nfcb200_stream_reset", "nfcb200_get_stats", "nfcb200_get_block_flags", "nfcb200_last_error",
-    "nfcb200_version",
+    "nfcb200_stream_push", "nfcb200_stream_reset", "nfcb200_get_stats", "nfcb200_get_block_flags", "nfcb200_pack_frames",
+    "nfcb200_last_error", "nfcb200_version",
 ]
 
 
@@ -109,6 +109,7 @@ def load_library():
     lib.nfcb200_stream_reset.argtypes = [C.c_void_p]
     lib.nfcb200_get_stats.argtypes = [C.c_void_p, C.POINTER(CStats)]
     lib.nfcb200_get_block_flags.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.nfcb200_pack_frames.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     _lib = lib
     return lib
 

@@ -10,8 +10,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -95,6 +97,24 @@ struct Counters
    unsigned long long live;
    u32 segTotal;
    u32 pad;
+};
+
+// host-side milestones of a call, printed when NFCB200_TRACE is set (debug aid)
+struct Trace
+{
+   bool on;
+   std::chrono::steady_clock::time_point t0, last;
+   Trace() : on(getenv("NFCB200_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), last(t0) {}
+   double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+   void mark(const char *what)
+   {
+      if (!on)
+         return;
+      auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[nfcb200] %-28s +%8.2f ms (%8.2f)\n", what, std::chrono::duration<double, std::milli>(now - last).count(),
+              std::chrono::duration<double, std::milli>(now - t0).count());
+      last = now;
+   }
 };
 
 struct nfcb200_handle
@@ -370,6 +390,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    S.samples += total;
    S.blocks += (uint64_t) n_streams * n_blocks;
 
+   Trace tr;
    cudaEventRecord(h->ev[1], st);
 
    // ---- K1: screening -------------------------------------------------------------------------------------------------
@@ -457,6 +478,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       }
    }
    S.segments = segTotal;
+   tr.mark("screen + segments");
 
    std::vector<u32> counts(n_streams), offsets(n_streams);
    CUDA_TRY(cudaMemcpyAsync(counts.data(), h->counts.ptr, n_streams * sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -510,6 +532,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       CUDA_TRY(cudaStreamSynchronize(st));
    }
 
+   tr.mark("lane fill + order");
    cudaEventRecord(h->ev[3], st);
 
    // ---- frame pool ----------------------------------------------------------------------------------------------------
@@ -597,6 +620,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    }
 
    S.rounds = rounds;
+   tr.mark("lanes + chain");
 
    cudaEventRecord(h->ev[4], st);
 
@@ -628,6 +652,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
 
    cudaEventRecord(h->ev[5], st);
    CUDA_TRY(cudaStreamSynchronize(st));
+   tr.mark("pool d2h");
 
    // keep only the frames of the final generation of live lanes.  Lanes are globally ordered by (stream, time) and a
    // run numbers its frames 0 .. nframes-1, so the output position of a frame is a counting sort: offset[lane] + seq
@@ -659,6 +684,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
          order[pos] = i;
    }
 
+   tr.mark("counting sort");
    {
       const uint64_t count = outOffset >= cap ? 0 : std::min<uint64_t>(nf, cap - outOffset);
       const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(16, count / 4096));
@@ -679,6 +705,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       }
    }
 
+   tr.mark("emit");
    *produced = nf;
 
    h->lastStreams = n_streams;
@@ -738,6 +765,7 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
 
    memset(&h->stats, 0, sizeof(h->stats));
    nfcb200_stats &S = h->stats;
+   Trace wall;
 
    cudaEventRecord(h->ev[0], st);
 
@@ -820,6 +848,7 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
    cudaEventRecord(h->ev[5], st);
    CUDA_TRY(cudaStreamSynchronize(st));
    cudaEventElapsedTime(&S.ms_total, h->ev[0], h->ev[5]);
+   S.ms_wall = (float) wall.ms();
 
    if (n_out)
       *n_out = nf;
@@ -827,6 +856,60 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
    if (nf > cap)
       return fail(NFCB200_ERR_CAPACITY, "%llu frames decoded but room for %llu only", (unsigned long long) nf, (unsigned long long) cap);
 
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// wire format of the multi-GPU frame gather: [u64 count][count x 80-byte headers][payloads back to back]
+// ---------------------------------------------------------------------------------------------------------------------
+int nfcb200_pack_frames(const nfcb200_frame *frames, uint64_t n, uint32_t stream_offset, uint8_t *out, uint64_t cap, uint64_t *n_bytes)
+{
+   if (n && !frames)
+      return fail(NFCB200_ERR_INVALID, "null frames");
+   const size_t headBytes = offsetof(nfcb200_frame, data);
+
+   std::vector<uint64_t> offs(n + 1);
+   uint64_t payload = 0;
+   for (uint64_t i = 0; i < n; i++)
+   {
+      offs[i] = payload;
+      payload += frames[i].length > 512 ? 512 : frames[i].length;
+   }
+   offs[n] = payload;
+
+   const uint64_t need = 8 + n * headBytes + payload;
+   if (n_bytes)
+      *n_bytes = need;
+   if (!out)
+      return 0;
+   if (cap < need)
+      return fail(NFCB200_ERR_CAPACITY, "%llu bytes needed, room for %llu", (unsigned long long) need, (unsigned long long) cap);
+
+   memcpy(out, &n, 8);
+   uint8_t *head = out + 8;
+   uint8_t *pay = head + n * headBytes;
+
+   auto work = [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; i++)
+      {
+         memcpy(head + i * headBytes, &frames[i], headBytes);
+         uint32_t stream = frames[i].stream + stream_offset;
+         memcpy(head + i * headBytes, &stream, 4);
+         memcpy(pay + offs[i], frames[i].data, offs[i + 1] - offs[i]);
+      }
+   };
+   const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(16, n / 8192));
+   if (workers <= 1)
+      work(0, n);
+   else
+   {
+      std::vector<std::thread> pool;
+      const uint64_t step = (n + workers - 1) / workers;
+      for (unsigned w = 0; w < workers; w++)
+         pool.emplace_back(work, std::min(n, w * step), std::min(n, (w + 1) * step));
+      for (auto &t: pool)
+         t.join();
+   }
    return 0;
 }
 

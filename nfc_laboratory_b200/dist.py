@@ -27,48 +27,51 @@ def frames_as_array(cbuf, n):
     return np.frombuffer(cbuf, dtype=FRAME_DTYPE, count=n)
 
 
-def pack_frames(arr, stream_offset=0, chunk=65536):
-    """frame records -> one flat uint8 buffer: per frame an 80-byte header followed by `length` payload bytes"""
-    parts = []
-    for i in range(0, arr.size, chunk):
-        a = arr[i:i + chunk]
-        head = np.zeros((a.size, HEADER_BYTES), dtype=np.uint8)
-        hv = head.view(np.dtype([("u", "<u4", (8,)), ("q", "<u8", (3,)), ("d", "<f8", (3,))]))[:, 0]
-        hv["u"][:, 0] = a["stream"] + stream_offset
-        for k, name in enumerate(("tech_type", "frame_type", "frame_flags", "frame_phase", "frame_rate", "length")):
-            hv["u"][:, k + 1] = a[name]
-        hv["q"][:, 0] = a["sample_start"]
-        hv["q"][:, 1] = a["sample_end"]
-        hv["q"][:, 2] = a["sample_rate"]
-        hv["d"][:, 0] = a["time_start"]
-        hv["d"][:, 1] = a["time_end"]
-        hv["d"][:, 2] = a["date_time"]
-        ln = a["length"].astype(np.int64)
-        mask = np.arange(512)[None, :] < ln[:, None]
-        width = HEADER_BYTES + ln
-        offs = np.concatenate([[0], np.cumsum(width)])
-        flat = np.empty(int(offs[-1]), dtype=np.uint8)
-        hidx = offs[:-1, None] + np.arange(HEADER_BYTES)[None, :]
-        flat[hidx.ravel()] = head.ravel()
-        pidx = (offs[:-1, None] + HEADER_BYTES + np.arange(512)[None, :])[mask]
-        flat[pidx] = a["data"][mask]
-        parts.append(flat)
-    return np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
+def pack_frames(arr, stream_offset=0):
+    """frame records (numpy FRAME_DTYPE array, e.g. a view of the decoder's output buffer) -> one flat uint8 buffer
+    [u64 count][count x 80-byte headers][payload bytes back to back], packed by nfcb200_pack_frames (host threads)"""
+    import ctypes as C
+    from .binding import load_library, _check
+    lib = load_library()
+    a = np.ascontiguousarray(arr)
+    n = int(a.size)
+    need = C.c_uint64(0)
+    ptr = a.ctypes.data if n else None
+    _check(lib, lib.nfcb200_pack_frames(ptr, n, int(stream_offset), None, 0, C.byref(need)))
+    flat = np.empty(int(need.value), dtype=np.uint8)
+    _check(lib, lib.nfcb200_pack_frames(ptr, n, int(stream_offset), flat.ctypes.data, flat.size, C.byref(need)))
+    return flat
 
 
 def unpack_frames(flat):
-    """inverse of pack_frames -> list of (stream, tech, type, flags, phase, rate, start, end, payload bytes)"""
+    """inverse of pack_frames (also accepts several packed buffers back to back, as gather_frames returns them)
+    -> list of (stream, tech, type, flags, phase, rate, start, end, payload bytes)"""
     out = []
     pos = 0
-    n = flat.size
-    while pos < n:
-        u = flat[pos:pos + 32].view("<u4")
-        q = flat[pos + 32:pos + 56].view("<u8")
-        ln = int(u[6])
-        out.append((int(u[0]), int(u[1]), int(u[2]), int(u[3]), int(u[4]), int(u[5]), int(q[0]), int(q[1]),
-                    bytes(flat[pos + HEADER_BYTES:pos + HEADER_BYTES + ln])))
-        pos += HEADER_BYTES + ln
+    while pos < flat.size:
+        n = int(flat[pos:pos + 8].view("<u8")[0])
+        head = flat[pos + 8:pos + 8 + n * HEADER_BYTES].reshape(n, HEADER_BYTES)
+        pay = pos + 8 + n * HEADER_BYTES
+        for i in range(n):
+            u = head[i, :32].view("<u4")
+            q = head[i, 32:56].view("<u8")
+            ln = int(u[6])
+            out.append((int(u[0]), int(u[1]), int(u[2]), int(u[3]), int(u[4]), int(u[5]), int(q[0]), int(q[1]), bytes(flat[pay:pay + ln])))
+            pay += ln
+        pos = pay
     return out
+
+
+def count_frames(flat):
+    """number of frames in a (possibly concatenated) packed buffer without unpacking the payloads"""
+    total = 0
+    pos = 0
+    while pos < flat.size:
+        n = int(flat[pos:pos + 8].view("<u8")[0])
+        head = flat[pos + 8:pos + 8 + n * HEADER_BYTES].reshape(n, HEADER_BYTES)
+        total += n
+        pos += 8 + n * HEADER_BYTES + int(head[:, 24:28].copy().view("<u4").sum())
+    return total
 
 
 def gather_frames(flat, device, group=None):

@@ -39,13 +39,15 @@ def test_pack_unpack_roundtrip():
     from nfc_laboratory_b200 import dist as ND
     rng = np.random.default_rng(3)
     a = _fake_frames(rng, 500, 0, 50)
-    flat = ND.pack_frames(a, stream_offset=7, chunk=128)
+    flat = ND.pack_frames(a, stream_offset=7)
     out = ND.unpack_frames(flat)
     assert len(out) == 500
     for rec, f in zip(a, out):
         assert f[0] == rec["stream"] + 7 and f[2] == rec["frame_type"] and f[6] == rec["sample_start"]
         assert f[8] == bytes(rec["data"][: rec["length"]])
-    assert ND.pack_frames(a[:0]).size == 0
+    assert ND.count_frames(flat) == 500
+    empty = ND.pack_frames(a[:0])
+    assert ND.unpack_frames(empty) == [] and ND.count_frames(np.concatenate([empty, flat, empty])) == 500
 
 
 def _worker(rank, world, port, q):
