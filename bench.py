@@ -88,6 +88,22 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def host_cores():
+    """threads the reference arm may use: the scheduler affinity of this process, clipped by a cgroup CPU quota"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, per = f.read().split()[:2]
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -115,7 +131,7 @@ def reference_arm(args, rank, world):
         return
     import torch
     from nfc_laboratory_b200 import synth
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     S = max(cores, min(4 * cores, 64))
     n = min(args.samples, 10_000_000)
     iq = synth.synth_batch(args.workload, S, n, seed=args.seed, device="cpu").numpy()
@@ -303,7 +319,7 @@ def main():
     # ---- CPU baseline: the reference decoder on this box's cores, bounded sample of the same batch -------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         Sc = min(S, max(cores, min(2 * cores, 32)))
         nc = min(n, 10_000_000)
         sub = iq[:Sc, :nc].cpu().numpy()

@@ -150,3 +150,22 @@ def test_reference_regression_tool_links_against_the_b200_decoder(tmp_path):
         shutil.copyfile(os.path.join(U.GOLDEN, name + ".json"), tmp_path / (name + ".json"))
     out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=900).stdout
     assert out.count("PASS") == 19 and "FAIL" not in out and "UPDATED" not in out, out
+
+
+@pytest.mark.skipif(U.ref_lib() is None, reason="oracle/_ref/libnfcref.so not built")
+@pytest.mark.parametrize("config", ["nfca106", "nfcb106", "nfca424", "mixed"])
+def test_synthetic_workloads_equal_reference(decoder, config):
+    """the benchmark's own streams (BASELINE.json configs 2-5 shapes), float2 IQ, 8 streams x 1.5e6 samples as one batch:
+    every frame of every stream == the compiled reference on sqrtf(I*I+Q*Q) of the same data"""
+    import nfc_laboratory_b200 as N
+    from nfc_laboratory_b200 import synth as Y
+    iq = Y.synth_batch(config, 8, 1_500_000, seed=77).numpy()
+    frames = decoder.decode_batch(iq, N.SIG_IQ_F32, 10_000_000)
+    total = 0
+    for s in range(iq.shape[0]):
+        mag = np.empty(iq.shape[1], np.float32)
+        U.ref_lib().nfcref_iq_magnitude(np.ascontiguousarray(iq[s]).ctypes.data, mag.size, mag.ctypes.data)
+        ref = U.ref_decode(mag, 10_000_000)
+        total += sum(1 for f in ref if f[1] in (0x102, 0x103))
+        assert [f.key() for f in frames if f.stream == s] == ref, (config, s)
+    assert total >= 8 * 10
