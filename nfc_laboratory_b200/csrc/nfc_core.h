@@ -195,7 +195,19 @@ NFC_HD bool odd_parity_ok(u32 value, u32 parity)
 // lane machine.  STRIDE = 1 on the host, 32 on the device (scratch words of the 32 lanes of a warp are interleaved).
 // SINK must provide: void frame(const FrameOut &f, const u8 *payload)
 // ---------------------------------------------------------------------------------------------------------------------
-template <int STRIDE, class SINK>
+// TAPS selects how the search-mode detectors fetch their ring taps (device latency hiding, no semantics):
+//   0  where the reference reads them (one dependent ring access after the other)
+//   1  same, after prefetch hints for the NEXT step's taps were issued at the top of the step
+//   2  all taps of the step are loaded up front (independent loads in flight together) and handed to the detectors
+struct SearchTaps
+{
+   float xa0[3], xa1[3], ca2[3], ca3[3]; // NFC-A: x[t-sdd], x[t-sdd-p2], C[fp2], C[fp3] per rate
+   float wb[2];                          // NFC-B: w[t-sdd] per rate
+   float xf1[2], cf2[2], cf3[2];         // NFC-F 212 / 424: x[t-p2], C[fp2], C[fp3]
+   float xv0, xv1, cv2;                  // NFC-V: x[t-sdd], x[t-sdd-p2], C[fp2]
+};
+
+template <int STRIDE, class SINK, int TAPS = 0>
 struct Machine
 {
    const Params &P;
@@ -203,8 +215,11 @@ struct Machine
    float *rg; // lane scratch (already offset by the lane index on the device)
    u8 *sb;    // 512-byte stream buffer
    SINK &sink;
+   SearchTaps T;      // TAPS == 2: this step's taps
+   bool tapsValid;    // TAPS == 2: T was loaded for this step
+   float curX, curW;  // sample and edge value of the current step (ring slot of delay 0)
 
-   NFC_HD Machine(const Params &p, Lane &l, float *r, u8 *s, SINK &k) : P(p), L(l), rg(r), sb(s), sink(k)
+   NFC_HD Machine(const Params &p, Lane &l, float *r, u8 *s, SINK &k) : P(p), L(l), rg(r), sb(s), sink(k), tapsValid(false), curX(0), curW(0)
    {
    }
 
@@ -331,7 +346,8 @@ struct Machine
    // ------------------------------------------------------------------------------------------------------------------
    // front end: NfcDecoderStatus::nextSample, NfcTech.cpp:28-105
    // ------------------------------------------------------------------------------------------------------------------
-   NFC_HD void front(float x)
+   // clock and ring phases of the new sample (first half of nextSample: everything that does not need the value)
+   NFC_HD void front_advance()
    {
       Front &f = L.fe;
 
@@ -350,6 +366,11 @@ struct Machine
          f.cV1 = 0;
       if (++f.cV0 == P.V.p0)
          f.cV0 = 0;
+   }
+
+   NFC_HD void front(float x)
+   {
+      Front &f = L.fe;
 
       // NfcTech.cpp:39-42: signalDiff = abs(x - env) / env; gate = signalDiff < 0.05f.  The IEEE division is only
       // executed when the quotient is within 2 % of the threshold; outside that band the comparison is decided by
@@ -391,6 +412,8 @@ struct Machine
       // in listen mode, and depth_at() evaluates the reference expression from the stored x and envelope when it is
       SMP(NFCB200_OFF_X, 0) = x;
       SMP(NFCB200_OFF_W, 0) = w;
+      curX = x;
+      curW = w;
       SMP(NFCB200_OFF_D, 0) = f.dev;
       SMP(NFCB200_OFF_M, 0) = f.env;
 
@@ -494,13 +517,16 @@ struct Machine
          corr_points(fp1, b.p1, b.p2, fp2, fp3);
 
          // :246-250
-         m.filterIntegrate += SMP(NFCB200_OFF_X, b.sdd);
-         m.filterIntegrate -= SMP(NFCB200_OFF_X, b.sdd + b.p2);
+         const bool hoisted = TAPS == 2 && tapsValid;
+         m.filterIntegrate += hoisted ? (b.sdd ? T.xa0[rate] : curX) : SMP(NFCB200_OFF_X, b.sdd);
+         m.filterIntegrate -= hoisted ? T.xa1[rate] : SMP(NFCB200_OFF_X, b.sdd + b.p2);
          RG(b.corr, fp1) = m.filterIntegrate;
 
          // :253-255
-         float s0 = m.filterIntegrate - RG(b.corr, fp2);
-         float s1 = RG(b.corr, fp2) - RG(b.corr, fp3);
+         const float c2 = hoisted ? T.ca2[rate] : RG(b.corr, fp2);
+         const float c3 = hoisted ? T.ca3[rate] : RG(b.corr, fp3);
+         float s0 = m.filterIntegrate - c2;
+         float s1 = c2 - c3;
 
          // idle fast path (not in the reference): with no search state pending, the rest of this iteration only acts when
          // correlatedSD < -minimumCorrelationValue (:291).  (s0 - s1) / p2 < -T needs s0 - s1 < -T p2 (1 - ulp): anything
@@ -1642,7 +1668,7 @@ struct Machine
          const RateParams &b = P.B[rate];
          Mod &m = L.c.mB[rate];
 
-         float edge = SMP(NFCB200_OFF_W, b.sdd);
+         float edge = (TAPS == 2 && tapsValid) ? (b.sdd ? T.wb[rate] : curW) : SMP(NFCB200_OFF_W, b.sdd);
 
          // idle fast path (not in the reference): with no SOF search pending the iteration only acts on a falling edge
          // below -envelope * minimumModulationDeep (:283); the per-sample rewrite of searchValueThreshold (:280) is dead
@@ -2376,8 +2402,9 @@ struct Machine
          const RateParams &b = P.F[rate];
          Mod &m = L.c.mF[rate - 1];
 
-         m.filterIntegrate += SMP(NFCB200_OFF_X, b.sdd);
-         m.filterIntegrate -= SMP(NFCB200_OFF_X, b.sdd + b.p2);
+         const bool hoisted = TAPS == 2 && tapsValid;
+         m.filterIntegrate += (hoisted && b.sdd == 0) ? curX : SMP(NFCB200_OFF_X, b.sdd);
+         m.filterIntegrate -= hoisted ? T.xf1[rate - 1] : SMP(NFCB200_OFF_X, b.sdd + b.p2);
 
          // idle fast path (not in the reference): with no search window pending (the residual pulse counter / threshold
          // only matter at a window end) the iteration only acts when correlatedSD > minimumCorrelationValue (:277); the
@@ -2388,8 +2415,10 @@ struct Machine
             const u32 fq1 = L.fe.cF[rate - 1];
             corr_points(fq1, b.p1, b.p2, fq2, fq3);
             RG(b.corr, fq1) = m.filterIntegrate;
-            float q0 = m.filterIntegrate - RG(b.corr, fq2);
-            float q1 = RG(b.corr, fq2) - RG(b.corr, fq3);
+            const float c2 = hoisted ? T.cf2[rate - 1] : RG(b.corr, fq2);
+            const float c3 = hoisted ? T.cf3[rate - 1] : RG(b.corr, fq3);
+            float q0 = m.filterIntegrate - c2;
+            float q1 = c2 - c3;
             if (fabsf(q0 - q1) < 0.5f * minimumCorrelationValue * (float) b.p2)
                continue;
          }
@@ -2756,14 +2785,16 @@ struct Machine
       if (fp2 >= b.p1)
          fp2 -= b.p1;
 
-      signalData = SMP(NFCB200_OFF_X, b.sdd);
+      const bool hoisted = TAPS == 2 && tapsValid && L.lock == LOCK_NONE;
+
+      signalData = hoisted ? T.xv0 : SMP(NFCB200_OFF_X, b.sdd);
 
       m.filterIntegrate += signalData;
-      m.filterIntegrate -= SMP(NFCB200_OFF_X, b.sdd + b.p2);
+      m.filterIntegrate -= hoisted ? T.xv1 : SMP(NFCB200_OFF_X, b.sdd + b.p2);
 
       RG(b.corr, fp1) = m.filterIntegrate;
 
-      return (RG(b.corr, fp2) - m.filterIntegrate) / (float) b.p2;
+      return ((hoisted ? T.cv2 : RG(b.corr, fp2)) - m.filterIntegrate) / (float) b.p2;
    }
 
    // NfcV::Impl::detectModulation, NfcV.cpp:236-435
@@ -3270,12 +3301,13 @@ struct Machine
    }
 
    // ------------------------------------------------------------------------------------------------------------------
-   // software prefetch of the ring taps the detectors will read NFCB200_PF steps from now.  Every tap is at least 12
-   // samples old when it is read (smallest delay: period2 of the 424k detectors), so the slots already hold their final
-   // value; a lone lane (warp) is otherwise bound by one L2 round trip per dependent tap.  Device only, no semantics.
+   // latency hiding for the ring taps (device; no semantics).  A lone ring access costs an L2 / HBM round trip: the lane
+   // scratch of all resident warps (852 kB per warp) is far larger than the caches, and every tap is its own 128-byte
+   // line (32 lanes x 4 bytes).  All taps of search mode are at least one step old when they are read (the smallest
+   // delay is period2 of the 424k detectors; slot c - 1 of a correlation ring was written by the previous step), so they
+   // can be fetched before the front end runs: TAPS == 2 loads them into registers back to back (one round trip for
+   // all instead of one each), TAPS == 1 issues prefetch hints for the next step.
    // ------------------------------------------------------------------------------------------------------------------
-#define NFCB200_PF 8
-
    NFC_HD void prefetch_slot(u32 off, u32 index)
    {
 #if defined(__CUDA_ARCH__)
@@ -3287,53 +3319,91 @@ struct Machine
 #endif
    }
 
-   NFC_HD void prefetch_sample(u32 off, u32 delay)
+   NFC_HD static u32 wrap(u32 slot, u32 period)
    {
-      if (delay > NFCB200_PF)
-         prefetch_slot(off, (L.fe.k + L.fe.kbase + NFCB200_PF - delay) & (NFCB200_RING - 1));
+      return slot >= period ? slot - period : slot;
    }
 
-   NFC_HD void prefetch_corr(const RateParams &b, u32 c, u32 period, u32 shift)
+   // ring slot of the sample `delay` steps before the step `ahead` steps from now (front_advance() already ran)
+   NFC_HD u32 slot_at(u32 delay, u32 ahead) const
    {
-      // slot (c + PF + shift) mod period, the one correlated against PF steps from now
-      u32 slot = c + NFCB200_PF + shift;
-      while (slot >= period)
-         slot -= period;
-      prefetch_slot(b.corr, slot);
+      return (L.fe.k + L.fe.kbase + ahead - delay) & (NFCB200_RING - 1);
    }
 
-   NFC_HD void prefetch_taps()
+   NFC_HD void load_search_taps()
+   {
+      for (int r = 0; r < 3; r++)
+      {
+         const RateParams &b = P.A[r];
+         const u32 c = L.fe.cA[r];
+         T.xa0[r] = b.sdd ? RG(NFCB200_OFF_X, slot_at(b.sdd, 0)) : 0.0f;
+         T.xa1[r] = RG(NFCB200_OFF_X, slot_at(b.sdd + b.p2, 0));
+         T.ca2[r] = RG(b.corr, wrap(c + b.p2, b.p1));
+         T.ca3[r] = RG(b.corr, c ? c - 1 : b.p1 - 1);
+      }
+      for (int r = 0; r < 2; r++)
+         T.wb[r] = P.B[r].sdd ? RG(NFCB200_OFF_W, slot_at(P.B[r].sdd, 0)) : 0.0f;
+      for (int r = 1; r <= 2; r++)
+      {
+         const RateParams &b = P.F[r];
+         const u32 c = L.fe.cF[r - 1];
+         T.xf1[r - 1] = RG(NFCB200_OFF_X, slot_at(b.sdd + b.p2, 0));
+         T.cf2[r - 1] = RG(b.corr, wrap(c + b.p2, b.p1));
+         T.cf3[r - 1] = RG(b.corr, c ? c - 1 : b.p1 - 1);
+      }
+      T.xv0 = RG(NFCB200_OFF_X, slot_at(P.V.sdd, 0));
+      T.xv1 = RG(NFCB200_OFF_X, slot_at(P.V.sdd + P.V.p2, 0));
+      T.cv2 = RG(P.V.corr, wrap(L.fe.cV1 + P.V.p2, P.V.p1));
+   }
+
+   // hints for the taps of the NEXT step (ring phases advance by one; slot c of a correlation ring, read as c - 1 by the
+   // next step, is written by this one and stays cached)
+   NFC_HD void prefetch_next_taps()
    {
 #if defined(__CUDA_ARCH__)
       if (L.lock == LOCK_NONE)
       {
          for (int r = 0; r < 3; r++)
          {
-            prefetch_sample(NFCB200_OFF_X, P.A[r].sdd);
-            prefetch_sample(NFCB200_OFF_X, P.A[r].sdd + P.A[r].p2);
-            prefetch_corr(P.A[r], L.fe.cA[r], P.A[r].p1, P.A[r].p2);
+            const RateParams &b = P.A[r];
+            if (b.sdd)
+               prefetch_slot(NFCB200_OFF_X, slot_at(b.sdd, 1));
+            prefetch_slot(NFCB200_OFF_X, slot_at(b.sdd + b.p2, 1));
+            prefetch_slot(b.corr, wrap(wrap(L.fe.cA[r] + 1, b.p1) + b.p2, b.p1));
          }
-         prefetch_sample(NFCB200_OFF_W, P.B[1].sdd);
+         if (P.B[1].sdd)
+            prefetch_slot(NFCB200_OFF_W, slot_at(P.B[1].sdd, 1));
          for (int r = 1; r <= 2; r++)
          {
-            prefetch_sample(NFCB200_OFF_X, P.F[r].p2);
-            prefetch_corr(P.F[r], L.fe.cF[r - 1], P.F[r].p1, P.F[r].p2);
+            const RateParams &b = P.F[r];
+            prefetch_slot(NFCB200_OFF_X, slot_at(b.sdd + b.p2, 1));
+            prefetch_slot(b.corr, wrap(wrap(L.fe.cF[r - 1] + 1, b.p1) + b.p2, b.p1));
          }
-         prefetch_sample(NFCB200_OFF_X, P.V.sdd);
-         prefetch_sample(NFCB200_OFF_X, P.V.sdd + P.V.p2);
-         prefetch_corr(P.V, L.fe.cV1, P.V.p1, P.V.p2);
+         prefetch_slot(NFCB200_OFF_X, slot_at(P.V.sdd, 1));
+         prefetch_slot(NFCB200_OFF_X, slot_at(P.V.sdd + P.V.p2, 1));
+         prefetch_slot(P.V.corr, wrap(wrap(L.fe.cV1 + 1, P.V.p1) + P.V.p2, P.V.p1));
       }
       else
       {
-         const RateParams &b = locked_rate();
-         prefetch_sample(NFCB200_OFF_X, b.sdd);
-         prefetch_sample(NFCB200_OFF_X, b.sdd + b.p2);
-         prefetch_sample(NFCB200_OFF_W, b.sdd);
-         prefetch_sample(NFCB200_OFF_W, b.sdd + b.p1);
-         prefetch_sample(NFCB200_OFF_I, b.sdd + b.p2);
-         prefetch_sample(NFCB200_OFF_I, b.sdd + b.p4);
-         prefetch_sample(NFCB200_OFF_I, b.sdd + b.p1);
+         prefetch_locked_taps(1);
       }
+#endif
+   }
+
+   // the symbol decoders of a locked lane read a handful of taps at fixed delays of their own rate
+   NFC_HD void prefetch_locked_taps(u32 ahead)
+   {
+#if defined(__CUDA_ARCH__)
+      const RateParams &b = locked_rate();
+      prefetch_slot(NFCB200_OFF_X, slot_at(b.sdd, ahead));
+      prefetch_slot(NFCB200_OFF_X, slot_at(b.sdd + b.p2, ahead));
+      prefetch_slot(NFCB200_OFF_W, slot_at(b.sdd, ahead));
+      prefetch_slot(NFCB200_OFF_W, slot_at(b.sdd + b.p1, ahead));
+      prefetch_slot(NFCB200_OFF_I, slot_at(b.sdd + b.p2, ahead));
+      prefetch_slot(NFCB200_OFF_I, slot_at(b.sdd + b.p4, ahead));
+      prefetch_slot(NFCB200_OFF_I, slot_at(b.sdd + b.p1, ahead));
+#else
+      (void) ahead;
 #endif
    }
 
@@ -3342,6 +3412,24 @@ struct Machine
    // ------------------------------------------------------------------------------------------------------------------
    NFC_HD void step(float x)
    {
+      front_advance();
+
+      if (TAPS == 2)
+      {
+         // search mode with the detectors past their gate: fetch every tap now (the envelope gate below is decided by
+         // this step's sample, an unused fetch is harmless); locked lanes get hints for the next step
+         tapsValid = L.lock == LOCK_NONE && !(L.fe.k - 1 < L.gate);
+         if (tapsValid)
+            load_search_taps();
+         else if (L.lock != LOCK_NONE)
+            prefetch_locked_taps(1);
+      }
+      else if (TAPS == 1)
+      {
+         if (L.lock != LOCK_NONE || !(L.fe.k < L.gate))
+            prefetch_next_taps();
+      }
+
       front(x);
 
       if (L.lock == LOCK_NONE)

@@ -116,6 +116,44 @@ __device__ __forceinline__ float load_sample(const void *samples, int sigtype, u
    }
 }
 
+// the same in two halves: the raw load can be issued a whole step before the value is needed (the IEEE square root
+// would otherwise wait for it on the spot)
+__device__ __forceinline__ float2 load_raw(const void *samples, int sigtype, uint64_t idx)
+{
+   switch (sigtype)
+   {
+      case SIG_IQ_F32:
+         return __ldg(((const float2 *) samples) + idx);
+      case SIG_MAG_F32:
+         return make_float2(__ldg(((const float *) samples) + idx), 0.0f);
+      case SIG_MAG_S16:
+         return make_float2((float) __ldg(((const short *) samples) + idx), 0.0f);
+      default:
+      {
+         short2 v = __ldg(((const short2 *) samples) + idx);
+         return make_float2((float) v.x, (float) v.y);
+      }
+   }
+}
+
+__device__ __forceinline__ float mag_from_raw(int sigtype, float2 raw)
+{
+   switch (sigtype)
+   {
+      case SIG_IQ_F32:
+         return sqrtf(raw.x * raw.x + raw.y * raw.y);
+      case SIG_MAG_F32:
+         return raw.x;
+      case SIG_MAG_S16:
+         return raw.x / 32768.0f;
+      default:
+      {
+         float I = raw.x / 32768.0f, Q = raw.y / 32768.0f;
+         return sqrtf(I * I + Q * Q);
+      }
+   }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // segments
 // ---------------------------------------------------------------------------------------------------------------------
@@ -341,7 +379,9 @@ struct LaneConfig
 
 #define LANE_THREADS 128
 
-__global__ void __launch_bounds__(LANE_THREADS, 4) lanes_kernel(LaneConfig c, const __grid_constant__ Params dP)
+// TAPS: how the detectors fetch their ring taps (nfc_core.h); MINB: resident blocks per SM the register budget is cut for
+template <int TAPS, int MINB>
+__global__ void __launch_bounds__(LANE_THREADS, MINB) lanes_kernel(LaneConfig c, const __grid_constant__ Params dP)
 {
    const uint32_t lane = threadIdx.x & 31;
    const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -380,7 +420,7 @@ __global__ void __launch_bounds__(LANE_THREADS, 4) lanes_kernel(LaneConfig c, co
       if (have)
          lane_begin(L, dP, R.in, R.first, NFCB200_HALO);
 
-      Machine<32, DeviceSink> M(dP, L, rg, sb, sink);
+      Machine<32, DeviceSink, TAPS> M(dP, L, rg, sb, sink);
 
       const uint64_t streamBase = have ? (uint64_t) R.stream * c.n_samples : 0;
       const uint8_t *flags = c.flags + (have ? (size_t) R.stream * c.n_blocks : 0);
@@ -391,7 +431,19 @@ __global__ void __launch_bounds__(LANE_THREADS, 4) lanes_kernel(LaneConfig c, co
       uint32_t stepped = 0;
       bool running = have;
 
-      auto load = [&](uint32_t p) { return load_sample(c.samples, c.sigtype, streamBase + p); };
+      // the raw sample of the next step is requested one step ahead: every lane walks its own stream, so a warp touches 32
+      // different lines and some lane misses the cache on almost every step
+      float2 pend = make_float2(0.0f, 0.0f);
+      uint32_t pendPos = 0xFFFFFFFFu;
+      auto load = [&](uint32_t p) {
+         const float2 raw = p == pendPos ? pend : load_raw(c.samples, c.sigtype, streamBase + p);
+         if (p + 1 < n)
+         {
+            pend = load_raw(c.samples, c.sigtype, streamBase + p + 1);
+            pendPos = p + 1;
+         }
+         return mag_from_raw(c.sigtype, raw);
+      };
       auto active = [&](uint32_t p) { return (flags[p >> 8] & SCR_ACTIVE) != 0; };
       auto zero = [&]() {
          for (uint32_t i = NFCB200_OFF_CA; i < NFCB200_SCRATCH_FLOATS; i++)

@@ -33,7 +33,7 @@ namespace nfcb200 {
 // sample formats accepted at the boundary (hw/SignalType.h:27-36 for 1 and 2; 3 and 4 are WAV ingest, RecordDevice.cpp:281-311)
 enum { SIG_IQ_F32 = 1, SIG_MAG_F32 = 2, SIG_MAG_S16 = 3, SIG_IQ_S16 = 4 };
 
-__host__ __device__ inline uint32_t sig_bytes(int sigtype)
+__host__ __device__ constexpr inline uint32_t sig_bytes(int sigtype)
 {
    return sigtype == SIG_IQ_F32 ? 8 : sigtype == SIG_MAG_F32 ? 4 : sigtype == SIG_MAG_S16 ? 2 : 4;
 }
@@ -61,38 +61,47 @@ __device__ __forceinline__ float sample_from_raw(const void *tile, int sigtype, 
    }
 }
 
-// magnitude for SCREENING only: approximate reciprocal square root (2 ulp) instead of the IEEE sqrt sequence; the exact
-// decoder lanes recompute the magnitude with sample_from_raw / load_sample
-__device__ __forceinline__ float screen_mag(const void *tile, int sigtype, uint32_t i)
+// magnitude for SCREENING only: one fused multiply-add and the approximate square root (MUFU) instead of the IEEE
+// sequence; the exact decoder lanes recompute the magnitude with sample_from_raw / load_sample
+__device__ __forceinline__ float approx_sqrt(float p)
 {
-   switch (sigtype)
+   float r;
+   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+   return r;
+}
+
+template <int SIG>
+__device__ __forceinline__ float screen_mag(const void *tile, uint32_t i)
+{
+   if (SIG == SIG_IQ_F32)
    {
-      case SIG_IQ_F32:
-      {
-         float2 v = ((const float2 *) tile)[i];
-         float p = v.x * v.x + v.y * v.y;
-         return p * rsqrtf(fmaxf(p, 1e-30f));
-      }
-      case SIG_MAG_F32:
-         return ((const float *) tile)[i];
-      case SIG_MAG_S16:
-         return (float) ((const short *) tile)[i] * (1.0f / 32768.0f);
-      default:
-      {
-         short2 v = ((const short2 *) tile)[i];
-         float I = (float) v.x * (1.0f / 32768.0f), Q = (float) v.y * (1.0f / 32768.0f);
-         float p = I * I + Q * Q;
-         return p * rsqrtf(fmaxf(p, 1e-30f));
-      }
+      float2 v = ((const float2 *) tile)[i];
+      return approx_sqrt(__fmaf_rn(v.y, v.y, v.x * v.x));
+   }
+   else if (SIG == SIG_MAG_F32)
+   {
+      return ((const float *) tile)[i];
+   }
+   else if (SIG == SIG_MAG_S16)
+   {
+      return (float) ((const short *) tile)[i] * (1.0f / 32768.0f);
+   }
+   else
+   {
+      short2 v = ((const short2 *) tile)[i];
+      float I = (float) v.x * (1.0f / 32768.0f), Q = (float) v.y * (1.0f / 32768.0f);
+      return approx_sqrt(__fmaf_rn(Q, Q, I * I));
    }
 }
 
 #define SCR_THREADS 256
+#define SCR_WARPS (SCR_THREADS / 32)
 #define SCR_PER_THREAD 17
 #define SCR_SPAN (SCR_THREADS * SCR_PER_THREAD)   /* 4352 samples staged per tile            */
 #define SCR_HALO 512                               /* history before the tile's own samples   */
 #define SCR_TILE (SCR_SPAN - SCR_HALO)             /* 3840 = 15 blocks of 256 own samples     */
 #define SCR_TILE_BLOCKS (SCR_TILE / NFCB200_BLOCK)
+#define SCR_WARP_SPAN (32 * SCR_PER_THREAD)        /* 544 consecutive samples per warp        */
 
 struct ScreenConfig
 {
@@ -110,6 +119,7 @@ struct ScreenConfig
    float thrA[3];          // |C[t] - C[t-q]| > thrA[r] * envelope flags rate r (see the derivation in the kernel)
    float thrV;             // same for the NFC-V pulse correlator
    float kB;               // |w| > kB * envelope flags an NFC-B edge
+   float quiet;            // a warp span whose sample range is <= quiet * (its minimum) cannot trigger any test
    int use_tma;
 };
 
@@ -152,18 +162,30 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                 : "memory");
 }
 
+// warp-wide min / max of a float through the integer reduction unit (redux.sync): order-preserving key
+__device__ __forceinline__ uint32_t float_key(float f)
+{
+   uint32_t u = __float_as_uint(f);
+   return u ^ ((uint32_t) ((int32_t) u >> 31) | 0x80000000u);
+}
+
+__device__ __forceinline__ float key_float(uint32_t k)
+{
+   uint32_t u = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+   return __uint_as_float(u);
+}
+
 // ---- the kernel --------------------------------------------------------------------------------------------------------
 
 struct ScreenSmem
 {
    // raw staging, two stages, 16-byte aligned; sized for the widest format (float2)
    unsigned char raw[2][SCR_SPAN * 8];
-   float P[SCR_SPAN + 1];   // mean-removed inclusive prefix sum, P[0] = 0
-   float warpAgg[8];        // cross-warp scan scratch (prefix)
-   float warpA[8], warpB[8];// cross-warp scan scratch (affine)
-   float lastX[8];          // last magnitude of every warp (x[n-1] of the next warp's first sample)
-   float envB[SCR_TILE_BLOCKS]; // per-block envelope reference
-   uint32_t blockHit[SCR_TILE_BLOCKS];
+   float P[SCR_SPAN + 1];       // inclusive prefix sum of the staged magnitudes, P[0] = 0
+   float warpAgg[SCR_WARPS];    // sum of every warp's 544 samples
+   float warpW[SCR_WARPS];      // IIR state at the end of every warp's span
+   float warpMin[SCR_WARPS], warpMax[SCR_WARPS];
+   uint32_t blockHit[SCR_TILE_BLOCKS + 1];
    uint64_t bar[2];
 };
 
@@ -173,6 +195,27 @@ struct ScreenTaps
    float t0, t1, t2, tv, tb;
 };
 
+// 0.9^(i+1): what is left after i + 1 samples of the IIR state that entered a thread's chunk
+__device__ __forceinline__ constexpr float iir_decay(int i)
+{
+   constexpr float d[SCR_PER_THREAD] = {0.9f,          0.81f,         0.729f,        0.6561f,       0.59049f,      0.531441f,
+                                        0.4782969f,    0.43046721f,   0.387420489f,  0.3486784401f, 0.3138105961f, 0.2824295365f,
+                                        0.2541865828f, 0.2287679245f, 0.2058911321f, 0.1853020189f, 0.166771817f};
+   return d[i];
+}
+
+#define SCR_IIR_CHUNK 0.166771817f /* 0.9^17: decay of the IIR state over one thread chunk */
+
+// envelope reference of tile block b: min(mean of the block, mean of the previous block) -- in idle both equal the
+// reference's envelope EMA to within the noise; during a pause the smaller one only makes the tests stricter
+__device__ __forceinline__ float block_env(const float *P, int b)
+{
+   const int bslot = SCR_HALO + (b << 8);
+   const float p0 = P[bslot - NFCB200_BLOCK], p1 = P[bslot], p2 = P[bslot + NFCB200_BLOCK];
+   const float env = fminf(p2 - p1, p1 - p0) * (1.0f / NFCB200_BLOCK);
+   return env < 0 ? 0 : env;
+}
+
 /*
  * Trigger tests of one thread's 17 consecutive own samples, branch-free.
  * Evaluation density: 424k window every sample, 212k at chunk offsets 0, 2, .., 16, 106k at 0, 4, .., 16, NFC-V at 0, 8,
@@ -180,13 +223,12 @@ struct ScreenTaps
  * |C[t] - C[t - q]| can undergo between evaluations (2 xmax per sample).  Chunk-relative phases keep every warp uniform.
  * The chunk spans at most two screening blocks: their envelope-scaled thresholds are formed once and selected per sample.
  */
-__device__ __forceinline__ void screen_tests(ScreenSmem &s, const ScreenTaps &tp, int first, float exclPref, float wCarry, const float (&loc)[SCR_PER_THREAD],
-                                             const float (&wl)[SCR_PER_THREAD])
+__device__ __forceinline__ void screen_tests(ScreenSmem &s, const ScreenTaps &tp, int first, float wCarry, const float (&wl)[SCR_PER_THREAD])
 {
    const int blkA = (first - SCR_HALO) >> 8;
    const int blkB = (first + SCR_PER_THREAD - 1 - SCR_HALO) >> 8;
    const int split = SCR_HALO + (blkB << 8) - first; // samples i < split belong to blkA (split >= 17 when blkA == blkB)
-   const float envA = s.envB[blkA], envB = s.envB[blkB];
+   const float envA = block_env(s.P, blkA), envB = blkB == blkA ? envA : block_env(s.P, blkB);
 
    const float bA = tp.tb * envA, bB = tp.tb * envB;
    const float a2A = tp.t2 * envA, a2B = tp.t2 * envB;
@@ -197,16 +239,14 @@ __device__ __forceinline__ void screen_tests(ScreenSmem &s, const ScreenTaps &tp
    const float *P = s.P + first + 1; // P[i] = inclusive prefix at the chunk's i-th sample
 
    bool hitA = false, hitB = false;
-   float decay = 1.0f; // 0.9^(i + 1): what is left of the IIR state that entered the chunk
 
 #pragma unroll
    for (int i = 0; i < SCR_PER_THREAD; i++)
    {
       const bool inA = i < split;
-      const float Pt = exclPref + loc[i];
+      const float Pt = P[i];
 
-      decay *= 0.9f;
-      bool hit = fabsf(wl[i] + decay * wCarry) > (inA ? bA : bB);
+      bool hit = fabsf(__fmaf_rn(iir_decay(i), wCarry, wl[i])) > (inA ? bA : bB);
 
       hit |= fabsf((Pt - P[i - tp.p22]) - (P[i - tp.q2] - P[i - tp.q2 - tp.p22])) > (inA ? a2A : a2B);
 
@@ -237,11 +277,11 @@ struct TileGeom
    int64_t lo, hi; // valid samples [lo, hi)
 };
 
-__device__ __forceinline__ TileGeom tile_geom(const ScreenConfig &c, uint64_t item)
+__device__ __forceinline__ TileGeom tile_geom(const ScreenConfig &c, uint32_t stream, uint32_t tile)
 {
    TileGeom g;
-   g.stream = (uint32_t) (item / c.tiles_per_stream);
-   g.tile = (uint32_t) (item % c.tiles_per_stream);
+   g.stream = stream;
+   g.tile = tile;
    g.base = (int64_t) g.tile * SCR_TILE - SCR_HALO;
    g.lo = g.base < 0 ? 0 : g.base;
    g.hi = g.base + SCR_SPAN;
@@ -250,11 +290,12 @@ __device__ __forceinline__ TileGeom tile_geom(const ScreenConfig &c, uint64_t it
    return g;
 }
 
-__device__ __forceinline__ void tile_issue(const ScreenConfig &c, ScreenSmem &s, int stage, uint64_t item)
+template <int SIG>
+__device__ __forceinline__ void tile_issue(const ScreenConfig &c, ScreenSmem &s, int stage, uint32_t stream, uint32_t tile)
 {
    // one elected thread arms the barrier and launches the bulk copy of the valid part of the tile
-   TileGeom g = tile_geom(c, item);
-   uint32_t bs = sig_bytes(c.sigtype);
+   TileGeom g = tile_geom(c, stream, tile);
+   constexpr uint32_t bs = sig_bytes(SIG);
    const unsigned char *src = (const unsigned char *) c.samples + ((uint64_t) g.stream * c.n_samples + (uint64_t) g.lo) * bs;
    uint32_t bytes = (uint32_t) (g.hi - g.lo) * bs;
    uint32_t dstoff = (uint32_t) (g.lo - g.base) * bs;
@@ -266,7 +307,21 @@ __device__ __forceinline__ void tile_issue(const ScreenConfig &c, ScreenSmem &s,
       tma_load_1d(s.raw[stage] + dstoff, src, bulk, &s.bar[stage]);
 }
 
-__global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, uint64_t n_items)
+/*
+ * One persistent CTA walks the work items (stream, tile) blockIdx.x, blockIdx.x + gridDim.x, ...  Per tile:
+ *   phase 1  every thread: 17 magnitudes from the staged raw tile, thread-local prefix sum / IIR / min / max, warp scans
+ *   phase 2  cross-warp carries, prefix sums to shared memory, the warp's QUIET test
+ *   phase 3  warps that are not quiet: envelope per block, the sliding correlator and edge tests (shared-memory taps)
+ *   phase 4  15 threads write the tile's block flags and block sums
+ * Quiet test: every quantity phase 3 compares is bounded by the range of the samples it covers --
+ *   |C[t] - C[t-q]| <= p2 (max - min),   |w| <= max - min (w = x minus a weighted average of its past) --
+ * and every threshold is a multiple of a block mean >= min.  All taps of a warp's samples (<= 283 back), the means of
+ * their blocks (<= 511 back, <= 255 ahead) and the IIR memory (0.9^544 = 1e-25) lie within the warp's own span, the
+ * previous and the next one, so with hi / lo taken over those three spans no test can fire when hi - lo <= quiet * lo
+ * (quiet = 0.999 min(kB, thrA[r] / p2[r], thrV / vp2), host side).  On an idle carrier that is every warp.
+ */
+template <int SIG>
+__global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, uint32_t n_items)
 {
    extern __shared__ __align__(128) unsigned char smem_raw[];
    ScreenSmem &s = *reinterpret_cast<ScreenSmem *>(smem_raw);
@@ -274,7 +329,7 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
    const int tid = threadIdx.x;
    const int lane = tid & 31;
    const int warp = tid >> 5;
-   const uint32_t bs = sig_bytes(c.sigtype);
+   constexpr uint32_t bs = sig_bytes(SIG);
 
    if (c.use_tma && tid == 0)
    {
@@ -282,42 +337,76 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
       mbar_init(&s.bar[1], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
+   if (tid <= SCR_TILE_BLOCKS)
+      s.blockHit[tid] = 0;
    __syncthreads();
 
-   uint64_t item = blockIdx.x;
-   uint32_t phase[2] = {0, 0};
+   // (stream, tile) of the current item, advanced without divisions
+   const uint32_t tps = c.tiles_per_stream;
+   const uint32_t stepS = gridDim.x / tps, stepT = gridDim.x % tps;
+   uint32_t stream = blockIdx.x / tps, tile = blockIdx.x % tps;
+
+   uint32_t item = blockIdx.x;
+   uint32_t phaseBits = 0; // bit s: parity the barrier of stage s completes next
    int stage = 0;
 
    if (c.use_tma && tid == 0 && item < n_items)
-      tile_issue(c, s, 0, item);
+      tile_issue<SIG>(c, s, 0, stream, tile);
+
+   ScreenTaps tp;
+   tp.p20 = (int) c.p2[0];
+   tp.q0 = (int) (c.p1[0] - c.p2[0]);
+   tp.p21 = (int) c.p2[1];
+   tp.q1 = (int) (c.p1[1] - c.p2[1]);
+   tp.p22 = (int) c.p2[2];
+   tp.q2 = (int) (c.p1[2] - c.p2[2]);
+   tp.pv = (int) c.vp2;
+   tp.qv = (int) (c.vp1 - c.vp2);
+   tp.t0 = c.thrA[0];
+   tp.t1 = c.thrA[1];
+   tp.t2 = c.thrA[2];
+   tp.tv = c.thrV;
+   tp.tb = c.kB;
 
    for (; item < n_items; item += gridDim.x, stage ^= 1)
    {
-      TileGeom g = tile_geom(c, item);
+      const TileGeom g = tile_geom(c, stream, tile);
+
+      // next item
+      uint32_t nstream = stream + stepS, ntile = tile + stepT;
+      if (ntile >= tps)
+      {
+         ntile -= tps;
+         nstream++;
+      }
+
+      const uint32_t bytes = (uint32_t) (g.hi - g.lo) * bs;
+      const uint32_t bulk = bytes & ~15u;
 
       if (c.use_tma)
       {
-         // prefetch the next tile into the other stage, then wait for this one
-         uint64_t next = item + gridDim.x;
-         if (tid == 0 && next < n_items)
-            tile_issue(c, s, stage ^ 1, next);
+         // prefetch the next tile into the other stage (every thread finished reading it: it passed the last barrier of
+         // the previous iteration after its phase 1), then wait for this one
+         if (tid == 0 && item + gridDim.x < n_items)
+            tile_issue<SIG>(c, s, stage ^ 1, nstream, ntile);
 
-         mbar_wait(&s.bar[stage], phase[stage]);
-         phase[stage] ^= 1;
+         mbar_wait(&s.bar[stage], (phaseBits >> stage) & 1u);
+         phaseBits ^= 1u << stage;
 
          // ragged tail (< 16 bytes) of the last tile of a stream
-         uint32_t bytes = (uint32_t) (g.hi - g.lo) * bs;
-         uint32_t bulk = bytes & ~15u;
-         if (tid < (int) (bytes - bulk))
+         if (bytes != bulk)
          {
-            const unsigned char *src = (const unsigned char *) c.samples + ((uint64_t) g.stream * c.n_samples + (uint64_t) g.lo) * bs;
-            s.raw[stage][(uint32_t) (g.lo - g.base) * bs + bulk + tid] = src[bulk + tid];
+            if (tid < (int) (bytes - bulk))
+            {
+               const unsigned char *src = (const unsigned char *) c.samples + ((uint64_t) g.stream * c.n_samples + (uint64_t) g.lo) * bs;
+               s.raw[stage][(uint32_t) (g.lo - g.base) * bs + bulk + tid] = src[bulk + tid];
+            }
+            __syncthreads();
          }
       }
       else
       {
          // plain coalesced 16-byte loads (debug knob; same staging layout)
-         uint32_t bytes = (uint32_t) (g.hi - g.lo) * bs;
          const unsigned char *src = (const unsigned char *) c.samples + ((uint64_t) g.stream * c.n_samples + (uint64_t) g.lo) * bs;
          unsigned char *dst = s.raw[stage] + (uint32_t) (g.lo - g.base) * bs;
          uint32_t vec = bytes >> 4;
@@ -325,14 +414,10 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
             ((uint4 *) dst)[i] = __ldg(((const uint4 *) src) + i);
          for (uint32_t i = (vec << 4) + tid; i < bytes; i += SCR_THREADS)
             dst[i] = src[i];
+         __syncthreads();
       }
 
-      if (tid < SCR_TILE_BLOCKS)
-         s.blockHit[tid] = 0;
-
-      __syncthreads();
-
-      // ---- per-thread chunk: magnitude, local prefix, local IIR ------------------------------------------------------
+      // ---- phase 1: per-thread chunk: magnitude, local prefix, local IIR, range -------------------------------------
       const int validLo = (int) (g.lo - g.base); // slots below hold no data (stream start): replicate the first sample
       const int validHi = (int) (g.hi - g.base); // slots at / above hold no data (stream end): replicate the last sample
       const void *raw = s.raw[stage];
@@ -340,15 +425,14 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
 
       float xs[SCR_PER_THREAD];
       const int first = tid * SCR_PER_THREAD;
-
-      // reference level for the mean-removed prefix: the first valid sample of the staged span
-      const float mu = screen_mag(raw, c.sigtype, (uint32_t) validLo);
+      float prevx; // x[first - 1] (the chunk's own first sample at the very start of the tile: w starts from zero)
 
       if (whole)
       {
 #pragma unroll
          for (int i = 0; i < SCR_PER_THREAD; i++)
-            xs[i] = screen_mag(raw, c.sigtype, (uint32_t) (first + i));
+            xs[i] = screen_mag<SIG>(raw, (uint32_t) (first + i));
+         prevx = screen_mag<SIG>(raw, (uint32_t) (first ? first - 1 : 0));
       }
       else
       {
@@ -357,88 +441,63 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
          {
             int slot = first + i;
             slot = slot < validLo ? validLo : (slot >= validHi ? validHi - 1 : slot);
-            xs[i] = screen_mag(raw, c.sigtype, (uint32_t) slot);
+            xs[i] = screen_mag<SIG>(raw, (uint32_t) slot);
          }
+         int slot = first ? first - 1 : 0;
+         slot = slot < validLo ? validLo : (slot >= validHi ? validHi - 1 : slot);
+         prevx = screen_mag<SIG>(raw, (uint32_t) slot);
       }
 
-      // additive scan of (x - mu): thread-local inclusive prefix, then warp shuffle scan of the chunk totals
-      float loc[SCR_PER_THREAD];
-      float run = 0;
+      // thread-local inclusive prefix, IIR from a zero state, minimum and maximum
+      float loc[SCR_PER_THREAD], wl[SCR_PER_THREAD];
+      float run = 0, w = 0, mn = xs[0], mx = xs[0];
 #pragma unroll
       for (int i = 0; i < SCR_PER_THREAD; i++)
       {
-         run += xs[i] - mu;
+         run += xs[i];
          loc[i] = run;
+         w = __fmaf_rn(w, 0.9f, xs[i] - prevx); // w[n] = 0.9 w[n-1] + (x[n] - x[n-1])
+         prevx = xs[i];
+         wl[i] = w;
+         mn = fminf(mn, xs[i]);
+         mx = fmaxf(mx, xs[i]);
       }
 
-      float incl = run;
+      // warp scans over the 32 chunks: additive for the prefix; affine with the constant factor 0.9^17 for the IIR
+      float incl = run, sW = w, fac = SCR_IIR_CHUNK;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1)
       {
-         float o = __shfl_up_sync(0xffffffffu, incl, d);
+         const float o = __shfl_up_sync(0xffffffffu, incl, d);
+         const float ow = __shfl_up_sync(0xffffffffu, sW, d);
          if (lane >= d)
+         {
             incl += o;
+            sW = __fmaf_rn(fac, ow, sW);
+         }
+         fac *= fac;
       }
+
+      const float wmn = key_float(__reduce_min_sync(0xffffffffu, float_key(mn)));
+      const float wmx = key_float(__reduce_max_sync(0xffffffffu, float_key(mx)));
+
       if (lane == 31)
       {
          s.warpAgg[warp] = incl;
-         s.lastX[warp] = xs[SCR_PER_THREAD - 1];
+         s.warpW[warp] = sW; // the state that entered the warp has decayed by 0.9^544 = 1e-25: dropped
+         s.warpMin[warp] = wmn;
+         s.warpMax[warp] = wmx;
       }
 
-      // affine scan of w[n] = 0.9 w[n-1] + (x[n] - x[n-1]); thread-local with zero carry first.  x[n-1] of the first
-      // sample of a chunk comes from the previous thread (previous warp through shared memory)
-      float prevx = __shfl_up_sync(0xffffffffu, xs[SCR_PER_THREAD - 1], 1);
-      __syncthreads();
-      if (lane == 0)
-         prevx = warp ? s.lastX[warp - 1] : xs[0];
-
-      float wl[SCR_PER_THREAD];
-      float A = 1.0f, B;
-      {
-         float w = 0, px = prevx;
-#pragma unroll
-         for (int i = 0; i < SCR_PER_THREAD; i++)
-         {
-            w = w * 0.9f + (xs[i] - px);
-            px = xs[i];
-            wl[i] = w;
-            A *= 0.9f;
-         }
-         B = w;
-      }
-
-      // warp-level inclusive scan of the affine maps (A, B): compose(earlier, later) = (Ae * Al, Al * Be + Bl)
-      float sA = A, sB = B;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1)
-      {
-         float oA = __shfl_up_sync(0xffffffffu, sA, d);
-         float oB = __shfl_up_sync(0xffffffffu, sB, d);
-         if (lane >= d)
-         {
-            sB = sA * oB + sB;
-            sA = sA * oA;
-         }
-      }
-      if (lane == 31)
-      {
-         s.warpA[warp] = sA;
-         s.warpB[warp] = sB;
-      }
       __syncthreads();
 
-      // cross-warp carries (8 warps: serial, tiny)
-      float prefBase = 0, wCarryWarp = 0;
-      for (int v = 0; v < warp; v++)
-      {
-         prefBase += s.warpAgg[v];
-         wCarryWarp = s.warpA[v] * wCarryWarp + s.warpB[v];
-      }
+      // ---- phase 2: carries across warps, prefix to shared memory, quiet test ---------------------------------------
+      float prefBase = 0;
+#pragma unroll
+      for (int v = 0; v < SCR_WARPS - 1; v++)
+         prefBase += v < warp ? s.warpAgg[v] : 0.0f;
 
       const float exclPref = prefBase + (incl - run);
-      const float eA = __shfl_up_sync(0xffffffffu, sA, 1);
-      const float eB = __shfl_up_sync(0xffffffffu, sB, 1);
-      const float wCarry = lane ? (eA * wCarryWarp + eB) : wCarryWarp; // IIR state entering this thread's chunk
 
 #pragma unroll
       for (int i = 0; i < SCR_PER_THREAD; i++)
@@ -446,25 +505,22 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
       if (tid == 0)
          s.P[0] = 0;
 
-      if (tid < SCR_TILE_BLOCKS)
-         s.blockHit[tid] = 0;
+      // IIR state entering this thread's chunk: the warp scan's value of the previous lane plus what is left of the state
+      // that entered the warp, 0.9^(17 lane) (exp2 of lane * log2(0.9^17); approximate like everything in this screen)
+      const float eW = __shfl_up_sync(0xffffffffu, sW, 1);
+      const float wWarp = warp ? s.warpW[warp - 1] : 0.0f;
+      const float wCarry = __fmaf_rn(exp2f((float) lane * -2.5840526f), wWarp, lane ? eW : 0.0f);
+
+      // range over the previous, this and the next warp's span (the block of this warp's last samples reaches up to 255
+      // samples into the next span; the last warp ends on a block boundary)
+      const int wp = warp ? warp - 1 : 0, wn = warp < SCR_WARPS - 1 ? warp + 1 : warp;
+      const float lo = fminf(wmn, fminf(s.warpMin[wp], s.warpMin[wn]));
+      const float hi = fmaxf(wmx, fmaxf(s.warpMax[wp], s.warpMax[wn]));
+      const bool quiet = (hi - lo) <= c.quiet * lo;
 
       __syncthreads();
 
-      // envelope reference per block: min(mean of this block, mean of the previous block) -- in idle both equal the
-      // reference's envelope EMA to within the noise; during a pause the smaller one only makes the test stricter
-      if (tid < SCR_TILE_BLOCKS)
-      {
-         int bslot = SCR_HALO + (tid << 8);
-         float meanCur = (s.P[bslot + NFCB200_BLOCK] - s.P[bslot]) * (1.0f / NFCB200_BLOCK) + mu;
-         float meanPrev = (s.P[bslot] - s.P[bslot - NFCB200_BLOCK]) * (1.0f / NFCB200_BLOCK) + mu;
-         float env = fminf(meanCur, meanPrev);
-         s.envB[tid] = env < 0 ? 0 : env;
-      }
-
-      __syncthreads();
-
-      // ---- correlators and trigger tests on the tile's own samples ---------------------------------------------------
+      // ---- phase 3: correlators and trigger tests on the tile's own samples ------------------------------------------
       // With C[t] = P[t] - P[t - p2] (half-symbol moving sum) the reference's correlator is
       //    S0 - S1 = (C[t] - C[t - q]) - (C[t - q] - C[t - 1]) = 2 (C[t] - C[t - q]) - (x[t] - x[t - p2])
       // so  |S0 - S1| <= 2 |C[t] - C[t - q]| + xmax, and a detector needing |S0 - S1| / p2 > T env cannot trigger while
@@ -472,46 +528,30 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
       // One difference of two moving sums (3 shared-memory taps) per rate and sample.  The long windows change slowly
       // (by at most 2 xmax per sample), so the 212k correlator is evaluated on every 2nd sample, the 106k one on every
       // 4th and the NFC-V one on every 8th, with the thresholds lowered by the possible change in between.
+      if (!quiet)
       {
-         ScreenTaps tp;
-         tp.p20 = (int) c.p2[0];
-         tp.q0 = (int) (c.p1[0] - c.p2[0]);
-         tp.p21 = (int) c.p2[1];
-         tp.q1 = (int) (c.p1[1] - c.p2[1]);
-         tp.p22 = (int) c.p2[2];
-         tp.q2 = (int) (c.p1[2] - c.p2[2]);
-         tp.pv = (int) c.vp2;
-         tp.qv = (int) (c.vp1 - c.vp2);
-         tp.t0 = c.thrA[0];
-         tp.t1 = c.thrA[1];
-         tp.t2 = c.thrA[2];
-         tp.tv = c.thrV;
-         tp.tb = c.kB;
-
          const int ownEnd = (int) ((int64_t) c.n_samples - g.base); // first slot past the stream
          const int lastSlot = first + SCR_PER_THREAD - 1;
 
          if (first >= SCR_HALO && lastSlot < ownEnd)
          {
             // whole chunk inside the tile's own samples: branch-free tests
-            screen_tests(s, tp, first, exclPref, wCarry, loc, wl);
+            screen_tests(s, tp, first, wCarry, wl);
          }
          else if (lastSlot >= SCR_HALO && first < ownEnd)
          {
             // chunk straddling the halo boundary or the end of the stream: same tests, checked per sample, no decimation
-            float a = 1.0f;
 #pragma unroll
             for (int i = 0; i < SCR_PER_THREAD; i++)
             {
-               a *= 0.9f;
                const int slot = first + i;
                if (slot < SCR_HALO || slot >= ownEnd)
                   continue;
                const int blk = (slot - SCR_HALO) >> 8;
-               const float env = s.envB[blk];
+               const float env = block_env(s.P, blk);
                const int t = slot + 1;
                const float Pt = s.P[t];
-               bool hit = fabsf(wl[i] + a * wCarry) > tp.tb * env;
+               bool hit = fabsf(__fmaf_rn(iir_decay(i), wCarry, wl[i])) > tp.tb * env;
                hit |= fabsf((Pt - s.P[t - tp.p20]) - (s.P[t - tp.q0] - s.P[t - tp.q0 - tp.p20])) > tp.t0 * env;
                hit |= fabsf((Pt - s.P[t - tp.p21]) - (s.P[t - tp.q1] - s.P[t - tp.q1 - tp.p21])) > tp.t1 * env;
                hit |= fabsf((Pt - s.P[t - tp.p22]) - (s.P[t - tp.q2] - s.P[t - tp.q2 - tp.p22])) > tp.t2 * env;
@@ -524,20 +564,26 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
 
       __syncthreads();
 
+      // ---- phase 4: block flags and block sums of the tile ------------------------------------------------------------
       if (tid < SCR_TILE_BLOCKS)
       {
-         uint32_t b = g.tile * SCR_TILE_BLOCKS + tid;
+         const uint32_t b = g.tile * SCR_TILE_BLOCKS + tid;
+         const uint32_t hit = s.blockHit[tid];
+         s.blockHit[tid] = 0; // phase 3 of the next tile is two barriers away
          if (b < c.n_blocks)
          {
-            int bslot = SCR_HALO + (tid << 8);
-            c.flags[(uint64_t) g.stream * c.n_blocks + b] = s.blockHit[tid] ? SCR_TRIGGER : 0;
+            const int bslot = SCR_HALO + (tid << 8);
+            c.flags[(uint64_t) g.stream * c.n_blocks + b] = hit ? SCR_TRIGGER : 0;
             // block sum of x over the samples that exist (the replicated tail contributes nothing real: the last block
             // of a stream is always active through the trailing margin, so its sum is only used for the envelope)
-            c.bsum[(uint64_t) g.stream * c.n_blocks + b] = (s.P[bslot + NFCB200_BLOCK] - s.P[bslot]) + mu * NFCB200_BLOCK;
+            c.bsum[(uint64_t) g.stream * c.n_blocks + b] = s.P[bslot + NFCB200_BLOCK] - s.P[bslot];
          }
       }
 
-      __syncthreads(); // the staging buffer of this stage is free again before the next issue targets it
+      stream = nstream;
+      tile = ntile;
+      // no barrier here: P, blockHit and the warp aggregates are rewritten in phase 2 / after the first barrier of the
+      // next iteration, which every thread reaches only after this phase 4
    }
 }
 

@@ -129,6 +129,9 @@ struct nfcb200_handle
    cudaEvent_t copied[2] = {};
    cudaEvent_t ev[8] = {};
 
+   int laneTaps = 2;   // lanes_kernel variant: ring tap fetch mode (NFCB200_LANE_TAPS overrides, development knob)
+   int laneBlocks = 4; // resident lane blocks per SM (NFCB200_LANE_BLOCKS overrides)
+
    DevBuf samples, flags, bsum, counts, offsets, lanes, queue, scratch, sbuf, pool, ext, meta, streamOf, counters;
    nfcb200_stats stats;
 
@@ -173,6 +176,47 @@ static int setup_params(nfcb200_handle *h, u32 sampleRate)
    return 0;
 }
 
+// K2 launch: tap fetch mode x resident blocks per SM (register budget), chosen at create time
+static void launch_lanes(const nfcb200_handle *h, const LaneConfig &lc, u32 blocks, cudaStream_t st)
+{
+#define NFCB200_LANES(T, B) lanes_kernel<T, B><<<blocks, LANE_THREADS, 0, st>>>(lc, h->P)
+   const int b = h->laneBlocks;
+   switch (h->laneTaps)
+   {
+      case 0:
+         if (b >= 4) NFCB200_LANES(0, 4); else if (b == 3) NFCB200_LANES(0, 3); else NFCB200_LANES(0, 2);
+         break;
+      case 1:
+         if (b >= 4) NFCB200_LANES(1, 4); else if (b == 3) NFCB200_LANES(1, 3); else NFCB200_LANES(1, 2);
+         break;
+      default:
+         if (b >= 4) NFCB200_LANES(2, 4); else if (b == 3) NFCB200_LANES(2, 3); else NFCB200_LANES(2, 2);
+         break;
+   }
+#undef NFCB200_LANES
+}
+
+// K1 launch: one instantiation per sample format, persistent grid of 2 CTAs per SM
+static void launch_screen(const nfcb200_handle *h, const ScreenConfig &sc, uint32_t items, cudaStream_t st)
+{
+   const u32 grid = std::min<u32>(items, (u32) h->smCount * 2);
+   switch (sc.sigtype)
+   {
+      case SIG_IQ_F32:
+         screen_kernel<SIG_IQ_F32><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
+         break;
+      case SIG_MAG_F32:
+         screen_kernel<SIG_MAG_F32><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
+         break;
+      case SIG_MAG_S16:
+         screen_kernel<SIG_MAG_S16><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
+         break;
+      default:
+         screen_kernel<SIG_IQ_S16><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
+         break;
+   }
+}
+
 static void fill_screen_config(const nfcb200_handle *h, ScreenConfig &sc)
 {
    const Params &P = h->P;
@@ -205,6 +249,14 @@ static void fill_screen_config(const nfcb200_handle *h, ScreenConfig &sc)
       sc.thrA[r] = std::max(sc.thrA[r], 0.25f);
    sc.thrV = std::max(sc.thrV, 0.25f);
    sc.kB = margin * P.thr[TECH_B].modMin;
+   // quiet bound of a warp span (nfc_screen.cuh): no test can fire while max - min <= quiet * min
+   {
+      float q = sc.kB;
+      for (int r = 0; r < 3; r++)
+         q = std::min(q, sc.thrA[r] / (float) P.A[r].p2);
+      q = std::min(q, sc.thrV / (float) P.V.p2);
+      sc.quiet = 0.999f * q;
+   }
    sc.use_tma = h->cfg.use_tma ? 1 : 0;
 }
 
@@ -284,7 +336,15 @@ int nfcb200_create(const nfcb200_config *cfg, nfcb200_handle **out)
    for (auto &ev: h->ev)
       cudaEventCreate(&ev);
 
-   cudaFuncSetAttribute(screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem));
+   if (const char *e = getenv("NFCB200_LANE_TAPS"))
+      h->laneTaps = std::max(0, std::min(2, atoi(e)));
+   if (const char *e = getenv("NFCB200_LANE_BLOCKS"))
+      h->laneBlocks = std::max(2, std::min(4, atoi(e)));
+
+   cudaFuncSetAttribute(screen_kernel<SIG_IQ_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem));
+   cudaFuncSetAttribute(screen_kernel<SIG_MAG_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem));
+   cudaFuncSetAttribute(screen_kernel<SIG_MAG_S16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem));
+   cudaFuncSetAttribute(screen_kernel<SIG_IQ_S16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem));
 
    *out = h;
    return 0;
@@ -421,8 +481,9 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
 
    {
       uint64_t items = (uint64_t) n_streams * tiles;
-      u32 grid = (u32) std::min<uint64_t>(items, (uint64_t) h->smCount * 2);
-      screen_kernel<<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
+      if (items >= 0xFFFF0000ull)
+         return fail(NFCB200_ERR_CAPACITY, "batch of %llu screening tiles exceeds one launch", (unsigned long long) items);
+      launch_screen(h, sc, (u32) items, st);
       launches++;
       CUDA_TRY(cudaGetLastError());
    }
@@ -466,7 +527,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    CUDA_TRY(cudaMemcpyAsync(&segTotal, &dC->segTotal, sizeof(u32), cudaMemcpyDeviceToHost, st));
    CUDA_TRY(cudaStreamSynchronize(st));
    {
-      const uint64_t residentLanes = (uint64_t) h->smCount * 16 * 32;
+      const uint64_t residentLanes = (uint64_t) h->smCount * (uint64_t) h->laneBlocks * (LANE_THREADS / 32) * 32;
       const uint64_t target = residentLanes * 2;
       u32 group = h->cfg.segments_per_lane ? h->cfg.segments_per_lane : (u32) std::max<uint64_t>(1, segTotal / std::max<uint64_t>(1, target));
       sg.group = std::min<u32>(group, 64);
@@ -555,7 +616,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
 
    // ---- lanes + chain, to the fixed point -----------------------------------------------------------------------------
    const u32 warpsPerBlock = LANE_THREADS / 32;
-   const u32 maxWarps = (u32) h->smCount * 16; // 128 registers per lane thread: 16 resident warps per SM
+   const u32 maxWarps = (u32) h->smCount * (u32) h->laneBlocks * warpsPerBlock; // resident warps: the kernel is persistent
 
    LaneConfig lc;
    memset(&lc, 0, sizeof(lc));
@@ -603,7 +664,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       lc.queue_count = queueCount;
 
       CUDA_TRY(cudaMemsetAsync(&dC->cursor, 0, sizeof(u32), st));
-      lanes_kernel<<<blocks, LANE_THREADS, 0, st>>>(lc, h->P);
+      launch_lanes(h, lc, blocks, st);
       launches++;
       CUDA_TRY(cudaGetLastError());
 
@@ -785,7 +846,9 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
       uint32_t chunkStreams = n_streams;
       if (total * bs > (1ull << 30) && n_streams >= 16)
       {
-         chunkStreams = (n_streams + 7) / 8;
+         // 16 chunks (8 below 4 GB): only the first copy and the last decode are not overlapped
+         const uint32_t parts = total * bs > (4ull << 30) && n_streams >= 64 ? 16 : 8;
+         chunkStreams = (n_streams + parts - 1) / parts;
          while (chunkStreams > 1 && (uint64_t) chunkStreams * streamBytes > (12ull << 30))
             chunkStreams = (chunkStreams + 1) / 2;
       }
@@ -1048,7 +1111,7 @@ int nfcb200_stream_push(nfcb200_handle *h, const void *samples, int sigtype, uin
       if ((((uintptr_t) sc.samples) & 15) || (((uint64_t) newCount * bs) & 15))
          sc.use_tma = 0;
 
-      screen_kernel<<<std::min<u32>(tiles, (u32) h->smCount * 2), SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, tiles);
+      launch_screen(h, sc, tiles, st);
       CUDA_TRY(cudaGetLastError());
 
       SegmentConfig sg;

@@ -14,6 +14,11 @@
 
 #include "../../nfc_laboratory_b200/csrc/nfc_chain.h"
 
+// tap fetch variant of the lane machine under test: the one the device library ships (nfcb200.cu laneTaps)
+#ifndef NFCB200_SIM_TAPS
+#define NFCB200_SIM_TAPS 2
+#endif
+
 using namespace nfcb200;
 
 extern "C" {
@@ -117,7 +122,7 @@ long hostsim_run(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t ena
    lane_begin(L, P, carry, first, warm);
 
    Sink sink {out, cap, 0};
-   Machine<1, Sink> M(P, L, scratch.data(), sb.data(), sink);
+   Machine<1, Sink, NFCB200_SIM_TAPS> M(P, L, scratch.data(), sb.data(), sink);
 
    uint64_t pos = first;
 
@@ -209,7 +214,7 @@ long hostsim_pipeline(const float *mag, uint64_t n, uint32_t sampleRate, uint32_
          Lane L;
          lane_begin(L, P, R.in, R.first, NFCB200_HALO);
 
-         Machine<1, Sink> M(P, L, scratch.data(), sb.data(), sink);
+         Machine<1, Sink, NFCB200_SIM_TAPS> M(P, L, scratch.data(), sb.data(), sink);
 
          uint32_t pos = R.first, kw = 0, stepped = 0;
 
