@@ -287,7 +287,7 @@ def main():
         except Exception:
             avail = 32 << 30
         Se = S
-        while Se > 1 and Se * n * 8 > min(0.25 * avail / world, 24 << 30):  # every rank pins its own copy; bounded host footprint
+        while Se > 1 and Se * n * 8 > min(0.25 * avail / world, 96 << 30):  # every rank pins its own copy; bounded host footprint
             Se //= 2
         host = torch.empty((Se, n, 2), dtype=torch.float32, pin_memory=True)
         host.copy_(iq[:Se])
