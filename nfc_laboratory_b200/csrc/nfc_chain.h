@@ -176,6 +176,7 @@ NFC_HD bool lane_iterate(MACH &M, Lane &L, const Params &P, u32 &pos, u32 end, u
          lane_begin(L, P, carry, target, NFCB200_HALO);
          L.lockedMask = locked;
          L.fe.kbase = kw;
+         M.reload_front();
          pos = target;
       }
    }

@@ -105,7 +105,10 @@ struct Carry
    u32 carrierOff; // carrierOffTime (0 = unset)
 };
 
-// front end (NfcDecoderStatus scalars, NfcTech.h:317-393)
+// front end (NfcDecoderStatus scalars, NfcTech.h:317-393) plus the rest of the state a lane touches on EVERY sample.
+// On the device this block lives in shared memory (31 words per lane, odd stride: no bank conflicts), everything else
+// of a lane in thread-local memory: with 16 resident warps per SM the local state (1.4 kB per lane) does not fit the L1
+// cache, and the per-sample fields were the bulk of its traffic.
 struct Front
 {
    u32 clk;         // signalClock
@@ -118,6 +121,15 @@ struct Front
    u32 edgeTime;
    // correlation ring phases, advanced every sample (replaces the reference's three `%` per rate per sample)
    u32 cA[3], cF[2], cV1, cV0;
+   // the detectors' running sums (NfcModulationStatus::filterIntegrate), indexed like the Mods of Carry: mA[0..2],
+   // mB[0..1] (unused), mF[0..1], mV.  They never cross lanes: a lane restarts them with its rings (carry_canon)
+   float fi[8];
+   // bit i: Mod i has search state pending, i.e. the precondition of its detector's idle fast path is false
+   u32 busy;
+   u32 lock;      // LOCK_*
+   u32 lockRate;  // rate index of the locked modulation
+   u32 gate;      // local steps during which the detectors are off (reference: signalClock < BUFFER_SIZE)
+   u32 warm;      // local steps during which carrier detection is suppressed (cold-started lanes)
 };
 
 enum { LOCK_NONE = 0, LOCK_A = 1, LOCK_B = 2, LOCK_F = 3, LOCK_V = 4 };
@@ -128,8 +140,6 @@ struct Lane
    Carry c;
    Sym sym;
    Bits st;
-   u32 lock;      // LOCK_*
-   u32 lockRate;  // rate index of the locked modulation
    u32 pulseBits; // NFC-V pulse code: 2 or 8 (decoder->pulse)
    u32 lockedMask; // techs that were locked at least once during this run (bit t), for the carry dependency check
    // finer dependency tracking of the run on its incoming carry (nfc_chain.h chain_walk):
@@ -140,8 +150,6 @@ struct Lane
    u32 fThrRead;   // bit r: ... and was compared before any assignment, against fThrSync[r]
    u32 fInc0[2];   // `searchPulseWidth++ < 94` tests executed before the first reset (NfcF.cpp:307)
    float fThrSync[2];
-   u32 warm;      // local steps during which carrier detection is suppressed (cold-started lanes)
-   u32 gate;      // local steps during which the detectors are off (reference: signalClock < BUFFER_SIZE)
 };
 
 // one decoded frame (payload stays in the lane's byte buffer until the sink copies it)
@@ -212,21 +220,72 @@ struct Machine
 {
    const Params &P;
    Lane &L;
+   Front &F;  // the per-sample state: L.fe itself, or its working copy in shared memory (device lanes)
    float *rg; // lane scratch (already offset by the lane index on the device)
    u8 *sb;    // 512-byte stream buffer
    SINK &sink;
    SearchTaps T;      // TAPS == 2: this step's taps
    bool tapsValid;    // TAPS == 2: T was loaded for this step
    float curX, curW;  // sample and edge value of the current step (ring slot of delay 0)
+   bool slow;         // a detector left its idle fast path during this step: F.busy must be rebuilt
 
-   NFC_HD Machine(const Params &p, Lane &l, float *r, u8 *s, SINK &k) : P(p), L(l), rg(r), sb(s), sink(k), tapsValid(false), curX(0), curW(0)
+   NFC_HD Machine(const Params &p, Lane &l, Front &f, float *r, u8 *s, SINK &k)
+      : P(p), L(l), F(f), rg(r), sb(s), sink(k), tapsValid(false), curX(0), curW(0), slow(false)
    {
    }
 
-#define RG(off, i) rg[((off) + (i)) * STRIDE]
-#define SMP(off, delay) RG(off, (L.fe.k + L.fe.kbase - (delay)) & (NFCB200_RING - 1))
+   // running sum of a Mod (index = position of the Mod inside Carry: mA, mB, mF, mV are contiguous)
+   NFC_HD float &FI(const Mod &m)
+   {
+      return F.fi[(u32) (&m - &L.c.mA[0])];
+   }
 
-   NFC_HD static void zero_mod(Mod &m)
+   // (re)load the working copy of the per-sample state after lane_begin() rewrote L.fe, and rebuild the busy mask
+   NFC_HD void reload_front()
+   {
+      if (&F != &L.fe)
+         F = L.fe;
+      refresh_busy();
+      slow = false;
+   }
+
+   // write the working copy back (suspended lanes: streaming entry point)
+   NFC_HD void store_front()
+   {
+      if (&F != &L.fe)
+         L.fe = F;
+   }
+
+   NFC_HD void refresh_busy()
+   {
+      u32 b = 0;
+      for (int r = 0; r < 3; r++)
+      {
+         const Mod &m = L.c.mA[r];
+         if (m.symbolStartTime | m.searchStartTime | m.searchEndTime | m.correlatedPeakTime)
+            b |= 1u << r;
+      }
+      for (int r = 0; r < 2; r++)
+      {
+         const Mod &m = L.c.mB[r];
+         if (m.symbolStartTime | m.searchEndTime | m.detectorPeakTime)
+            b |= 8u << r;
+         const Mod &f = L.c.mF[r];
+         if (f.symbolStartTime | f.symbolEndTime | f.searchStartTime | f.searchEndTime | f.searchSyncTime | f.correlatedPeakTime)
+            b |= 32u << r;
+      }
+      {
+         const Mod &m = L.c.mV;
+         if (m.searchStartTime | m.searchEndTime | m.correlatedPeakTime)
+            b |= 128u;
+      }
+      F.busy = b;
+   }
+
+#define RG(off, i) rg[((off) + (i)) * STRIDE]
+#define SMP(off, delay) RG(off, (F.k + F.kbase - (delay)) & (NFCB200_RING - 1))
+
+   NFC_HD void zero_mod(Mod &m)
    {
       m.searchModeState = 0;
       m.searchStartTime = 0;
@@ -244,7 +303,7 @@ struct Machine
       m.symbolStartTime = 0;
       m.symbolEndTime = 0;
       m.symbolRiseTime = 0;
-      m.filterIntegrate = 0;
+      FI(m) = 0;
       m.phaseIntegrate = 0;
       m.correlatedPeakValue = 0;
       m.detectorPeakValue = 0;
@@ -278,14 +337,14 @@ struct Machine
 
    NFC_HD Mod &locked_mod()
    {
-      switch (L.lock)
+      switch (F.lock)
       {
          case LOCK_A:
-            return L.c.mA[L.lockRate];
+            return L.c.mA[F.lockRate];
          case LOCK_B:
-            return L.c.mB[L.lockRate];
+            return L.c.mB[F.lockRate];
          case LOCK_F:
-            return L.c.mF[L.lockRate - 1];
+            return L.c.mF[F.lockRate - 1];
          default:
             return L.c.mV;
       }
@@ -293,14 +352,14 @@ struct Machine
 
    NFC_HD const RateParams &locked_rate() const
    {
-      switch (L.lock)
+      switch (F.lock)
       {
          case LOCK_A:
-            return P.A[L.lockRate];
+            return P.A[F.lockRate];
          case LOCK_B:
-            return P.B[L.lockRate];
+            return P.B[F.lockRate];
          case LOCK_F:
-            return P.F[L.lockRate];
+            return P.F[F.lockRate];
          default:
             return P.V;
       }
@@ -312,7 +371,7 @@ struct Machine
    {
       m.symbolStartTime = 0;
       m.symbolEndTime = 0;
-      m.filterIntegrate = 0;
+      FI(m) = 0;
       m.phaseIntegrate = 0;
       m.searchModeState = 0;
       m.searchSyncTime = 0;
@@ -349,7 +408,7 @@ struct Machine
    // clock and ring phases of the new sample (first half of nextSample: everything that does not need the value)
    NFC_HD void front_advance()
    {
-      Front &f = L.fe;
+      Front &f = F;
 
       ++f.clk;
       ++f.k;
@@ -370,7 +429,7 @@ struct Machine
 
    NFC_HD void front(float x)
    {
-      Front &f = L.fe;
+      Front &f = F;
 
       // NfcTech.cpp:39-42: signalDiff = abs(x - env) / env; gate = signalDiff < 0.05f.  The IEEE division is only
       // executed when the quotient is within 2 % of the threshold; outside that band the comparison is decided by
@@ -445,7 +504,7 @@ struct Machine
    // NfcDecoder::Impl::detectCarrier, NfcDecoder.cpp:472-523
    NFC_HD void detect_carrier()
    {
-      Front &f = L.fe;
+      Front &f = F;
 
       if (f.avg > P.highThr)
       {
@@ -497,14 +556,14 @@ struct Machine
       L.c.t[TECH_A].fs.frameType = 0;
       L.c.t[TECH_A].fs.frameStart = 0;
       L.c.t[TECH_A].fs.frameEnd = 0;
-      L.lock = LOCK_NONE;
+      F.lock = LOCK_NONE;
    }
 
    // NfcA::Impl::detectModulation, NfcA.cpp:217-411 (the clock / envelope gates are applied by the caller)
    NFC_HD bool A_detect()
    {
-      const float env = L.fe.env;
-      const u32 clk = L.fe.clk;
+      const float env = F.env;
+      const u32 clk = F.clk;
       const float minimumCorrelationValue = env * P.thr[TECH_A].corr;
       const float minDeep = P.thr[TECH_A].modMin;
 
@@ -513,26 +572,28 @@ struct Machine
          const RateParams &b = P.A[rate];
          Mod &m = L.c.mA[rate];
 
-         u32 fp1 = L.fe.cA[rate], fp2, fp3;
+         u32 fp1 = F.cA[rate], fp2, fp3;
          corr_points(fp1, b.p1, b.p2, fp2, fp3);
 
          // :246-250
          const bool hoisted = TAPS == 2 && tapsValid;
-         m.filterIntegrate += hoisted ? (b.sdd ? T.xa0[rate] : curX) : SMP(NFCB200_OFF_X, b.sdd);
-         m.filterIntegrate -= hoisted ? T.xa1[rate] : SMP(NFCB200_OFF_X, b.sdd + b.p2);
-         RG(b.corr, fp1) = m.filterIntegrate;
+         FI(m) += hoisted ? (b.sdd ? T.xa0[rate] : curX) : SMP(NFCB200_OFF_X, b.sdd);
+         FI(m) -= hoisted ? T.xa1[rate] : SMP(NFCB200_OFF_X, b.sdd + b.p2);
+         RG(b.corr, fp1) = FI(m);
 
          // :253-255
          const float c2 = hoisted ? T.ca2[rate] : RG(b.corr, fp2);
          const float c3 = hoisted ? T.ca3[rate] : RG(b.corr, fp3);
-         float s0 = m.filterIntegrate - c2;
+         float s0 = FI(m) - c2;
          float s1 = c2 - c3;
 
          // idle fast path (not in the reference): with no search state pending, the rest of this iteration only acts when
          // correlatedSD < -minimumCorrelationValue (:291).  (s0 - s1) / p2 < -T needs s0 - s1 < -T p2 (1 - ulp): anything
          // above half of that cannot trigger, so the IEEE division and the state tests are skipped
-         if ((m.symbolStartTime | m.searchStartTime | m.searchEndTime | m.correlatedPeakTime) == 0 && (s0 - s1) > -0.5f * minimumCorrelationValue * (float) b.p2)
+         if (!(F.busy & (1u << rate)) && (s0 - s1) > -0.5f * minimumCorrelationValue * (float) b.p2)
             continue;
+
+         slow = true;
 
          float sd = (s0 - s1) / (float) b.p2;
 
@@ -658,8 +719,8 @@ struct Machine
          L.sym.length = L.sym.end - L.sym.start;
          L.sym.pattern = 4; // PatternZ
 
-         L.lock = LOCK_A;
-         L.lockRate = rate;
+         F.lock = LOCK_A;
+         F.lockRate = rate;
          return true;
       }
 
@@ -942,9 +1003,9 @@ struct Machine
 
       if (poll) // :1548-1577
       {
-         if (L.lock == LOCK_A)
+         if (F.lock == LOCK_A)
          {
-            u32 sdd = P.A[L.lockRate].sdd;
+            u32 sdd = P.A[F.lockRate].sdd;
             fs.guardEnd = fs.frameEnd + fs.frameGuardTime + sdd;
             fs.waitingEnd = fs.frameEnd + fs.frameWaitingTime + sdd;
             fs.frameType = FT_Listen;
@@ -952,8 +1013,8 @@ struct Machine
       }
       else
       {
-         if (L.lock == LOCK_A)
-            fs.guardEnd = fs.frameEnd + fs.frameGuardTime + P.A[L.lockRate].sdd;
+         if (F.lock == LOCK_A)
+            fs.guardEnd = fs.frameEnd + fs.frameGuardTime + P.A[F.lockRate].sdd;
          fs.frameType = 0;
          fs.lastCommand = 0;
          L.lcWritten |= 1u << TECH_A;
@@ -966,18 +1027,18 @@ struct Machine
    // one sample of decodePollFrameSymbolAsk, NfcA.cpp:812-934.  Returns a pattern or A_Invalid (no symbol yet).
    NFC_HD int A_poll_symbol()
    {
-      const RateParams &b = P.A[L.lockRate];
-      Mod &m = L.c.mA[L.lockRate];
-      const u32 clk = L.fe.clk;
+      const RateParams &b = P.A[F.lockRate];
+      Mod &m = L.c.mA[F.lockRate];
+      const u32 clk = F.clk;
 
-      u32 fp1 = L.fe.cA[L.lockRate], fp2, fp3;
+      u32 fp1 = F.cA[F.lockRate], fp2, fp3;
       corr_points(fp1, b.p1, b.p2, fp2, fp3);
 
-      m.filterIntegrate += SMP(NFCB200_OFF_X, b.sdd);
-      m.filterIntegrate -= SMP(NFCB200_OFF_X, b.sdd + b.p2);
-      RG(b.corr, fp1) = m.filterIntegrate;
+      FI(m) += SMP(NFCB200_OFF_X, b.sdd);
+      FI(m) -= SMP(NFCB200_OFF_X, b.sdd + b.p2);
+      RG(b.corr, fp1) = FI(m);
 
-      float s0 = m.filterIntegrate - RG(b.corr, fp2);
+      float s0 = FI(m) - RG(b.corr, fp2);
       float s1 = RG(b.corr, fp2) - RG(b.corr, fp3);
       float sd = fabsf(s0 - s1) / (float) b.p2;
 
@@ -1085,8 +1146,8 @@ struct Machine
 
             clear_bits();
 
-            if (L.lock == LOCK_A) // :491-511
-               clear_for_listen(L.c.mA[L.lockRate], P.A[L.lockRate].corr, P.A[L.lockRate].p1);
+            if (F.lock == LOCK_A) // :491-511
+               clear_for_listen(L.c.mA[F.lockRate], P.A[F.lockRate].corr, P.A[F.lockRate].p1);
 
             return;
          }
@@ -1125,9 +1186,9 @@ struct Machine
    // NfcA::Impl::resetFrameSearch, NfcA.cpp:1426-1446
    NFC_HD void A_reset_frame_search()
    {
-      if (L.lock == LOCK_A)
+      if (F.lock == LOCK_A)
       {
-         Mod &m = L.c.mA[L.lockRate];
+         Mod &m = L.c.mA[F.lockRate];
          m.symbolStartTime = 0;
          m.symbolEndTime = 0;
          m.symbolRiseTime = 0;
@@ -1146,7 +1207,7 @@ struct Machine
    // common part of the ASK listen integrator (w^2 * 10 over half a symbol), NfcA.cpp:955-973 / 1110-1130
    NFC_HD void A_listen_ask_integrate(const RateParams &b, Mod &m, float &s0, float &s1)
    {
-      u32 fp1 = L.fe.cA[L.lockRate], fp2, fp3;
+      u32 fp1 = F.cA[F.lockRate], fp2, fp3;
       corr_points(fp1, b.p1, b.p2, fp2, fp3);
 
       float data = SMP(NFCB200_OFF_W, b.sdd);
@@ -1154,22 +1215,22 @@ struct Machine
 
       SMP(NFCB200_OFF_I, b.sdd) = v;
 
-      m.filterIntegrate += v;
-      m.filterIntegrate -= SMP(NFCB200_OFF_I, b.sdd + b.p2);
+      FI(m) += v;
+      FI(m) -= SMP(NFCB200_OFF_I, b.sdd + b.p2);
 
-      RG(b.corr, fp1) = m.filterIntegrate;
+      RG(b.corr, fp1) = FI(m);
 
-      s0 = m.filterIntegrate - RG(b.corr, fp2);
+      s0 = FI(m) - RG(b.corr, fp2);
       s1 = RG(b.corr, fp2) - RG(b.corr, fp3);
    }
 
    // one sample of decodeListenFrameStartAsk, NfcA.cpp:939-1090
    NFC_HD int A_listen_start_ask()
    {
-      const RateParams &b = P.A[L.lockRate];
-      Mod &m = L.c.mA[L.lockRate];
+      const RateParams &b = P.A[F.lockRate];
+      Mod &m = L.c.mA[F.lockRate];
       FrameSt &fs = L.c.t[TECH_A].fs;
-      const u32 clk = L.fe.clk;
+      const u32 clk = F.clk;
 
       float s0, s1;
       A_listen_ask_integrate(b, m, s0, s1);
@@ -1261,9 +1322,9 @@ struct Machine
    // one sample of decodeListenFrameSymbolAsk, NfcA.cpp:1095-1214
    NFC_HD int A_listen_symbol_ask()
    {
-      const RateParams &b = P.A[L.lockRate];
-      Mod &m = L.c.mA[L.lockRate];
-      const u32 clk = L.fe.clk;
+      const RateParams &b = P.A[F.lockRate];
+      Mod &m = L.c.mA[F.lockRate];
+      const u32 clk = F.clk;
 
       float s0, s1;
       A_listen_ask_integrate(b, m, s0, s1);
@@ -1332,10 +1393,10 @@ struct Machine
    // one sample of decodeListenFrameStartBpsk, NfcA.cpp:1220-1329
    NFC_HD int A_listen_start_bpsk()
    {
-      const RateParams &b = P.A[L.lockRate];
-      Mod &m = L.c.mA[L.lockRate];
+      const RateParams &b = P.A[F.lockRate];
+      Mod &m = L.c.mA[F.lockRate];
       FrameSt &fs = L.c.t[TECH_A].fs;
-      const u32 clk = L.fe.clk;
+      const u32 clk = F.clk;
 
       float data = SMP(NFCB200_OFF_W, b.sdd);
       float delay1 = SMP(NFCB200_OFF_W, b.sdd + b.p1);
@@ -1403,7 +1464,7 @@ struct Machine
    // pattern codes.  Returns 0 none, 1 end-of-frame (PatternO), 2 symbol
    NFC_HD int bpsk_symbol(const RateParams &b, Mod &m, bool &toggled)
    {
-      const u32 clk = L.fe.clk;
+      const u32 clk = F.clk;
 
       float data = SMP(NFCB200_OFF_W, b.sdd);
       float delay1 = SMP(NFCB200_OFF_W, b.sdd + b.p1);
@@ -1450,7 +1511,7 @@ struct Machine
    {
       TechSt &t = L.c.t[TECH_A];
       u32 phase = 0;
-      u32 len = L.st.bytes, rate = P.A[L.lockRate].sps, start = t.fs.frameStart, end = t.fs.frameEnd;
+      u32 len = L.st.bytes, rate = P.A[F.lockRate].sps, start = t.fs.frameStart, end = t.fs.frameEnd;
       A_process(FT_Listen, len, flags, phase);
       emit(TT_A, FT_Listen, flags, phase, rate, start, end, sb, len);
       A_reset();
@@ -1464,7 +1525,7 @@ struct Machine
       Bits &st = L.st;
       bool frameEnd = false, truncateError = false;
 
-      if (L.lockRate == 0) // 106k ASK / Manchester
+      if (F.lockRate == 0) // 106k ASK / Manchester
       {
          if (!fs.frameStart)
          {
@@ -1545,8 +1606,8 @@ struct Machine
          return;
       }
 
-      const RateParams &b = P.A[L.lockRate];
-      Mod &m = L.c.mA[L.lockRate];
+      const RateParams &b = P.A[F.lockRate];
+      Mod &m = L.c.mA[F.lockRate];
       bool toggled = false;
       int r = bpsk_symbol(b, m, toggled);
 
@@ -1642,7 +1703,7 @@ struct Machine
       L.c.t[TECH_B].fs.frameType = 0;
       L.c.t[TECH_B].fs.frameStart = 0;
       L.c.t[TECH_B].fs.frameEnd = 0;
-      L.lock = LOCK_NONE;
+      F.lock = LOCK_NONE;
    }
 
    NFC_HD static void B_clear_search(Mod &m, bool sync)
@@ -1660,8 +1721,8 @@ struct Machine
    // NfcB::Impl::detectModulation, NfcB.cpp:238-432
    NFC_HD bool B_detect()
    {
-      const u32 clk = L.fe.clk;
-      const float env = L.fe.env;
+      const u32 clk = F.clk;
+      const float env = F.env;
 
       for (int rate = 0; rate <= 1; rate++)
       {
@@ -1672,8 +1733,10 @@ struct Machine
 
          // idle fast path (not in the reference): with no SOF search pending the iteration only acts on a falling edge
          // below -envelope * minimumModulationDeep (:283); the per-sample rewrite of searchValueThreshold (:280) is dead
-         if ((m.symbolStartTime | m.searchEndTime | m.detectorPeakTime) == 0 && !(edge < -(env * P.thr[TECH_B].modMin)))
+         if (!(F.busy & (8u << rate)) && !(edge < -(env * P.thr[TECH_B].modMin)))
             continue;
+
+         slow = true;
 
          float deep = depth_at(b.sdd);
 
@@ -1798,8 +1861,8 @@ struct Machine
          fs.frameStart = m.symbolStartTime - b.sdd;
          fs.frameEnd = 0;
 
-         L.lock = LOCK_B;
-         L.lockRate = rate;
+         F.lock = LOCK_B;
+         F.lockRate = rate;
          return true;
       }
 
@@ -1911,9 +1974,9 @@ struct Machine
 
       if (poll)
       {
-         if (L.lock == LOCK_B)
+         if (F.lock == LOCK_B)
          {
-            u32 sdd = P.B[L.lockRate].sdd;
+            u32 sdd = P.B[F.lockRate].sdd;
             fs.guardEnd = fs.frameEnd + fs.frameGuardTime + sdd;
             fs.waitingEnd = fs.frameEnd + fs.frameWaitingTime + sdd;
             fs.frameType = FT_Listen;
@@ -1921,8 +1984,8 @@ struct Machine
       }
       else
       {
-         if (L.lock == LOCK_B)
-            fs.guardEnd = fs.frameEnd + fs.frameGuardTime + P.B[L.lockRate].sdd;
+         if (F.lock == LOCK_B)
+            fs.guardEnd = fs.frameEnd + fs.frameGuardTime + P.B[F.lockRate].sdd;
          fs.frameType = 0;
          fs.lastCommand = 0;
          L.lcWritten |= 1u << TECH_B;
@@ -1935,9 +1998,9 @@ struct Machine
    // one sample of decodePollFrameSymbolAsk, NfcB.cpp:684-762
    NFC_HD int B_poll_symbol()
    {
-      const RateParams &b = P.B[L.lockRate];
-      Mod &m = L.c.mB[L.lockRate];
-      const u32 clk = L.fe.clk;
+      const RateParams &b = P.B[F.lockRate];
+      Mod &m = L.c.mB[F.lockRate];
+      const u32 clk = F.clk;
 
       float edge = SMP(NFCB200_OFF_W, b.sdd);
       float deep = depth_at(b.sdd);
@@ -2014,15 +2077,15 @@ struct Machine
             if (truncateError || streamError)
                flags |= FL_Truncated;
 
-            u32 len = st.bytes, rate = P.B[L.lockRate].sps, start = t.fs.frameStart, end = t.fs.frameEnd;
+            u32 len = st.bytes, rate = P.B[F.lockRate].sps, start = t.fs.frameStart, end = t.fs.frameEnd;
 
             B_process(FT_Poll, len, flags, phase);
             emit(TT_B, FT_Poll, flags, phase, rate, start, end, sb, len);
 
             clear_bits();
 
-            if (L.lock == LOCK_B)
-               clear_for_listen(L.c.mB[L.lockRate], 0, 0);
+            if (F.lock == LOCK_B)
+               clear_for_listen(L.c.mB[F.lockRate], 0, 0);
 
             return;
          }
@@ -2049,10 +2112,10 @@ struct Machine
    // one sample of decodeListenFrameStartBpsk, NfcB.cpp:767-949
    NFC_HD int B_listen_start()
    {
-      const RateParams &b = P.B[L.lockRate];
-      Mod &m = L.c.mB[L.lockRate];
+      const RateParams &b = P.B[F.lockRate];
+      Mod &m = L.c.mB[F.lockRate];
       FrameSt &fs = L.c.t[TECH_B].fs;
-      const u32 clk = L.fe.clk;
+      const u32 clk = F.clk;
 
       float data = SMP(NFCB200_OFF_W, b.sdd);
       float delay1 = SMP(NFCB200_OFF_W, b.sdd + b.p1);
@@ -2168,8 +2231,8 @@ struct Machine
          return;
       }
 
-      const RateParams &b = P.B[L.lockRate];
-      Mod &m = L.c.mB[L.lockRate];
+      const RateParams &b = P.B[F.lockRate];
+      Mod &m = L.c.mB[F.lockRate];
       bool toggled = false;
       int r = bpsk_symbol(b, m, toggled);
 
@@ -2262,7 +2325,7 @@ struct Machine
       L.c.t[TECH_F].fs.frameType = 0;
       L.c.t[TECH_F].fs.frameStart = 0;
       L.c.t[TECH_F].fs.frameEnd = 0;
-      L.lock = LOCK_NONE;
+      F.lock = LOCK_NONE;
    }
 
    NFC_HD void F_note_zeroed(const Mod &m)
@@ -2291,7 +2354,7 @@ struct Machine
    // was accepted (symbol timings are left in m).
    NFC_HD bool F_track_preamble(const RateParams &b, Mod &m, float s0, float sd, float minimumCorrelationValue, bool ge)
    {
-      const u32 clk = L.fe.clk;
+      const u32 clk = F.clk;
 
       if (clk < m.searchStartTime)
          return false;
@@ -2385,8 +2448,8 @@ struct Machine
    {
       u32 fp2, fp3;
       corr_points(fp1, b.p1, b.p2, fp2, fp3);
-      RG(b.corr, fp1) = m.filterIntegrate;
-      s0 = m.filterIntegrate - RG(b.corr, fp2);
+      RG(b.corr, fp1) = FI(m);
+      s0 = FI(m) - RG(b.corr, fp2);
       s1 = RG(b.corr, fp2) - RG(b.corr, fp3);
       sd = fabsf(s0 - s1) / (float) b.p2;
    }
@@ -2394,8 +2457,8 @@ struct Machine
    // NfcF::Impl::detectModulation, NfcF.cpp:206-408
    NFC_HD bool F_detect()
    {
-      const u32 clk = L.fe.clk;
-      const float minimumCorrelationValue = L.fe.env * P.thr[TECH_F].corr;
+      const u32 clk = F.clk;
+      const float minimumCorrelationValue = F.env * P.thr[TECH_F].corr;
 
       for (int rate = 1; rate <= 2; rate++)
       {
@@ -2403,30 +2466,32 @@ struct Machine
          Mod &m = L.c.mF[rate - 1];
 
          const bool hoisted = TAPS == 2 && tapsValid;
-         m.filterIntegrate += (hoisted && b.sdd == 0) ? curX : SMP(NFCB200_OFF_X, b.sdd);
-         m.filterIntegrate -= hoisted ? T.xf1[rate - 1] : SMP(NFCB200_OFF_X, b.sdd + b.p2);
+         FI(m) += (hoisted && b.sdd == 0) ? curX : SMP(NFCB200_OFF_X, b.sdd);
+         FI(m) -= hoisted ? T.xf1[rate - 1] : SMP(NFCB200_OFF_X, b.sdd + b.p2);
 
          // idle fast path (not in the reference): with no search window pending (the residual pulse counter / threshold
          // only matter at a window end) the iteration only acts when correlatedSD > minimumCorrelationValue (:277); the
          // "recover" block (:260-271) rewrites zeros.  |s0 - s1| below half of T p2 cannot reach the threshold.
-         if ((m.symbolStartTime | m.symbolEndTime | m.searchStartTime | m.searchEndTime | m.searchSyncTime | m.correlatedPeakTime) == 0)
+         if (!(F.busy & (16u << rate)))
          {
             u32 fq2, fq3;
-            const u32 fq1 = L.fe.cF[rate - 1];
+            const u32 fq1 = F.cF[rate - 1];
             corr_points(fq1, b.p1, b.p2, fq2, fq3);
-            RG(b.corr, fq1) = m.filterIntegrate;
+            RG(b.corr, fq1) = FI(m);
             const float c2 = hoisted ? T.cf2[rate - 1] : RG(b.corr, fq2);
             const float c3 = hoisted ? T.cf3[rate - 1] : RG(b.corr, fq3);
-            float q0 = m.filterIntegrate - c2;
+            float q0 = FI(m) - c2;
             float q1 = c2 - c3;
             if (fabsf(q0 - q1) < 0.5f * minimumCorrelationValue * (float) b.p2)
                continue;
          }
 
+         slow = true;
+
          float deep = depth_at(b.sdd);
 
          float s0, s1, sd;
-         F_correlate(b, m, L.fe.cF[rate - 1], s0, s1, sd);
+         F_correlate(b, m, F.cF[rate - 1], s0, s1, sd);
 
          // :260-271
          if (deep > P.thr[TECH_F].modMax || (m.correlatedPeakTime && clk > m.correlatedPeakTime + b.p1))
@@ -2456,8 +2521,8 @@ struct Machine
          fs.frameStart = L.sym.start;
          fs.frameEnd = 0;
 
-         L.lock = LOCK_F;
-         L.lockRate = rate;
+         F.lock = LOCK_F;
+         F.lockRate = rate;
          return true;
       }
 
@@ -2539,9 +2604,9 @@ struct Machine
 
       if (poll)
       {
-         if (L.lock == LOCK_F)
+         if (F.lock == LOCK_F)
          {
-            u32 sdd = P.F[L.lockRate].sdd;
+            u32 sdd = P.F[F.lockRate].sdd;
             fs.guardEnd = fs.frameEnd + fs.frameGuardTime + sdd;
             fs.waitingEnd = fs.frameEnd + fs.frameWaitingTime + sdd;
             fs.frameType = FT_Listen;
@@ -2549,8 +2614,8 @@ struct Machine
       }
       else
       {
-         if (L.lock == LOCK_F)
-            fs.guardEnd = fs.frameEnd + fs.frameGuardTime + P.F[L.lockRate].sdd;
+         if (F.lock == LOCK_F)
+            fs.guardEnd = fs.frameEnd + fs.frameGuardTime + P.F[F.lockRate].sdd;
          fs.frameType = 0;
          fs.lastCommand = 0;
          L.lcWritten |= 1u << TECH_F;
@@ -2563,15 +2628,15 @@ struct Machine
    // one sample of decodePollFrameSymbolAsk / decodeListenFrameSymbolAsk, NfcF.cpp:641-744, 941-1042 (identical bodies)
    NFC_HD int F_symbol()
    {
-      const RateParams &b = P.F[L.lockRate];
-      Mod &m = L.c.mF[L.lockRate - 1];
-      const u32 clk = L.fe.clk;
+      const RateParams &b = P.F[F.lockRate];
+      Mod &m = L.c.mF[F.lockRate - 1];
+      const u32 clk = F.clk;
 
-      m.filterIntegrate += SMP(NFCB200_OFF_X, b.sdd);
-      m.filterIntegrate -= SMP(NFCB200_OFF_X, b.sdd + b.p2);
+      FI(m) += SMP(NFCB200_OFF_X, b.sdd);
+      FI(m) -= SMP(NFCB200_OFF_X, b.sdd + b.p2);
 
       float s0, s1, sd;
-      F_correlate(b, m, L.fe.cF[L.lockRate - 1], s0, s1, sd);
+      F_correlate(b, m, F.cF[F.lockRate - 1], s0, s1, sd);
 
       if (clk < m.searchStartTime)
          return F_Invalid;
@@ -2646,7 +2711,7 @@ struct Machine
                flags |= FL_Sync;
 
             u32 total = st.bytes > 512 ? 512 : st.bytes;
-            u32 len = total - 2, rate = P.F[L.lockRate].sps, start = t.fs.frameStart, end = t.fs.frameEnd;
+            u32 len = total - 2, rate = P.F[F.lockRate].sps, start = t.fs.frameStart, end = t.fs.frameEnd;
 
             F_process(type, sb + 2, len, flags, phase);
             emit(TT_F, type, flags, phase, rate, start, end, sb + 2, len);
@@ -2655,10 +2720,10 @@ struct Machine
             {
                clear_bits();
 
-               if (L.lock == LOCK_F)
+               if (F.lock == LOCK_F)
                {
-                  clear_for_listen(L.c.mF[L.lockRate - 1], P.F[L.lockRate].corr, P.F[L.lockRate].p1);
-                  F_note_zeroed(L.c.mF[L.lockRate - 1]);
+                  clear_for_listen(L.c.mF[F.lockRate - 1], P.F[F.lockRate].corr, P.F[F.lockRate].p1);
+                  F_note_zeroed(L.c.mF[F.lockRate - 1]);
                }
 
                return;
@@ -2682,19 +2747,19 @@ struct Machine
    // one sample of decodeListenFrameStartAsk, NfcF.cpp:749-936
    NFC_HD int F_listen_start()
    {
-      const RateParams &b = P.F[L.lockRate];
-      Mod &m = L.c.mF[L.lockRate - 1];
+      const RateParams &b = P.F[F.lockRate];
+      Mod &m = L.c.mF[F.lockRate - 1];
       FrameSt &fs = L.c.t[TECH_F].fs;
-      const u32 clk = L.fe.clk;
+      const u32 clk = F.clk;
 
-      m.filterIntegrate += SMP(NFCB200_OFF_X, b.sdd);
-      m.filterIntegrate -= SMP(NFCB200_OFF_X, b.sdd + b.p2);
+      FI(m) += SMP(NFCB200_OFF_X, b.sdd);
+      FI(m) -= SMP(NFCB200_OFF_X, b.sdd + b.p2);
 
       if (clk < (fs.guardEnd - b.p1))
          return F_Invalid;
 
       float s0, s1, sd;
-      F_correlate(b, m, L.fe.cF[L.lockRate - 1], s0, s1, sd);
+      F_correlate(b, m, F.cF[F.lockRate - 1], s0, s1, sd);
 
       if (clk < fs.guardEnd)
          return F_Invalid;
@@ -2761,7 +2826,7 @@ struct Machine
       L.c.t[TECH_V].fs.frameStart = 0;
       L.c.t[TECH_V].fs.frameEnd = 0;
       L.pulseBits = 0;
-      L.lock = LOCK_NONE;
+      F.lock = LOCK_NONE;
    }
 
    NFC_HD static void V_clear_search(Mod &m)
@@ -2780,21 +2845,21 @@ struct Machine
    NFC_HD float V_pulse_corr(Mod &m, float &signalData)
    {
       const RateParams &b = P.V;
-      u32 fp1 = L.fe.cV1;
+      u32 fp1 = F.cV1;
       u32 fp2 = fp1 + b.p2;
       if (fp2 >= b.p1)
          fp2 -= b.p1;
 
-      const bool hoisted = TAPS == 2 && tapsValid && L.lock == LOCK_NONE;
+      const bool hoisted = TAPS == 2 && tapsValid && F.lock == LOCK_NONE;
 
       signalData = hoisted ? T.xv0 : SMP(NFCB200_OFF_X, b.sdd);
 
-      m.filterIntegrate += signalData;
-      m.filterIntegrate -= hoisted ? T.xv1 : SMP(NFCB200_OFF_X, b.sdd + b.p2);
+      FI(m) += signalData;
+      FI(m) -= hoisted ? T.xv1 : SMP(NFCB200_OFF_X, b.sdd + b.p2);
 
-      RG(b.corr, fp1) = m.filterIntegrate;
+      RG(b.corr, fp1) = FI(m);
 
-      return ((hoisted ? T.cv2 : RG(b.corr, fp2)) - m.filterIntegrate) / (float) b.p2;
+      return ((hoisted ? T.cv2 : RG(b.corr, fp2)) - FI(m)) / (float) b.p2;
    }
 
    // NfcV::Impl::detectModulation, NfcV.cpp:236-435
@@ -2802,15 +2867,17 @@ struct Machine
    {
       const RateParams &b = P.V;
       Mod &m = L.c.mV;
-      const u32 clk = L.fe.clk;
-      const float minimumCorrelationValue = L.fe.env * P.thr[TECH_V].corr;
+      const u32 clk = F.clk;
+      const float minimumCorrelationValue = F.env * P.thr[TECH_V].corr;
 
       float signalData;
       float s0 = V_pulse_corr(m, signalData);
 
       // idle fast path (not in the reference): nothing pending and the pulse correlation far below the trigger (:305)
-      if ((m.searchStartTime | m.searchEndTime | m.correlatedPeakTime) == 0 && !(s0 > minimumCorrelationValue))
+      if (!(F.busy & 128u) && !(s0 > minimumCorrelationValue))
          return false;
+
+      slow = true;
 
       float deep = depth_at(b.sdd + b.p8);
 
@@ -2901,8 +2968,8 @@ struct Machine
       m.correlatedPeakValue = 0;
       m.searchValueThreshold = minimumCorrelationValue;
 
-      L.lock = LOCK_V;
-      L.lockRate = 0;
+      F.lock = LOCK_V;
+      F.lockRate = 0;
       return true;
    }
 
@@ -2942,7 +3009,7 @@ struct Machine
 
       if (poll)
       {
-         if (L.lock == LOCK_V)
+         if (F.lock == LOCK_V)
          {
             fs.guardEnd = fs.frameEnd + fs.frameGuardTime - P.V.sdd; // minus: NfcV.cpp:1147-1150
             fs.waitingEnd = fs.frameEnd + fs.frameWaitingTime - P.V.sdd;
@@ -2951,7 +3018,7 @@ struct Machine
       }
       else
       {
-         if (L.lock == LOCK_V)
+         if (F.lock == LOCK_V)
             fs.guardEnd = fs.frameEnd + fs.frameGuardTime + P.V.sdd;
          fs.frameType = 0;
          fs.lastCommand = 0;
@@ -2967,7 +3034,7 @@ struct Machine
    {
       const RateParams &b = P.V;
       Mod &m = L.c.mV;
-      const u32 clk = L.fe.clk;
+      const u32 clk = F.clk;
 
       float signalData;
       float s0 = V_pulse_corr(m, signalData);
@@ -3072,7 +3139,7 @@ struct Machine
             {
                clear_bits();
 
-               if (L.lock == LOCK_V)
+               if (F.lock == LOCK_V)
                   clear_for_listen(L.c.mV, P.V.corr, P.V.p0 > P.V.p1 ? P.V.p0 : P.V.p1);
 
                return;
@@ -3098,7 +3165,7 @@ struct Machine
    NFC_HD float V_listen_corr(Mod &m)
    {
       const RateParams &b = P.V;
-      u32 fp1 = L.fe.cV0;
+      u32 fp1 = F.cV0;
       u32 fp2 = fp1 + b.p1;
       if (fp2 >= b.p0)
          fp2 -= b.p0;
@@ -3107,12 +3174,12 @@ struct Machine
       float v = data * data * 10;
       SMP(NFCB200_OFF_I, b.sdd) = v;
 
-      m.filterIntegrate += v;
-      m.filterIntegrate -= SMP(NFCB200_OFF_I, b.sdd + b.p1);
+      FI(m) += v;
+      FI(m) -= SMP(NFCB200_OFF_I, b.sdd + b.p1);
 
-      RG(b.corr, fp1) = m.filterIntegrate;
+      RG(b.corr, fp1) = FI(m);
 
-      return RG(b.corr, fp2) - m.filterIntegrate;
+      return RG(b.corr, fp2) - FI(m);
    }
 
    // one sample of decodeListenFrameStartAsk, NfcV.cpp:800-980
@@ -3121,7 +3188,7 @@ struct Machine
       const RateParams &b = P.V;
       Mod &m = L.c.mV;
       FrameSt &fs = L.c.t[TECH_V].fs;
-      const u32 clk = L.fe.clk;
+      const u32 clk = F.clk;
 
       float s0 = V_listen_corr(m);
       float deep = depth_at(0);
@@ -3232,7 +3299,7 @@ struct Machine
    {
       const RateParams &b = P.V;
       Mod &m = L.c.mV;
-      const u32 clk = L.fe.clk;
+      const u32 clk = F.clk;
 
       float s0 = V_listen_corr(m);
       float sd = fabsf(s0);
@@ -3327,7 +3394,7 @@ struct Machine
    // ring slot of the sample `delay` steps before the step `ahead` steps from now (front_advance() already ran)
    NFC_HD u32 slot_at(u32 delay, u32 ahead) const
    {
-      return (L.fe.k + L.fe.kbase + ahead - delay) & (NFCB200_RING - 1);
+      return (F.k + F.kbase + ahead - delay) & (NFCB200_RING - 1);
    }
 
    NFC_HD void load_search_taps()
@@ -3335,7 +3402,7 @@ struct Machine
       for (int r = 0; r < 3; r++)
       {
          const RateParams &b = P.A[r];
-         const u32 c = L.fe.cA[r];
+         const u32 c = F.cA[r];
          T.xa0[r] = b.sdd ? RG(NFCB200_OFF_X, slot_at(b.sdd, 0)) : 0.0f;
          T.xa1[r] = RG(NFCB200_OFF_X, slot_at(b.sdd + b.p2, 0));
          T.ca2[r] = RG(b.corr, wrap(c + b.p2, b.p1));
@@ -3346,14 +3413,14 @@ struct Machine
       for (int r = 1; r <= 2; r++)
       {
          const RateParams &b = P.F[r];
-         const u32 c = L.fe.cF[r - 1];
+         const u32 c = F.cF[r - 1];
          T.xf1[r - 1] = RG(NFCB200_OFF_X, slot_at(b.sdd + b.p2, 0));
          T.cf2[r - 1] = RG(b.corr, wrap(c + b.p2, b.p1));
          T.cf3[r - 1] = RG(b.corr, c ? c - 1 : b.p1 - 1);
       }
       T.xv0 = RG(NFCB200_OFF_X, slot_at(P.V.sdd, 0));
       T.xv1 = RG(NFCB200_OFF_X, slot_at(P.V.sdd + P.V.p2, 0));
-      T.cv2 = RG(P.V.corr, wrap(L.fe.cV1 + P.V.p2, P.V.p1));
+      T.cv2 = RG(P.V.corr, wrap(F.cV1 + P.V.p2, P.V.p1));
    }
 
    // hints for the taps of the NEXT step (ring phases advance by one; slot c of a correlation ring, read as c - 1 by the
@@ -3361,7 +3428,7 @@ struct Machine
    NFC_HD void prefetch_next_taps()
    {
 #if defined(__CUDA_ARCH__)
-      if (L.lock == LOCK_NONE)
+      if (F.lock == LOCK_NONE)
       {
          for (int r = 0; r < 3; r++)
          {
@@ -3369,7 +3436,7 @@ struct Machine
             if (b.sdd)
                prefetch_slot(NFCB200_OFF_X, slot_at(b.sdd, 1));
             prefetch_slot(NFCB200_OFF_X, slot_at(b.sdd + b.p2, 1));
-            prefetch_slot(b.corr, wrap(wrap(L.fe.cA[r] + 1, b.p1) + b.p2, b.p1));
+            prefetch_slot(b.corr, wrap(wrap(F.cA[r] + 1, b.p1) + b.p2, b.p1));
          }
          if (P.B[1].sdd)
             prefetch_slot(NFCB200_OFF_W, slot_at(P.B[1].sdd, 1));
@@ -3377,11 +3444,11 @@ struct Machine
          {
             const RateParams &b = P.F[r];
             prefetch_slot(NFCB200_OFF_X, slot_at(b.sdd + b.p2, 1));
-            prefetch_slot(b.corr, wrap(wrap(L.fe.cF[r - 1] + 1, b.p1) + b.p2, b.p1));
+            prefetch_slot(b.corr, wrap(wrap(F.cF[r - 1] + 1, b.p1) + b.p2, b.p1));
          }
          prefetch_slot(NFCB200_OFF_X, slot_at(P.V.sdd, 1));
          prefetch_slot(NFCB200_OFF_X, slot_at(P.V.sdd + P.V.p2, 1));
-         prefetch_slot(P.V.corr, wrap(wrap(L.fe.cV1 + 1, P.V.p1) + P.V.p2, P.V.p1));
+         prefetch_slot(P.V.corr, wrap(wrap(F.cV1 + 1, P.V.p1) + P.V.p2, P.V.p1));
       }
       else
       {
@@ -3412,33 +3479,58 @@ struct Machine
    // ------------------------------------------------------------------------------------------------------------------
    NFC_HD void step(float x)
    {
+      const bool wasLocked = F.lock != LOCK_NONE;
+
+      step_body(x);
+
+      // the busy mask is only read in search mode: rebuild it after a detector did more than its idle fast path, and
+      // when a frame ended (the symbol decoders, process() and the resets rewrite the Mods freely)
+      if (slow || (wasLocked && F.lock == LOCK_NONE))
+      {
+         refresh_busy();
+         slow = false;
+      }
+
+#if defined(NFCB200_CHECK_BUSY)
+      if (F.lock == LOCK_NONE)
+      {
+         const u32 have = F.busy;
+         refresh_busy();
+         if (have != F.busy)
+            nfcb200_busy_mismatch(F.clk, have, F.busy);
+      }
+#endif
+   }
+
+   NFC_HD void step_body(float x)
+   {
       front_advance();
 
       if (TAPS == 2)
       {
          // search mode with the detectors past their gate: fetch every tap now (the envelope gate below is decided by
          // this step's sample, an unused fetch is harmless); locked lanes get hints for the next step
-         tapsValid = L.lock == LOCK_NONE && !(L.fe.k - 1 < L.gate);
+         tapsValid = F.lock == LOCK_NONE && !(F.k - 1 < F.gate);
          if (tapsValid)
             load_search_taps();
-         else if (L.lock != LOCK_NONE)
+         else if (F.lock != LOCK_NONE)
             prefetch_locked_taps(1);
       }
       else if (TAPS == 1)
       {
-         if (L.lock != LOCK_NONE || !(L.fe.k < L.gate))
+         if (F.lock != LOCK_NONE || !(F.k < F.gate))
             prefetch_next_taps();
       }
 
       front(x);
 
-      if (L.lock == LOCK_NONE)
+      if (F.lock == LOCK_NONE)
       {
-         if (L.fe.k > L.warm)
+         if (F.k > F.warm)
             detect_carrier();
 
          // `signalClock < BUFFER_SIZE` and `signalEnvelope < powerLevelThreshold` gates of every detectModulation
-         if (L.fe.k - 1 < L.gate || L.fe.env < P.power)
+         if (F.k - 1 < F.gate || F.env < P.power)
             return;
 
          if ((P.enabled & EN_A) && A_detect())
@@ -3455,7 +3547,7 @@ struct Machine
 
       u32 frameType;
 
-      switch (L.lock)
+      switch (F.lock)
       {
          case LOCK_A:
             frameType = L.c.t[TECH_A].fs.frameType;
@@ -3507,13 +3599,13 @@ struct Machine
 
    NFC_HD bool dormant() const
    {
-      if (L.lock != LOCK_NONE)
+      if (F.lock != LOCK_NONE)
          return false;
 
-      if (L.fe.closed >= 16) // envelope not settled
+      if (F.closed >= 16) // envelope not settled
          return false;
 
-      const u32 clk = L.fe.clk;
+      const u32 clk = F.clk;
       const u32 horizon = P.V.p0 + 2; // longest recover timeout (NfcV.cpp:287) + margin
 
       for (int r = 0; r < 3; r++)
@@ -3527,7 +3619,7 @@ struct Machine
          // a stalled NFC-B SOF search reacts to edges above ITS OWN threshold (NfcB.cpp:313, 327, 366, 380); the
          // screening kernel only guarantees to flag edges above modMin * envelope, so a more sensitive residue keeps
          // the lane awake
-         if (L.c.mB[r].symbolStartTime && L.c.mB[r].searchValueThreshold < L.fe.env * P.thr[TECH_B].modMin)
+         if (L.c.mB[r].symbolStartTime && L.c.mB[r].searchValueThreshold < F.env * P.thr[TECH_B].modMin)
             return false;
       }
       return mod_dormant(L.c.mV, clk, horizon);
@@ -3713,11 +3805,11 @@ NFC_HD void lane_begin(Lane &L, const Params &P, const Carry &carry, u32 first, 
    L.fe.cV1 = P.V.c1 ? P.V.c1 - 1 : P.V.p1 - 1;
    L.fe.cV0 = P.V.c0 ? P.V.c0 - 1 : P.V.p0 - 1;
 
-   L.warm = first ? warm : 0;
+   L.fe.warm = first ? warm : 0;
    // detectors stay off for the first 1024 samples of a stream like in the reference (signalClock < BUFFER_SIZE); a
    // cold-started lane keeps them off until 512 samples before its own region: enough to refill the correlation rings
    // (longest period 378), while the front end alone converges over the rest of the halo
-   L.gate = (first && warm > NFCB200_RING + 512) ? warm - 512 : NFCB200_RING;
+   L.fe.gate = (first && warm > NFCB200_RING + 512) ? warm - 512 : NFCB200_RING;
 }
 
 }

@@ -389,6 +389,11 @@ __global__ void __launch_bounds__(LANE_THREADS, MINB) lanes_kernel(LaneConfig c,
    float *rg = c.scratch + (size_t) wg * NFCB200_SCRATCH_FLOATS * 32 + lane;
    u8 *sb = c.sbuf + ((size_t) wg * 32 + lane) * 512;
 
+   // the per-sample state of every lane (nfc_core.h Front): 31 words per thread, odd stride
+   static_assert(sizeof(Front) == 31 * 4, "Front must stay 31 words: odd shared-memory stride");
+   __shared__ u32 hot[LANE_THREADS * (sizeof(Front) / 4)];
+   Front &F = *reinterpret_cast<Front *>(&hot[threadIdx.x * (sizeof(Front) / 4)]);
+
    for (;;)
    {
       uint32_t base = 0;
@@ -411,6 +416,14 @@ __global__ void __launch_bounds__(LANE_THREADS, MINB) lanes_kernel(LaneConfig c,
       LaneRec &R = c.lanes[li];
 
       Lane L;
+      if (!have)
+      {
+         u32 *raw = (u32 *) &L.fe;
+         for (u32 i = 0; i < sizeof(Front) / 4; i++)
+            raw[i] = 0;
+         for (u32 i = 0; i < sizeof(Carry) / 4; i++)
+            ((u32 *) &L.c)[i] = 0;
+      }
       DeviceSink sink;
       sink.pool = c.pool;
       sink.lane = li;
@@ -420,7 +433,8 @@ __global__ void __launch_bounds__(LANE_THREADS, MINB) lanes_kernel(LaneConfig c,
       if (have)
          lane_begin(L, dP, R.in, R.first, NFCB200_HALO);
 
-      Machine<32, DeviceSink, TAPS> M(dP, L, rg, sb, sink);
+      Machine<32, DeviceSink, TAPS> M(dP, L, F, rg, sb, sink);
+      M.reload_front();
 
       const uint64_t streamBase = have ? (uint64_t) R.stream * c.n_samples : 0;
       const uint8_t *flags = c.flags + (have ? (size_t) R.stream * c.n_blocks : 0);
@@ -565,7 +579,7 @@ __global__ void stream_kernel(StreamConfig c, const __grid_constant__ Params dP)
    sink.gen = 1;
    sink.seq = S.seq;
 
-   Machine<1, DeviceSink> M(dP, L, c.scratch, c.sbuf, sink);
+   Machine<1, DeviceSink> M(dP, L, L.fe, c.scratch, c.sbuf, sink);
 
    u32 pos = S.pos;
    u32 running = S.running;
@@ -613,6 +627,7 @@ __global__ void stream_kernel(StreamConfig c, const __grid_constant__ Params dP)
             for (u32 i = NFCB200_OFF_CA; i < NFCB200_SCRATCH_FLOATS; i++)
                c.scratch[i] = 0.0f;
             lane_begin(L, dP, S.carry, first, first ? NFCB200_HALO : 0);
+            M.reload_front();
             pos = first;
          }
          // else: too close for a cold start and the parked machine is still positioned at pos: resume it

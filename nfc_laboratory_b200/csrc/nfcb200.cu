@@ -152,6 +152,7 @@ struct nfcb200_handle
 static int setup_params(nfcb200_handle *h, u32 sampleRate)
 {
    Params &P = h->P;
+   h->paramsRate = 0; // the block is rebuilt in place: a rejected rate must not leave the previous rate marked as current
    memset(&P, 0, sizeof(P));
    params_defaults(&P);
    P.enabled = h->cfg.enabled & 0xF;

@@ -11,6 +11,15 @@
 #include <cstring>
 #include <cstdlib>
 #include <vector>
+#include <cstdio>
+
+// the host build always cross-checks the detectors' busy mask against the Mod fields it summarises (nfc_core.h step())
+#define NFCB200_CHECK_BUSY 1
+static inline void nfcb200_busy_mismatch(unsigned clk, unsigned have, unsigned want)
+{
+   std::fprintf(stderr, "host_sim: busy mask out of date at clock %u: have %02x, fields say %02x\n", clk, have, want);
+   std::abort();
+}
 
 #include "../../nfc_laboratory_b200/csrc/nfc_chain.h"
 
@@ -122,7 +131,8 @@ long hostsim_run(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t ena
    lane_begin(L, P, carry, first, warm);
 
    Sink sink {out, cap, 0};
-   Machine<1, Sink, NFCB200_SIM_TAPS> M(P, L, scratch.data(), sb.data(), sink);
+   Machine<1, Sink, NFCB200_SIM_TAPS> M(P, L, L.fe, scratch.data(), sb.data(), sink);
+   M.reload_front();
 
    uint64_t pos = first;
 
@@ -146,7 +156,7 @@ long hostsim_run(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t ena
    {
       res->stop = (uint32_t) pos;
       res->dormant = M.dormant();
-      res->locked = L.lock;
+      res->locked = L.fe.lock;
       res->reserved = 0;
    }
 
@@ -214,7 +224,8 @@ long hostsim_pipeline(const float *mag, uint64_t n, uint32_t sampleRate, uint32_
          Lane L;
          lane_begin(L, P, R.in, R.first, NFCB200_HALO);
 
-         Machine<1, Sink, NFCB200_SIM_TAPS> M(P, L, scratch.data(), sb.data(), sink);
+         Machine<1, Sink, NFCB200_SIM_TAPS> M(P, L, L.fe, scratch.data(), sb.data(), sink);
+   M.reload_front();
 
          uint32_t pos = R.first, kw = 0, stepped = 0;
 
