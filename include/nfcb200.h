@@ -60,7 +60,7 @@ typedef struct nfcb200_frame
    double time_start;     /* double(sample_start) / double(sample_rate)                            */
    double time_end;
    double date_time;      /* streamTime + time_start                                               */
-   uint8_t data[512];
+   uint8_t data[512];     /* `length` payload bytes, zero padded to the next 64-byte boundary; the rest is not written */
 } nfcb200_frame;
 
 /* decoder configuration: the NfcDecoder setters (NfcDecoder.h:47-117) / RadioDecoderTask JSON keys

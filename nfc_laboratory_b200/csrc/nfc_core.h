@@ -215,9 +215,38 @@ struct SearchTaps
    float xv0, xv1, cv2;                  // NFC-V: x[t-sdd], x[t-sdd-p2], C[fp2]
 };
 
-template <int STRIDE, class SINK, int TAPS = 0>
+// CG: ring accesses bypass the L1 cache (ld/st.global.cg).  A ring line is written once and read a few times hundreds
+// of steps later -- no L1 reuse -- while the lanes' local state and sample lines live in the same L1.
+template <int STRIDE, class SINK, int TAPS = 0, bool CG = false>
 struct Machine
 {
+   // one ring word: converts to float (load) and takes a float (store)
+   struct RingRef
+   {
+      float *p;
+
+      NFC_HD operator float() const
+      {
+#if defined(__CUDA_ARCH__)
+         if (CG)
+            return __ldcg(p);
+#endif
+         return *p;
+      }
+
+      NFC_HD void operator=(float v) const
+      {
+#if defined(__CUDA_ARCH__)
+         if (CG)
+         {
+            __stcg(p, v);
+            return;
+         }
+#endif
+         *p = v;
+      }
+   };
+
    const Params &P;
    Lane &L;
    Front &F;  // the per-sample state: L.fe itself, or its working copy in shared memory (device lanes)
@@ -226,11 +255,12 @@ struct Machine
    SINK &sink;
    SearchTaps T;      // TAPS == 2: this step's taps
    bool tapsValid;    // TAPS == 2: T was loaded for this step
+   bool pollTaps;     // TAPS == 2: slots [0] of T hold the taps of the locked NFC-A poll symbol decoder for this step
    float curX, curW;  // sample and edge value of the current step (ring slot of delay 0)
    bool slow;         // a detector left its idle fast path during this step: F.busy must be rebuilt
 
    NFC_HD Machine(const Params &p, Lane &l, Front &f, float *r, u8 *s, SINK &k)
-      : P(p), L(l), F(f), rg(r), sb(s), sink(k), tapsValid(false), curX(0), curW(0), slow(false)
+      : P(p), L(l), F(f), rg(r), sb(s), sink(k), tapsValid(false), pollTaps(false), curX(0), curW(0), slow(false)
    {
    }
 
@@ -282,7 +312,7 @@ struct Machine
       F.busy = b;
    }
 
-#define RG(off, i) rg[((off) + (i)) * STRIDE]
+#define RG(off, i) (RingRef {&rg[((off) + (i)) * STRIDE]})
 #define SMP(off, delay) RG(off, (F.k + F.kbase - (delay)) & (NFCB200_RING - 1))
 
    NFC_HD void zero_mod(Mod &m)
@@ -1034,16 +1064,20 @@ struct Machine
       u32 fp1 = F.cA[F.lockRate], fp2, fp3;
       corr_points(fp1, b.p1, b.p2, fp2, fp3);
 
-      FI(m) += SMP(NFCB200_OFF_X, b.sdd);
-      FI(m) -= SMP(NFCB200_OFF_X, b.sdd + b.p2);
+      const bool hoisted = TAPS == 2 && pollTaps;
+      FI(m) += hoisted ? (b.sdd ? T.xa0[0] : curX) : (float) SMP(NFCB200_OFF_X, b.sdd);
+      FI(m) -= hoisted ? T.xa1[0] : (float) SMP(NFCB200_OFF_X, b.sdd + b.p2);
       RG(b.corr, fp1) = FI(m);
 
-      float s0 = FI(m) - RG(b.corr, fp2);
-      float s1 = RG(b.corr, fp2) - RG(b.corr, fp3);
-      float sd = fabsf(s0 - s1) / (float) b.p2;
+      const float c2 = hoisted ? T.ca2[0] : (float) RG(b.corr, fp2);
+      const float c3 = hoisted ? T.ca3[0] : (float) RG(b.corr, fp3);
+      float s0 = FI(m) - c2;
+      float s1 = c2 - c3;
 
-      if (clk < m.searchStartTime)
+      if (clk < m.searchStartTime) // the quotient below is only read past this point
          return A_Invalid;
+
+      float sd = fabsf(s0 - s1) / (float) b.p2;
 
       if (sd > m.correlatedPeakValue && sd > m.searchValueThreshold) // :858
       {
@@ -3378,8 +3412,8 @@ struct Machine
    NFC_HD void prefetch_slot(u32 off, u32 index)
    {
 #if defined(__CUDA_ARCH__)
-      const float *ptr = &RG(off, index);
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+      const float *ptr = &rg[(off + index) * STRIDE];
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 #else
       (void) off;
       (void) index;
@@ -3421,6 +3455,17 @@ struct Machine
       T.xv0 = RG(NFCB200_OFF_X, slot_at(P.V.sdd, 0));
       T.xv1 = RG(NFCB200_OFF_X, slot_at(P.V.sdd + P.V.p2, 0));
       T.cv2 = RG(P.V.corr, wrap(F.cV1 + P.V.p2, P.V.p1));
+   }
+
+   // the four taps of A_poll_symbol() (the longest-running locked state of an NFC-A capture), same idea
+   NFC_HD void load_poll_taps()
+   {
+      const RateParams &b = P.A[F.lockRate];
+      const u32 c = F.cA[F.lockRate];
+      T.xa0[0] = b.sdd ? RG(NFCB200_OFF_X, slot_at(b.sdd, 0)) : 0.0f;
+      T.xa1[0] = RG(NFCB200_OFF_X, slot_at(b.sdd + b.p2, 0));
+      T.ca2[0] = RG(b.corr, wrap(c + b.p2, b.p1));
+      T.ca3[0] = RG(b.corr, c ? c - 1 : b.p1 - 1);
    }
 
    // hints for the taps of the NEXT step (ring phases advance by one; slot c of a correlation ring, read as c - 1 by the
@@ -3511,8 +3556,11 @@ struct Machine
          // search mode with the detectors past their gate: fetch every tap now (the envelope gate below is decided by
          // this step's sample, an unused fetch is harmless); locked lanes get hints for the next step
          tapsValid = F.lock == LOCK_NONE && !(F.k - 1 < F.gate);
+         pollTaps = F.lock == LOCK_A && L.c.t[TECH_A].fs.frameType == FT_Poll;
          if (tapsValid)
             load_search_taps();
+         else if (pollTaps)
+            load_poll_taps();
          else if (F.lock != LOCK_NONE)
             prefetch_locked_taps(1);
       }

@@ -123,7 +123,13 @@ __device__ __forceinline__ float2 load_raw(const void *samples, int sigtype, uin
    switch (sigtype)
    {
       case SIG_IQ_F32:
-         return __ldg(((const float2 *) samples) + idx);
+      {
+         // a volatile load keeps its place in the instruction stream: the compiler would otherwise sink a read-only load
+         // to its use one step later, which defeats the point of requesting the sample early
+         float2 v;
+         asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(((const float2 *) samples) + idx));
+         return v;
+      }
       case SIG_MAG_F32:
          return make_float2(__ldg(((const float *) samples) + idx), 0.0f);
       case SIG_MAG_S16:
@@ -380,7 +386,7 @@ struct LaneConfig
 #define LANE_THREADS 128
 
 // TAPS: how the detectors fetch their ring taps (nfc_core.h); MINB: resident blocks per SM the register budget is cut for
-template <int TAPS, int MINB>
+template <int TAPS, int MINB, bool CG>
 __global__ void __launch_bounds__(LANE_THREADS, MINB) lanes_kernel(LaneConfig c, const __grid_constant__ Params dP)
 {
    const uint32_t lane = threadIdx.x & 31;
@@ -433,7 +439,7 @@ __global__ void __launch_bounds__(LANE_THREADS, MINB) lanes_kernel(LaneConfig c,
       if (have)
          lane_begin(L, dP, R.in, R.first, NFCB200_HALO);
 
-      Machine<32, DeviceSink, TAPS> M(dP, L, F, rg, sb, sink);
+      Machine<32, DeviceSink, TAPS, CG> M(dP, L, F, rg, sb, sink);
       M.reload_front();
 
       const uint64_t streamBase = have ? (uint64_t) R.stream * c.n_samples : 0;

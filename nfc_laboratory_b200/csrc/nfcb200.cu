@@ -87,6 +87,43 @@ struct DevBuf
    }
 };
 
+// pinned host staging that only grows (frame records travel device -> host at link speed, not through a pageable bounce)
+struct HostBuf
+{
+   void *ptr = nullptr;
+   size_t cap = 0;
+
+   int reserve(size_t bytes)
+   {
+      if (bytes <= cap)
+         return 0;
+      if (ptr)
+         cudaFreeHost(ptr);
+      ptr = nullptr;
+      cap = 0;
+      size_t want = bytes + bytes / 4 + 4096;
+      cudaError_t e = cudaHostAlloc(&ptr, want, cudaHostAllocDefault);
+      if (e != cudaSuccess)
+         return fail(NFCB200_ERR_CUDA, "cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
+      cap = want;
+      return 0;
+   }
+
+   void release()
+   {
+      if (ptr)
+         cudaFreeHost(ptr);
+      ptr = nullptr;
+      cap = 0;
+   }
+
+   template <class T>
+   T *as() const
+   {
+      return (T *) ptr;
+   }
+};
+
 struct Counters
 {
    u32 poolCount;
@@ -131,6 +168,9 @@ struct nfcb200_handle
 
    int laneTaps = 2;   // lanes_kernel variant: ring tap fetch mode (NFCB200_LANE_TAPS overrides, development knob)
    int laneBlocks = 4; // resident lane blocks per SM (NFCB200_LANE_BLOCKS overrides)
+   int laneCg = 1;     // ring accesses bypass L1 (NFCB200_LANE_CG overrides)
+
+   HostBuf hRecs, hExt, hMeta, hStreamOf; // gather staging
 
    DevBuf samples, flags, bsum, counts, offsets, lanes, queue, scratch, sbuf, pool, ext, meta, streamOf, counters;
    nfcb200_stats stats;
@@ -177,22 +217,23 @@ static int setup_params(nfcb200_handle *h, u32 sampleRate)
    return 0;
 }
 
-// K2 launch: tap fetch mode x resident blocks per SM (register budget), chosen at create time
+// K2 launch: tap fetch mode x resident blocks per SM (register budget) x ring cache policy, chosen at create time
 static void launch_lanes(const nfcb200_handle *h, const LaneConfig &lc, u32 blocks, cudaStream_t st)
 {
-#define NFCB200_LANES(T, B) lanes_kernel<T, B><<<blocks, LANE_THREADS, 0, st>>>(lc, h->P)
+#define NFCB200_LANES(T, B, G) lanes_kernel<T, B, G><<<blocks, LANE_THREADS, 0, st>>>(lc, h->P)
    const int b = h->laneBlocks;
-   switch (h->laneTaps)
+   if (h->laneTaps == 0)
    {
-      case 0:
-         if (b >= 4) NFCB200_LANES(0, 4); else if (b == 3) NFCB200_LANES(0, 3); else NFCB200_LANES(0, 2);
-         break;
-      case 1:
-         if (b >= 4) NFCB200_LANES(1, 4); else if (b == 3) NFCB200_LANES(1, 3); else NFCB200_LANES(1, 2);
-         break;
-      default:
-         if (b >= 4) NFCB200_LANES(2, 4); else if (b == 3) NFCB200_LANES(2, 3); else NFCB200_LANES(2, 2);
-         break;
+      if (h->laneCg) { if (b >= 6) NFCB200_LANES(0, 6, true); else NFCB200_LANES(0, 4, true); }
+      else NFCB200_LANES(0, 4, false);
+   }
+   else if (h->laneCg)
+   {
+      if (b >= 8) NFCB200_LANES(2, 8, true); else if (b >= 6) NFCB200_LANES(2, 6, true); else NFCB200_LANES(2, 4, true);
+   }
+   else
+   {
+      if (b >= 6) NFCB200_LANES(2, 6, false); else NFCB200_LANES(2, 4, false);
    }
 #undef NFCB200_LANES
 }
@@ -340,7 +381,11 @@ int nfcb200_create(const nfcb200_config *cfg, nfcb200_handle **out)
    if (const char *e = getenv("NFCB200_LANE_TAPS"))
       h->laneTaps = std::max(0, std::min(2, atoi(e)));
    if (const char *e = getenv("NFCB200_LANE_BLOCKS"))
-      h->laneBlocks = std::max(2, std::min(4, atoi(e)));
+      h->laneBlocks = atoi(e) >= 8 ? 8 : atoi(e) >= 6 ? 6 : 4;
+   if (const char *e = getenv("NFCB200_LANE_CG"))
+      h->laneCg = atoi(e) ? 1 : 0;
+   if (h->laneTaps == 1)
+      h->laneTaps = 2;
 
    cudaFuncSetAttribute(screen_kernel<SIG_IQ_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem));
    cudaFuncSetAttribute(screen_kernel<SIG_MAG_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem));
@@ -360,6 +405,9 @@ void nfcb200_destroy(nfcb200_handle *h)
    DevBuf *bufs[] = {&h->samples, &h->flags, &h->bsum, &h->counts, &h->offsets, &h->lanes, &h->queue, &h->scratch, &h->sbuf, &h->pool, &h->ext, &h->meta,
                      &h->streamOf, &h->counters, &h->sState, &h->sScratch, &h->sSbuf, &h->sSamples, &h->sFlags, &h->sBsum, &h->sCounts};
    for (DevBuf *b: bufs)
+      b->release();
+   HostBuf *hbufs[] = {&h->hRecs, &h->hExt, &h->hMeta, &h->hStreamOf};
+   for (HostBuf *b: hbufs)
       b->release();
    for (auto &ev: h->ev)
       if (ev)
@@ -410,9 +458,11 @@ int nfcb200_get_block_flags(nfcb200_handle *h, uint8_t *out, uint64_t cap, uint6
 }
 
 // convert one pool record to the ABI frame
-static void emit_frame(const nfcb200_handle *h, const FrameRec &r, const std::vector<unsigned char> &ext, u32 stream, u32 sampleRate, nfcb200_frame &o)
+static void emit_frame(const nfcb200_handle *h, const FrameRec &r, const unsigned char *ext, size_t extBytes, u32 stream, u32 sampleRate, nfcb200_frame &o)
 {
-   memset(&o, 0, sizeof(o));
+   // header, payload, and zeros up to the next 64-byte boundary after the payload (the rest of data[] is not touched:
+   // a batch of 4e5 frames would otherwise write 250 MB of zeros)
+   memset(&o, 0, offsetof(nfcb200_frame, data));
    o.stream = stream;
    o.tech_type = r.tech;
    o.frame_type = r.type;
@@ -426,11 +476,21 @@ static void emit_frame(const nfcb200_handle *h, const FrameRec &r, const std::ve
    o.time_end = (double) r.end / (double) sampleRate;
    o.date_time = (double) h->P.streamTime + o.time_start;
    u32 len = r.len > 512 ? 512 : r.len;
-   o.length = len;
    u32 inl = len < 80 ? len : 80;
    memcpy(o.data, r.data, inl);
-   if (len > 80 && r.ext != 0xFFFFFFFFu && (size_t) r.ext * 128 + (len - 80) <= ext.size())
-      memcpy(o.data + 80, ext.data() + (size_t) r.ext * 128, len - 80);
+   if (len > 80)
+   {
+      if (r.ext != 0xFFFFFFFFu && (size_t) r.ext * 128 + (len - 80) <= extBytes)
+         memcpy(o.data + 80, ext + (size_t) r.ext * 128, len - 80);
+      else
+         len = 80; // extension chunk missing (pool exhausted, reported by the caller): truncated payload
+   }
+   o.length = len;
+   u32 padEnd = (len + 63u) & ~63u;
+   if (padEnd > 512)
+      padEnd = 512;
+   if (padEnd > len)
+      memset(o.data + len, 0, padEnd - len);
 }
 
 // decode one device-resident batch [n_streams][n_samples]; frames are written to out[outOffset ...) (bounded by cap) with
@@ -701,16 +761,27 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    if (hc.poolCount > poolCap || hc.extCount > extCap)
       return fail(NFCB200_ERR_CAPACITY, "frame pool exhausted (%u frames, %u extension chunks)", hc.poolCount, hc.extCount);
 
-   std::vector<FrameRec> recs(hc.poolCount);
-   std::vector<unsigned char> ext((size_t) hc.extCount * 128);
-   std::vector<u32> meta(nLanes), streamOf(nLanes);
+   {
+      int rc = h->hRecs.reserve((size_t) hc.poolCount * sizeof(FrameRec));
+      rc = rc ? rc : h->hExt.reserve((size_t) hc.extCount * 128);
+      rc = rc ? rc : h->hMeta.reserve((size_t) nLanes * sizeof(u32));
+      rc = rc ? rc : h->hStreamOf.reserve((size_t) nLanes * sizeof(u32));
+      if (rc)
+         return rc;
+   }
+
+   const FrameRec *recs = h->hRecs.as<FrameRec>();
+   const unsigned char *ext = h->hExt.as<unsigned char>();
+   const u32 *meta = h->hMeta.as<u32>();
+   const u32 *streamOf = h->hStreamOf.as<u32>();
+   const u32 nRecs = hc.poolCount;
 
    if (hc.poolCount)
-      CUDA_TRY(cudaMemcpyAsync(recs.data(), h->pool.ptr, (size_t) hc.poolCount * sizeof(FrameRec), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(h->hRecs.ptr, h->pool.ptr, (size_t) hc.poolCount * sizeof(FrameRec), cudaMemcpyDeviceToHost, st));
    if (hc.extCount)
-      CUDA_TRY(cudaMemcpyAsync(ext.data(), h->ext.ptr, ext.size(), cudaMemcpyDeviceToHost, st));
-   CUDA_TRY(cudaMemcpyAsync(meta.data(), h->meta.ptr, (size_t) nLanes * sizeof(u32), cudaMemcpyDeviceToHost, st));
-   CUDA_TRY(cudaMemcpyAsync(streamOf.data(), h->streamOf.ptr, (size_t) nLanes * sizeof(u32), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(h->hExt.ptr, h->ext.ptr, (size_t) hc.extCount * 128, cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaMemcpyAsync(h->hMeta.ptr, h->meta.ptr, (size_t) nLanes * sizeof(u32), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaMemcpyAsync(h->hStreamOf.ptr, h->streamOf.ptr, (size_t) nLanes * sizeof(u32), cudaMemcpyDeviceToHost, st));
 
    cudaEventRecord(h->ev[5], st);
    CUDA_TRY(cudaStreamSynchronize(st));
@@ -719,8 +790,9 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    // keep only the frames of the final generation of live lanes.  Lanes are globally ordered by (stream, time) and a
    // run numbers its frames 0 .. nframes-1, so the output position of a frame is a counting sort: offset[lane] + seq
    std::vector<u32> laneCount(nLanes + 1, 0);
-   for (const FrameRec &r: recs)
+   for (u32 i = 0; i < nRecs; i++)
    {
+      const FrameRec &r = recs[i];
       if (r.lane >= nLanes)
          continue;
       u32 m = meta[r.lane];
@@ -733,7 +805,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
 
    const uint64_t nf = laneCount[nLanes];
    std::vector<u32> order(nf);
-   for (u32 i = 0; i < recs.size(); i++)
+   for (u32 i = 0; i < nRecs; i++)
    {
       const FrameRec &r = recs[i];
       if (r.lane >= nLanes)
@@ -752,7 +824,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(16, count / 4096));
       auto work = [&](uint64_t lo, uint64_t hi) {
          for (uint64_t i = lo; i < hi; i++)
-            emit_frame(h, recs[order[i]], ext, streamBase + streamOf[recs[order[i]].lane], sample_rate, out[outOffset + i]);
+            emit_frame(h, recs[order[i]], ext, (size_t) hc.extCount * 128, streamBase + streamOf[recs[order[i]].lane], sample_rate, out[outOffset + i]);
       };
       if (workers <= 1)
          work(0, count);
@@ -1192,7 +1264,7 @@ int nfcb200_stream_push(nfcb200_handle *h, const void *samples, int sigtype, uin
    for (const FrameRec &r: recs)
    {
       if (nf < cap)
-         emit_frame(h, r, ext, 0, h->sRate, out[nf]);
+         emit_frame(h, r, ext.data(), ext.size(), 0, h->sRate, out[nf]);
       nf++;
    }
 
