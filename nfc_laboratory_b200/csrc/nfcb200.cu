@@ -18,6 +18,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <atomic>
+#include <functional>
 #include <vector>
 
 #include "../../include/nfcb200.h"
@@ -168,7 +170,7 @@ struct nfcb200_handle
 
    int laneTaps = 2;   // lanes_kernel variant: ring tap fetch mode (NFCB200_LANE_TAPS overrides, development knob)
    int laneBlocks = 4; // resident lane blocks per SM (NFCB200_LANE_BLOCKS overrides)
-   int laneCg = 1;     // ring accesses bypass L1 (NFCB200_LANE_CG overrides)
+   int laneCg = 0;     // ring accesses bypass L1 (NFCB200_LANE_CG overrides; measured neutral, profiles/)
 
    HostBuf hRecs, hExt, hMeta, hStreamOf; // gather staging
 
@@ -788,55 +790,67 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    tr.mark("pool d2h");
 
    // keep only the frames of the final generation of live lanes.  Lanes are globally ordered by (stream, time) and a
-   // run numbers its frames 0 .. nframes-1, so the output position of a frame is a counting sort: offset[lane] + seq
-   std::vector<u32> laneCount(nLanes + 1, 0);
-   for (u32 i = 0; i < nRecs; i++)
-   {
-      const FrameRec &r = recs[i];
-      if (r.lane >= nLanes)
-         continue;
-      u32 m = meta[r.lane];
-      if ((m & 1) || (m >> 1) != r.gen)
-         continue;
-      laneCount[r.lane + 1]++;
-   }
-   for (u32 i = 0; i < nLanes; i++)
-      laneCount[i + 1] += laneCount[i];
+   // run numbers its frames 0 .. nframes-1, so the output position of a frame is a counting sort: offset[lane] + seq.
+   // Both passes over the records and the conversion to ABI frames run on a few host threads (4e5 frames per batch).
+   const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(16, nRecs / 4096));
+   auto parallel = [&](uint64_t count, const std::function<void(uint64_t, uint64_t)> &fn) {
+      if (workers <= 1 || count < 8192)
+      {
+         fn(0, count);
+         return;
+      }
+      std::vector<std::thread> pool;
+      const uint64_t step = (count + workers - 1) / workers;
+      for (unsigned w = 0; w < workers; w++)
+         pool.emplace_back(fn, std::min(count, w * step), std::min(count, (w + 1) * step));
+      for (auto &t: pool)
+         t.join();
+   };
 
-   const uint64_t nf = laneCount[nLanes];
-   std::vector<u32> order(nf);
-   for (u32 i = 0; i < nRecs; i++)
-   {
-      const FrameRec &r = recs[i];
+   auto kept = [&](const FrameRec &r) {
       if (r.lane >= nLanes)
-         continue;
-      u32 m = meta[r.lane];
-      if ((m & 1) || (m >> 1) != r.gen)
-         continue;
-      uint64_t pos = (uint64_t) laneCount[r.lane] + r.seq;
-      if (pos < (uint64_t) laneCount[r.lane + 1])
-         order[pos] = i;
-   }
+         return false;
+      const u32 m = meta[r.lane];
+      return !(m & 1) && (m >> 1) == r.gen;
+   };
+
+   std::vector<std::atomic<u32>> laneCount(nLanes + 1);
+   parallel(nLanes + 1, [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; i++)
+         laneCount[i].store(0, std::memory_order_relaxed);
+   });
+   parallel(nRecs, [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; i++)
+         if (kept(recs[i]))
+            laneCount[recs[i].lane + 1].fetch_add(1, std::memory_order_relaxed);
+   });
+
+   std::vector<u32> laneOff(nLanes + 1);
+   laneOff[0] = 0;
+   for (u32 i = 0; i < nLanes; i++)
+      laneOff[i + 1] = laneOff[i] + laneCount[i + 1].load(std::memory_order_relaxed);
+
+   const uint64_t nf = laneOff[nLanes];
+   std::vector<u32> order(nf);
+   parallel(nRecs, [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; i++)
+      {
+         const FrameRec &r = recs[i];
+         if (!kept(r))
+            continue;
+         const uint64_t pos = (uint64_t) laneOff[r.lane] + r.seq;
+         if (pos < (uint64_t) laneOff[r.lane + 1])
+            order[pos] = (u32) i;
+      }
+   });
 
    tr.mark("counting sort");
    {
       const uint64_t count = outOffset >= cap ? 0 : std::min<uint64_t>(nf, cap - outOffset);
-      const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(16, count / 4096));
-      auto work = [&](uint64_t lo, uint64_t hi) {
+      parallel(count, [&](uint64_t lo, uint64_t hi) {
          for (uint64_t i = lo; i < hi; i++)
             emit_frame(h, recs[order[i]], ext, (size_t) hc.extCount * 128, streamBase + streamOf[recs[order[i]].lane], sample_rate, out[outOffset + i]);
-      };
-      if (workers <= 1)
-         work(0, count);
-      else
-      {
-         std::vector<std::thread> pool;
-         const uint64_t step = (count + workers - 1) / workers;
-         for (unsigned w = 0; w < workers; w++)
-            pool.emplace_back(work, std::min(count, w * step), std::min(count, (w + 1) * step));
-         for (auto &t: pool)
-            t.join();
-      }
+      });
    }
 
    tr.mark("emit");
