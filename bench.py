@@ -104,6 +104,26 @@ def host_cores():
     return n
 
 
+def host_memory_budget():
+    """bytes of host memory this job may still use: MemAvailable, clipped by the cgroup limit when there is one"""
+    avail = 32 << 30
+    try:
+        import psutil
+        avail = int(psutil.virtual_memory().available)
+    except Exception:
+        pass
+    try:
+        with open("/sys/fs/cgroup/memory.max") as f:
+            lim = f.read().strip()
+        if lim != "max":
+            with open("/sys/fs/cgroup/memory.current") as f:
+                cur = int(f.read().strip())
+            avail = min(avail, max(0, int(lim) - cur))
+    except Exception:
+        pass
+    return avail
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -254,6 +274,9 @@ def main():
         dist.barrier()
     dt = time.perf_counter() - t0
 
+    # digest of the last resident decode (frames of this rank): the host-input decode below must reproduce it
+    digest_resident = ND.frames_digest(ND.frames_as_array(buf, nf))
+
     tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -281,13 +304,12 @@ def main():
     # ---- e2e: the same decode through the C ABI with HOST buffers (H2D inside the timed region) ---------------------------
     e2e = None
     if not args.no_e2e:
-        try:
-            import psutil
-            avail = psutil.virtual_memory().available
-        except Exception:
-            avail = 32 << 30
+        # every rank pins its own copy of (a part of) its batch: bounded by a quarter of the host memory the job may use,
+        # and by 12 GB per rank when several ranks share the host (the e2e rate is PCIe-bound either way)
+        avail = host_memory_budget()
+        limit = min(0.25 * avail / world, (96 << 30) if world == 1 else (12 << 30))
         Se = S
-        while Se > 1 and Se * n * 8 > min(0.25 * avail / world, 96 << 30):  # every rank pins its own copy; bounded host footprint
+        while Se > 1 and Se * n * 8 > limit:
             Se //= 2
         host = torch.empty((Se, n, 2), dtype=torch.float32, pin_memory=True)
         host.copy_(iq[:Se])
@@ -311,8 +333,13 @@ def main():
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         de = float(tm.item())
+        same = None
+        if Se == S:
+            same = ND.frames_digest(ND.frames_as_array(buf, nf)) == digest_resident
+            if not same:
+                raise SystemExit("the host-input decode and the device-resident decode of the same batch differ: refusing to report a number")
         e2e = {"value": world * Se * n * esteps / de / 1e6, "unit": UNIT, "h2d_bytes_per_step": Se * n * 8, "d2h_bytes_per_step": int(d2h),
-               "streams": Se, "note": "host-pinned float2 IQ -> nfcb200_decode_batch -> frames in host memory"
+               "streams": Se, "same_frames_as_resident": same, "note": "host-pinned float2 IQ -> nfcb200_decode_batch -> frames in host memory"
                                       + ("" if Se == S else " (sub-batch of %d streams: host memory bound)" % Se)}
         del host
 
@@ -347,7 +374,7 @@ def main():
             "phases_ms": {k: statistics.mean(s[k] for s in stats) for k in ("ms_screen", "ms_segment", "ms_lanes", "ms_gather", "ms_total", "ms_wall")},
             "decode": {"frames_per_step": frames_total // max(1, args.steps), "segments": st["segments"], "lanes": st["lanes"], "rounds": st["rounds"],
                        "lane_runs": st["lane_runs"], "lane_samples_frac": st["lane_samples"] / max(1, st["samples"])},
-            "parity_spot_check": parity,
+            "parity_spot_check": parity, "frames_digest": "%016x" % digest_resident,
         }
         print(json.dumps(line))
 

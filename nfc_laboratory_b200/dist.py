@@ -27,6 +27,29 @@ def frames_as_array(cbuf, n):
     return np.frombuffer(cbuf, dtype=FRAME_DTYPE, count=n)
 
 
+def frames_digest(arr):
+    """order-dependent 64-bit digest of a frame array (every header field the reference compares plus the payload bytes):
+    two decodes of the same batch -- device-resident or from host memory, one GPU or several -- must agree on it"""
+    a = np.asarray(arr)
+    n = int(a.size)
+    if n == 0:
+        return 0
+    mask = np.uint64(0xFFFFFFFFFFFFFFFF)
+    h = np.zeros(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for k, name in enumerate(("stream", "tech_type", "frame_type", "frame_flags", "frame_phase", "frame_rate", "length", "sample_start", "sample_end")):
+            h = (h * np.uint64(0x100000001B3) + a[name].astype(np.uint64) + np.uint64(k + 1)) & mask
+        L = int(a["length"].max())
+        if L:
+            d = a["data"][:, :L].astype(np.uint64)
+            live = np.arange(L, dtype=np.uint64)[None, :] < a["length"].astype(np.uint64)[:, None]
+            w = (np.arange(L, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(1)) & mask
+            h = (h + ((d + np.uint64(1)) * w[None, :] * live).sum(axis=1, dtype=np.uint64)) & mask
+        idx = np.arange(1, n + 1, dtype=np.uint64)
+        total = int(((h ^ (idx * np.uint64(0xD6E8FEB86659FD93))) * np.uint64(0xFF51AFD7ED558CCD)).sum(dtype=np.uint64))
+    return total & 0xFFFFFFFFFFFFFFFF
+
+
 def pack_frames(arr, stream_offset=0):
     """frame records (numpy FRAME_DTYPE array, e.g. a view of the decoder's output buffer) -> one flat uint8 buffer
     [u64 count][count x 80-byte headers][payload bytes back to back], packed by nfcb200_pack_frames (host threads)"""
@@ -96,3 +119,53 @@ def gather_frames(flat, device, group=None):
     if rank != 0:
         return None
     return np.concatenate([b[:s].cpu().numpy() for b, s in zip(bufs, sizes)])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# one long capture, time-sharded with a block-overlap stitch (BASELINE.json configs[4], SURVEY.md 8e)
+# ---------------------------------------------------------------------------------------------------------------------
+BLOCK = 256
+
+
+def time_shards(n_samples, n_shards, overlap):
+    """[(own_begin, own_end, window_begin, window_end)] of a capture cut into `n_shards` contiguous time shards.  A shard
+    is decoded over its window -- its own samples plus `overlap` samples either side -- by a decoder cold-started at
+    window_begin, and keeps the frames that START inside its own range.  `overlap` must exceed the longest exchange
+    (poll frame + frame waiting time + listen frame): the frame a shard keeps then always has its poll frame inside the
+    same window, which is the only context a cold-started decoder cannot re-derive (448 / 475 arbitrary
+    cold starts reproduce the full decode field for field, every miss is a listen frame whose poll was cut off)."""
+    cuts = [min(n_samples, (n_samples * r // n_shards) // BLOCK * BLOCK) for r in range(n_shards)] + [n_samples]
+    out = []
+    for r in range(n_shards):
+        b, e = cuts[r], cuts[r + 1]
+        out.append((b, e, max(0, b - overlap) // BLOCK * BLOCK, min(n_samples, e + overlap)))
+    return out
+
+
+def stitch_shard(frames, own_begin, own_end, window_begin, first):
+    """frames of one shard window (tuples (tech, type, flags, phase, rate, start, end, payload), window-relative sample
+    indices) -> the frames this shard owns, in absolute sample indices.  The first shard keeps everything before its end
+    (including the reference's two carrier-off frames at samples 0 and 1); later shards drop what starts in their
+    overlap, which also removes the cold-start artefacts of their decoder."""
+    out = []
+    for f in frames:
+        start = f[5] + window_begin
+        if (first or start >= own_begin) and start < own_end:
+            out.append(f[:5] + (start, f[6] + window_begin) + tuple(f[7:]))
+    return out
+
+
+def decode_long_capture(decode, samples, n_shards, overlap=1 << 20, rank=None):
+    """time-sharded decode of ONE capture: `decode(window) -> frames` is called once per shard (rank=None: all shards
+    here, e.g. one GPU after the other; rank=r: only shard r, for one process per GPU followed by gather_frames).
+    Exact as long as no sticky protocol state (FSD / FWT from RATS / ATTRIB, the Encrypted flag after AUTH) is set
+    further back than `overlap` before a cut -- the block-overlap stitch BASELINE.json names, stated here as it is."""
+    shards = time_shards(len(samples), n_shards, overlap)
+    todo = range(n_shards) if rank is None else [rank]
+    out = []
+    for r in todo:
+        b, e, wb, we = shards[r]
+        if e <= b:
+            continue
+        out += stitch_shard(decode(samples[wb:we]), b, e, wb, r == 0)
+    return out

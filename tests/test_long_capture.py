@@ -1,0 +1,126 @@
+"""One long capture, time-sharded with a block-overlap stitch (BASELINE.json configs[4]).
+
+CPU part: the stitch is exercised with the compiled reference decoder and with the host build of the lane pipeline as the
+per-shard decoder (every shard cold-starts at its window, like one GPU per shard would), single process and over gloo.
+GPU part: the same through the C ABI.  The bar is the full, uncut decode of the same capture, field for field."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import nfcutil as U
+import screen_ref as S
+from test_golden_oracle import committed_ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NAMES = U.fixture_names()
+OVERLAP = 400_000  # longer than the longest exchange of the regression captures (an NFC-V listen frame of 337 k samples)
+
+needs_ref = pytest.mark.skipif(U.ref_lib() is None, reason="oracle/_ref/libnfcref.so not built")
+
+
+def test_time_shards_cover_the_capture():
+    from nfc_laboratory_b200 import dist as ND
+    for n in (1, 255, 256, 100_000, 8_000_000_000):
+        for g in (1, 2, 3, 8):
+            sh = ND.time_shards(n, g, 1 << 20)
+            assert sh[0][0] == 0 and sh[-1][1] == n
+            assert all(sh[i][1] == sh[i + 1][0] for i in range(g - 1))
+            assert all(wb <= b and e <= we and wb % 256 == 0 and b % 256 == 0 for b, e, wb, we in sh)
+
+
+@needs_ref
+@pytest.mark.parametrize("name", NAMES)
+def test_stitch_with_the_reference_decoder(name):
+    """every shard decoded by the reference itself, cold-started at the shard window: stitched == uncut"""
+    from nfc_laboratory_b200 import dist as ND
+    mag, rate, _ = U.fixture_wav(name)
+    full = committed_ref(name)[0]
+    for shards in (2, 3):
+        got = ND.decode_long_capture(lambda w: U.ref_decode(np.ascontiguousarray(w), rate), mag, shards, OVERLAP)
+        assert got == full, (name, shards)
+
+
+@needs_ref
+def test_short_overlap_loses_only_frames_longer_than_the_overlap():
+    """the documented limit of the stitch: a frame longer than the overlap is lost at a cut, nothing else changes"""
+    from nfc_laboratory_b200 import dist as ND
+    mag, rate, _ = U.fixture_wav("test_NFC-V_26kbps_001")
+    full = committed_ref("test_NFC-V_26kbps_001")[0]
+    got = ND.decode_long_capture(lambda w: U.ref_decode(np.ascontiguousarray(w), rate), mag, 2, 131072)
+    missing = [f for f in full if f not in got]
+    assert [f for f in got if f not in full] == []
+    assert len(missing) == 1 and missing[0][6] - missing[0][5] > 131072
+
+
+@pytest.mark.parametrize("name", ["test_NFC-A_106kbps_424kbps_001", "test_NFC-A_424kbps_002", "test_NFC-B_106kbps_002", "test_NFC-F_212kbps_003",
+                                  "test_NFC-V_26kbps_001", "test_POLL_ABF_001"])
+def test_stitch_with_the_lane_pipeline(name):
+    """the host build of the device pipeline (screen model + speculative lanes) as the per-shard decoder"""
+    from nfc_laboratory_b200 import dist as ND
+    mag, rate, _ = U.fixture_wav(name)
+    full = committed_ref(name)[0]
+
+    def decode(w):
+        w = np.ascontiguousarray(w)
+        return U.sim_pipeline(w, S.block_flags_device_model(w, S.ScreenParams(rate)), rate)[0]
+
+    assert ND.decode_long_capture(decode, mag, 3, OVERLAP) == full
+
+
+def _worker(rank, world, port, name, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import nfcutil as V
+    from nfc_laboratory_b200 import dist as ND
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mag, rate, _ = V.fixture_wav(name)
+    mine = ND.decode_long_capture(lambda w: V.ref_decode(np.ascontiguousarray(w), rate), mag, world, OVERLAP, rank=rank)
+    a = np.zeros(len(mine), dtype=ND.FRAME_DTYPE)
+    for i, f in enumerate(mine):
+        a[i]["tech_type"], a[i]["frame_type"], a[i]["frame_flags"], a[i]["frame_phase"], a[i]["frame_rate"] = f[0], f[1], f[2], f[3], f[4]
+        a[i]["sample_start"], a[i]["sample_end"], a[i]["length"] = f[5], f[6], len(f[7])
+        a[i]["data"][: len(f[7])] = np.frombuffer(f[7], dtype=np.uint8)
+    allf = ND.gather_frames(ND.pack_frames(a), "cpu")
+    if rank == 0:
+        q.put([f[1:] for f in ND.unpack_frames(allf)])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@needs_ref
+def test_time_sharded_capture_over_gloo_world2():
+    """one process per shard, frame gather to rank 0: the concatenation in rank order is the uncut decode"""
+    import torch.multiprocessing as mp
+    name = "test_NFC-A_106kbps_424kbps_001"
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got == committed_ref(name)[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["test_NFC-A_106kbps_424kbps_001", "test_NFC-F_212kbps_003", "test_NFC-V_26kbps_001"])
+def test_time_sharded_capture_on_the_device(decoder, name):
+    """shards decoded one after the other by the CUDA path (each call cold-starts at its window)"""
+    import nfc_laboratory_b200 as N
+    from nfc_laboratory_b200 import dist as ND
+    mag, rate, _ = U.fixture_wav(name)
+    full = committed_ref(name)[0]
+
+    def decode(w):
+        return [f.key() for f in decoder.decode_batch(np.ascontiguousarray(w)[None, :], N.SIG_MAG_F32, rate)]
+
+    for shards in (2, 4):
+        assert ND.decode_long_capture(decode, mag, shards, OVERLAP) == full, (name, shards)
