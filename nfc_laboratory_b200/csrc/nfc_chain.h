@@ -19,13 +19,18 @@ namespace nfcb200 {
 
 #define NFCB200_BLOCK 256       /* samples per screening block                                   */
 #define NFCB200_HALO 4096       /* lane warm-up, samples                                          */
+#ifndef NFCB200_HALO_SHORT
+#define NFCB200_HALO_SHORT 1536 /* warm-up of a lane that never comes near the carrier thresholds */
+#endif
 #define NFCB200_PRE_BLOCKS 2    /* active margin before a flagged block                           */
+#ifndef NFCB200_POST_BLOCKS
 #define NFCB200_POST_BLOCKS 4   /* active margin after a flagged block                            */
+#endif
 #define NFCB200_GAP_BLOCKS 32   /* regions closer than this form one segment (>= 2 * HALO / BLOCK) */
 #define NFCB200_START_BLOCKS 8  /* the stream start is always a segment                           */
 
 // screening flag bits (one byte per block)
-enum { SCR_TRIGGER = 1, SCR_ACTIVE = 2, SCR_START = 4 };
+enum { SCR_TRIGGER = 1, SCR_ACTIVE = 2, SCR_START = 4, SCR_BAND = 8 };
 
 struct LaneRec
 {
@@ -47,6 +52,31 @@ struct LaneRec
    Carry in;       // carry the last run started from
    Carry out;      // canonical carry the last run retired with
 };
+
+/*
+ * First sample of the lane whose own region starts at block `bb`.  The warm-up exists for the front-end recurrences to
+ * re-converge bit-exactly; the slowest is the carrier average (0.995 per sample, ~3500 samples), which only feeds
+ * detect_carrier()'s comparisons against the power thresholds.  SCR_BAND marks the blocks in which that average (block
+ * model of segment_flags_kernel, 20 % margins) can come near a threshold.  Without such a block anywhere between the long
+ * warm-up start and the point where the average is exact again, the 0.05 % the average is still off after the short
+ * warm-up cannot change a comparison: the lane may start HALO_SHORT samples early (the deviation EMA, 0.98 per sample,
+ * the envelope and the DC filter converge in < 1000 samples, the sample rings fill in 1024, the detectors open 512
+ * samples before the region either way).
+ */
+NFC_HD u32 lane_first_sample(const u8 *flags, u32 nb, u32 bb)
+{
+   const u32 begin = bb * NFCB200_BLOCK;
+   if (begin <= NFCB200_HALO)
+      return 0;
+   const u32 lo = bb - NFCB200_HALO / NFCB200_BLOCK;
+   u32 hi = bb + (NFCB200_HALO - NFCB200_HALO_SHORT) / NFCB200_BLOCK + 1;
+   if (hi > nb)
+      hi = nb;
+   for (u32 b = lo; b < hi; b++)
+      if (flags[b] & SCR_BAND)
+         return begin - NFCB200_HALO;
+   return begin - NFCB200_HALO_SHORT;
+}
 
 // dilate the raw trigger flags into active blocks, in place: bit SCR_ACTIVE
 NFC_HD void blocks_activate(u8 *flags, u32 nb)
@@ -112,7 +142,7 @@ NFC_HD u32 blocks_segments(const u8 *flags, u32 nb, u32 nsamples, u32 stream, La
             l.stream = stream;
             l.begin = b * NFCB200_BLOCK;
             l.end = segEnd;
-            l.first = l.begin > NFCB200_HALO ? l.begin - NFCB200_HALO : 0;
+            l.first = lane_first_sample(flags, nb, b);
             l.stop = 0;
             l.lockedMask = 0;
             l.gen = 0;
@@ -341,7 +371,7 @@ NFC_HD void carry_speculate(Carry &c, const Params &P)
 
 /*
  * Walk the lanes [0, n) of ONE stream (time ordered).  Returns the number of lanes left dirty.
- *   - a lane whose predecessor was still busy less than HALO samples before its own region is swallowed: the
+ *   - a lane whose predecessor was still busy after the lane's own warm-up had started is swallowed: the
  *     predecessor's region is extended over it (and the predecessor re-runs if it had already retired earlier)
  *   - otherwise the lane's last run is valid iff, on every carry group it can observe, it started from the carry
  *     composed so far; groups it cannot observe (protocol state of techs it never locked) pass through
@@ -371,7 +401,7 @@ NFC_HD u32 chain_walk(LaneRec *lanes, u32 n, const Params &P)
          // Q's reach: where its last run stopped, or -- once its region was extended -- at least the new region end
          u32 reach = Q.stop > Q.end ? Q.stop : Q.end;
 
-         if (Q.gen > 0 && (!Q.dirty || Q.stop < Q.end) && reach + NFCB200_HALO > L.begin)
+         if (Q.gen > 0 && (!Q.dirty || Q.stop < Q.end) && reach > L.first)
          {
             L.dead = 1;
             L.dirty = 0;

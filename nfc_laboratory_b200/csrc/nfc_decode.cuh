@@ -213,7 +213,7 @@ __global__ void segment_flags_kernel(SegmentConfig c)
    const float lo = fminf(fminf(avg, avgEnd), mean);
    const float hi = fmaxf(fmaxf(avg, avgEnd), mean);
    if (lo < 1.2f * c.high && hi > 0.8f * c.low)
-      f |= SCR_TRIGGER;
+      f |= SCR_TRIGGER | SCR_BAND;
 
    c.flags[i] = f;
 }
@@ -321,7 +321,7 @@ __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Par
                l.stream = s;
                l.begin = (base + p) * NFCB200_BLOCK;
                l.end = l.begin;
-               l.first = l.begin > NFCB200_HALO ? l.begin - NFCB200_HALO : 0;
+               l.first = lane_first_sample(flags, c.n_blocks, base + p);
                l.stop = 0;
                l.lockedMask = 0;
                l.gen = 0;
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(LANE_THREADS, MINB) lanes_kernel(LaneConfig c,
       sink.seq = 0;
 
       if (have)
-         lane_begin(L, dP, R.in, R.first, NFCB200_HALO);
+         lane_begin(L, dP, R.in, R.first, R.begin - R.first);
 
       Machine<32, DeviceSink, TAPS, CG> M(dP, L, F, rg, sb, sink);
       M.reload_front();

@@ -164,6 +164,12 @@ long hostsim_run(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t ena
 }
 
 
+// first sample of the lane whose own region starts at block bb (nfc_chain.h lane_first_sample)
+uint32_t hostsim_first_sample(const uint8_t *flags, uint32_t nb, uint32_t bb)
+{
+   return lane_first_sample(flags, nb, bb);
+}
+
 /*
  * Whole-stream model of the product pipeline: segments from the screening flags (one byte per block, bit 0 = trigger),
  * one lane per segment, carry chain to the fixed point.  stats: [0] lanes [1] live lanes [2] rounds [3] lane runs
@@ -222,7 +228,7 @@ long hostsim_pipeline(const float *mag, uint64_t n, uint32_t sampleRate, uint32_
          Sink sink {buf.data(), (long) buf.size(), 0};
 
          Lane L;
-         lane_begin(L, P, R.in, R.first, NFCB200_HALO);
+         lane_begin(L, P, R.in, R.first, R.begin - R.first);
 
          Machine<1, Sink, NFCB200_SIM_TAPS> M(P, L, L.fe, scratch.data(), sb.data(), sink);
    M.reload_front();

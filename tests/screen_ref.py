@@ -126,7 +126,7 @@ def segments(act, n):
     return segs
 
 
-def block_flags_device_model(x, sp):
+def block_flags_device_model(x, sp, band=True):
     """block trigger flags as csrc/nfc_screen.cuh + segment_count_kernel compute them (float64 model):
     per-sample correlator / edge tests against the per-block envelope min(mean(block), mean(previous block)), then the
     block-granular level-shift and carrier-band rules"""
@@ -154,6 +154,7 @@ def block_flags_device_model(x, sp):
     meanW = sp.meanW0 ** BLOCK
     avg = 0.0
     pm = means[0]
+    inband = np.zeros(nb, dtype=bool)
     for b in range(nb):
         m = means[b]
         if abs(m - pm) > 0.025 * max(pm, 1e-6):
@@ -162,5 +163,9 @@ def block_flags_device_model(x, sp):
         lo, hi = min(avg, avg_end, m), max(avg, avg_end, m)
         if lo < 1.2 * sp.high and hi > 0.8 * sp.low:
             trig[b] = True
+            inband[b] = True
         pm, avg = m, avg_end
-    return trig
+    if not band:
+        return trig
+    # one byte per block as the device writes it: bit 0 trigger, bit 3 (SCR_BAND) carrier average near its thresholds
+    return trig.astype(np.uint8) | (inband.astype(np.uint8) << 3)

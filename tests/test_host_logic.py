@@ -85,3 +85,24 @@ def test_struct_layouts_match_header():
     import nfc_laboratory_b200.binding as B
     assert C.sizeof(B.CFrame) == 32 + 24 + 24 + 512
     assert C.sizeof(B.CConfig) == 4 + 4 + 4 + 48 + 4 * 3 + 20
+
+
+def test_lane_warm_up_is_long_only_near_the_carrier_thresholds():
+    """a lane starts 1536 samples before its region, 4096 when a block in which the carrier average can come near its
+    thresholds (SCR_BAND, bit 3) lies between the long warm-up start and the sample where the average is exact again"""
+    import ctypes as C
+    lib = U.sim_lib()
+    lib.hostsim_first_sample.restype = C.c_uint32
+    lib.hostsim_first_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    nb = 200
+    bb = 100
+
+    def first(band_blocks, b=bb):
+        f = np.zeros(nb, dtype=np.uint8)
+        f[list(band_blocks)] = 9
+        return lib.hostsim_first_sample(f.ctypes.data, nb, b)
+
+    assert first([]) == bb * 256 - 1536
+    assert first([bb - 16]) == bb * 256 - 4096 and first([bb - 17]) == bb * 256 - 1536
+    assert first([bb + 10]) == bb * 256 - 4096 and first([bb + 11]) == bb * 256 - 1536
+    assert first([], b=16) == 0 and first([], b=17) == 17 * 256 - 1536
