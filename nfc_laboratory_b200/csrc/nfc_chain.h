@@ -63,11 +63,13 @@ struct LaneRec
  * the envelope and the DC filter converge in < 1000 samples, the sample rings fill in 1024, the detectors open 512
  * samples before the region either way).
  */
-NFC_HD u32 lane_first_sample(const u8 *flags, u32 nb, u32 bb)
+NFC_HD u32 lane_first_sample(const u8 *flags, u32 nb, u32 bb, bool allowShort = true)
 {
    const u32 begin = bb * NFCB200_BLOCK;
    if (begin <= NFCB200_HALO)
       return 0;
+   if (!allowShort)
+      return begin - NFCB200_HALO;
    const u32 lo = bb - NFCB200_HALO / NFCB200_BLOCK;
    u32 hi = bb + (NFCB200_HALO - NFCB200_HALO_SHORT) / NFCB200_BLOCK + 1;
    if (hi > nb)

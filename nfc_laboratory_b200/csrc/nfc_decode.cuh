@@ -177,6 +177,7 @@ struct SegmentConfig
    float meanW;         // per-block decay of the carrier average: signalMeanW0 ^ 256
    uint32_t group;      // segments per lane
    uint32_t *segTotal;  // total number of segments (statistics / group sizing)
+   uint32_t shortHalo;  // lanes may use the short warm-up (nfc_chain.h lane_first_sample)
 };
 
 // ---- block-granular part of the screen, parallel over all blocks ---------------------------------------------------------
@@ -321,7 +322,7 @@ __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Par
                l.stream = s;
                l.begin = (base + p) * NFCB200_BLOCK;
                l.end = l.begin;
-               l.first = lane_first_sample(flags, c.n_blocks, base + p);
+               l.first = lane_first_sample(flags, c.n_blocks, base + p, c.shortHalo != 0);
                l.stop = 0;
                l.lockedMask = 0;
                l.gen = 0;

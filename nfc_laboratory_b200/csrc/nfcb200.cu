@@ -170,6 +170,7 @@ struct nfcb200_handle
 
    int laneTaps = 2;   // lanes_kernel variant: ring tap fetch mode (NFCB200_LANE_TAPS overrides, development knob)
    int laneBlocks = 4; // resident lane blocks per SM (NFCB200_LANE_BLOCKS overrides)
+   int shortHalo = 1;  // NFCB200_HALO_SHORT=0 forces the long warm-up for every lane (measurement knob)
    int laneCg = 0;     // ring accesses bypass L1 (NFCB200_LANE_CG overrides; measured neutral, profiles/)
 
    HostBuf hRecs, hExt, hMeta, hStreamOf; // gather staging
@@ -384,6 +385,8 @@ int nfcb200_create(const nfcb200_config *cfg, nfcb200_handle **out)
       h->laneTaps = std::max(0, std::min(2, atoi(e)));
    if (const char *e = getenv("NFCB200_LANE_BLOCKS"))
       h->laneBlocks = atoi(e) >= 8 ? 8 : atoi(e) >= 6 ? 6 : 4;
+   if (const char *e = getenv("NFCB200_HALO_SHORT"))
+      h->shortHalo = atoi(e) ? 1 : 0;
    if (const char *e = getenv("NFCB200_LANE_CG"))
       h->laneCg = atoi(e) ? 1 : 0;
    if (h->laneTaps == 1)
@@ -566,6 +569,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    sg.low = h->P.lowThr;
    sg.high = h->P.highThr;
    sg.meanW = powf(h->P.meanW0, (float) NFCB200_BLOCK);
+   sg.shortHalo = (u32) h->shortHalo;
 
    Counters *dC = h->counters.as<Counters>();
    CUDA_TRY(cudaMemsetAsync(dC, 0, sizeof(Counters), st));
