@@ -52,7 +52,8 @@ def parse_args():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)"""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md): NVML every 20 ms (a timed region of
+    a few hundred milliseconds is over before one nvidia-smi process has started); nvidia-smi is the fallback"""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -60,32 +61,75 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.sm = []
+        self.max_mhz = None
+        self.reasons = set()
+        self.power = []
         self.stop_flag = threading.Event()
+        self.source = "nvml"
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+            self.source = "nvidia-smi"
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip() != ""]
+        if ids and index < len(ids) and ids[index].strip().isdigit():
+            return int(ids[index])
+        return index
+
+    def _sample_nvml(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+        try:
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+        except Exception:
+            pass
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return
+        r = [c.strip() for c in out.split(",")]
+        if r[0].replace(".", "").isdigit():
+            self.sm.append(float(r[0]))
+        if len(r) > 1 and r[1].replace(".", "").isdigit():
+            self.max_mhz = float(r[1])
+        for k, nm in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                self.reasons.add(nm)
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nv is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02 if self.nv is not None else 0.2)
 
     def summary(self):
         self.stop_flag.set()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for k, nm in enumerate(names):
-                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None, "source": self.source}
 
 
 def host_cores():
@@ -304,10 +348,10 @@ def main():
     # ---- e2e: the same decode through the C ABI with HOST buffers (H2D inside the timed region) ---------------------------
     e2e = None
     if not args.no_e2e:
-        # every rank pins its own copy of (a part of) its batch: bounded by a quarter of the host memory the job may use,
-        # and by 12 GB per rank when several ranks share the host (the e2e rate is PCIe-bound either way)
+        # every rank pins its own copy of (a part of) its batch: the whole batch on one GPU when it fits 42 % of the host
+        # memory the job may use (cgroup limit), 12 GB per rank when several ranks share the host (PCIe-bound either way)
         avail = host_memory_budget()
-        limit = min(0.25 * avail / world, (96 << 30) if world == 1 else (12 << 30))
+        limit = min(0.42 * avail, 96 << 30) if world == 1 else min(0.25 * avail / world, 12 << 30)
         Se = S
         while Se > 1 and Se * n * 8 > limit:
             Se //= 2
