@@ -27,6 +27,14 @@
 #define NFC_HDN inline
 #endif
 
+// per-sample value tap for the tests (tests/native/host_sim.cpp defines NFCB200_TRACE_VALUES and the sink); the product
+// build compiles it away.  Channels follow the reference's signal debugger (NfcTech.h:32-37).
+#if defined(NFCB200_TRACE_VALUES)
+#define NFC_TRACE(ch, v) nfcb200_trace_value((ch), (v))
+#else
+#define NFC_TRACE(ch, v) ((void) 0)
+#endif
+
 namespace nfcb200 {
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -503,6 +511,10 @@ struct Machine
       SMP(NFCB200_OFF_W, 0) = w;
       curX = x;
       curW = w;
+      NFC_TRACE(0, x);     // NfcTech.cpp:98-101
+      NFC_TRACE(1, w);
+      NFC_TRACE(2, f.dev);
+      NFC_TRACE(3, f.avg);
       SMP(NFCB200_OFF_D, 0) = f.dev;
       SMP(NFCB200_OFF_M, 0) = f.env;
 
@@ -616,6 +628,9 @@ struct Machine
          const float c3 = hoisted ? T.ca3[rate] : RG(b.corr, fp3);
          float s0 = FI(m) - c2;
          float s1 = c2 - c3;
+
+         NFC_TRACE(4, FI(m) / (float) b.p2); // NfcA.cpp:259-261 (the highest rate writes last)
+         NFC_TRACE(5, (s0 - s1) / (float) b.p2);
 
          // idle fast path (not in the reference): with no search state pending, the rest of this iteration only acts when
          // correlatedSD < -minimumCorrelationValue (:291).  (s0 - s1) / p2 < -T needs s0 - s1 < -T p2 (1 - ulp): anything
@@ -1073,6 +1088,9 @@ struct Machine
       const float c3 = hoisted ? T.ca3[0] : (float) RG(b.corr, fp3);
       float s0 = FI(m) - c2;
       float s1 = c2 - c3;
+
+      NFC_TRACE(4, FI(m) / (float) b.p2); // NfcA.cpp:845-846
+      NFC_TRACE(5, s0 / (float) b.p4);
 
       if (clk < m.searchStartTime) // the quotient below is only read past this point
          return A_Invalid;

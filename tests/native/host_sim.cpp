@@ -8,6 +8,7 @@
  *
  * Build (tests/conftest.py does this): g++ -O2 -msse2 -mfpmath=sse -ffp-contract=off -shared -fPIC
  */
+#include <cmath>
 #include <cstring>
 #include <cstdlib>
 #include <vector>
@@ -19,6 +20,15 @@ static inline void nfcb200_busy_mismatch(unsigned clk, unsigned have, unsigned w
 {
    std::fprintf(stderr, "host_sim: busy mask out of date at clock %u: have %02x, fields say %02x\n", clk, have, want);
    std::abort();
+}
+
+// per-sample value tap (nfc_core.h NFC_TRACE): rows of 8 floats [x, w, dev, avg, ch4, ch5, locked, 0], NaN = not written
+#define NFCB200_TRACE_VALUES 1
+static float *g_trace_row = nullptr;
+static inline void nfcb200_trace_value(int channel, float value)
+{
+   if (g_trace_row && channel >= 0 && channel < 6)
+      g_trace_row[channel] = value;
 }
 
 #include "../../nfc_laboratory_b200/csrc/nfc_chain.h"
@@ -163,6 +173,51 @@ long hostsim_run(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t ena
    return sink.count;
 }
 
+
+/*
+ * One lane from sample `first` (0 = the exact stream start; otherwise a cold start with `warm` warm-up samples), every
+ * sample stepped, with the value tap on: rows[8 * i] for sample first + i.  Channel 6 = lock state after the step.
+ */
+long hostsim_trace(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t enabled, uint32_t first, uint32_t warm, float *rows)
+{
+   Params P;
+   if (!hostsim_params(sampleRate, enabled, &P))
+      return -1;
+
+   std::vector<float> scratch(NFCB200_SCRATCH_FLOATS, 0.0f);
+   std::vector<u8> sb(512, 0);
+   std::vector<sim_frame> frames(4096);
+
+   Carry carry;
+   if (first)
+      carry_speculate(carry, P);
+   else
+   {
+      carry_init(carry, P);
+      carry_canon(carry);
+   }
+
+   Lane L;
+   lane_begin(L, P, carry, first, warm);
+
+   Sink sink {frames.data(), (long) frames.size(), 0};
+   Machine<1, Sink, NFCB200_SIM_TAPS> M(P, L, L.fe, scratch.data(), sb.data(), sink);
+   M.reload_front();
+
+   const float nan = std::nanf("");
+   for (uint64_t pos = first; pos < n; pos++)
+   {
+      float *row = rows + 8 * (pos - first);
+      for (int c = 0; c < 8; c++)
+         row[c] = nan;
+      g_trace_row = row;
+      M.step(mag[pos]);
+      row[6] = (float) L.fe.lock;
+      row[7] = 0;
+   }
+   g_trace_row = nullptr;
+   return (long) (n - first);
+}
 
 // first sample of the lane whose own region starts at block bb (nfc_chain.h lane_first_sample)
 uint32_t hostsim_first_sample(const uint8_t *flags, uint32_t nb, uint32_t bb)

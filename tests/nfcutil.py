@@ -108,6 +108,46 @@ def ref_lib():
     return _ref
 
 
+TAP_SO = os.path.join(os.path.dirname(REF_SO), "libnfcref_tap.so")
+_tap = None
+
+
+def tap_lib():
+    """the reference decoder with its signal debugger recording float rows in memory (oracle/ref_tap.cpp)"""
+    global _tap
+    if _tap is None:
+        if not os.path.exists(TAP_SO):
+            return None
+        lib = C.CDLL(TAP_SO)
+        lib.nfcref_tap_decode.restype = C.c_long
+        lib.nfcref_tap_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint, C.c_void_p, C.c_long]
+        _tap = lib
+    return _tap
+
+
+def ref_tap(mag, rate=10000000, enabled=0xF, chunk=65536):
+    """[n - 1, 10] float32: the reference's per-sample debug channels (0 x, 1 w, 2 deviation, 3 average, 4.. last writer)"""
+    mag = np.ascontiguousarray(mag, dtype=np.float32)
+    rows = np.zeros((mag.size, 10), dtype=np.float32)
+    n = tap_lib().nfcref_tap_decode(mag.ctypes.data, mag.size, rate, chunk, enabled, rows.ctypes.data, mag.size)
+    assert 0 <= n <= mag.size
+    return rows[:n]
+
+
+def sim_trace(mag, rate=10000000, enabled=0xF, first=0, warm=0, stop=None):
+    """[stop - first, 8] float32 from the host build of the lane machine: the same channels 0..5 (NaN where this build
+    does not tap the value), 6 = lock state after the sample"""
+    lib = sim_lib()
+    lib.hostsim_trace.restype = C.c_long
+    lib.hostsim_trace.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    mag = np.ascontiguousarray(mag, dtype=np.float32)
+    stop = mag.size if stop is None else min(stop, mag.size)
+    rows = np.zeros((stop - first, 8), dtype=np.float32)
+    n = lib.hostsim_trace(mag.ctypes.data, stop, rate, enabled, first, warm, rows.ctypes.data)
+    assert n == stop - first
+    return rows
+
+
 def ref_decode(mag, rate=10000000, chunk=65536, enabled=0xF, cap=65536):
     """all frames (carrier frames included) of the UNMODIFIED reference decoder"""
     lib = ref_lib()
