@@ -256,68 +256,115 @@ NFC_HD float u32_as_float(u32 v)
    return c.f;
 }
 
+// what the last run of a lane recorded about its use of the incoming carry (copied from LaneRec: the word rules below
+// are shared by the scalar walk and by the warp-parallel device walk)
+struct LaneObs
+{
+   u32 lcWritten, lcLive, fZeroed, fThrWritten, fThrRead;
+   u32 fInc0[2];
+   float fThrSync[2];
+};
+
+NFC_HD LaneObs lane_obs(const LaneRec &L)
+{
+   LaneObs o;
+   o.lcWritten = L.lcWritten;
+   o.lcLive = L.lcLive;
+   o.fZeroed = L.fZeroed;
+   o.fThrWritten = L.fThrWritten;
+   o.fThrRead = L.fThrRead;
+   o.fInc0[0] = L.fInc0[0];
+   o.fInc0[1] = L.fInc0[1];
+   o.fThrSync[0] = L.fThrSync[0];
+   o.fThrSync[1] = L.fThrSync[1];
+   return o;
+}
+
 /*
- * Did the last run of L observe anything of carry group g that differs between the carry it assumed (L.in) and the
- * true carry `cur`?  Plain word equality, except for three values whose only reads are known:
+ * Word w of carry group g differs between the carry the run assumed (a) and the true carry (t): could the run have
+ * observed the difference?  Plain word equality decides, except for three values whose only reads are known:
  *   - frameStatus.lastCommand (word 0 of the protocol groups): read only by the listen-frame classifiers; a run whose
  *     first classified listen frame followed an assignment in the same run never saw the carried value (lcLive)
  *   - NFC-F searchPulseWidth: read only by `searchPulseWidth++ < 94` (NfcF.cpp:307, 844); until its first reset the run
  *     executed fInc0 such tests, all with the same outcome under both carries iff both stay below / above 94 throughout
  *   - NFC-F searchValueThreshold: until its first assignment it is compared once, against fThrSync (NfcF.cpp:313, 331)
  */
+NFC_HD bool word_observed_equal(const LaneObs &L, int g, u32 w, u32 a, u32 t)
+{
+   if (a == t)
+      return true;
+
+   if (g >= 4 && g < 8 && w == 0)
+      return !((L.lcLive >> (g - 4)) & 1);
+
+   if (g == 2)
+   {
+      u32 r = w / NFCB200_MOD_WORDS, f = w % NFCB200_MOD_WORDS;
+
+      if (f == NFCB200_W_PULSE)
+      {
+         u32 n = L.fInc0[r];
+         u32 hi = a > t ? a : t;
+         u32 lo = a > t ? t : a;
+         return n == 0 || hi + n <= 94 || lo >= 94;
+      }
+
+      if (f == NFCB200_W_THR)
+      {
+         if (!((L.fThrRead >> r) & 1))
+            return true;
+         float sv = L.fThrSync[r], fa = u32_as_float(a), ft = u32_as_float(t);
+         return (sv < fa) == (sv < ft) && (sv > fa) == (sv > ft);
+      }
+   }
+
+   return false;
+}
+
+// did the last run of L observe anything of carry group g that differs between L.in and the true carry `cur`?
 NFC_HD bool group_observed_equal(LaneRec &L, Carry &cur, int g)
 {
    u32 *pa, *pb, wa, wb;
    carry_group(L.in, g, pa, wa);
    carry_group(cur, g, pb, wb);
+   const LaneObs obs = lane_obs(L);
 
    for (u32 w = 0; w < wa; w++)
-   {
-      if (pa[w] == pb[w])
-         continue;
-
-      if (g >= 4 && g < 8 && w == 0)
-      {
-         if (!((L.lcLive >> (g - 4)) & 1))
-            continue;
+      if (!word_observed_equal(obs, g, w, pa[w], pb[w]))
          return false;
-      }
-
-      if (g == 2)
-      {
-         u32 r = w / NFCB200_MOD_WORDS, f = w % NFCB200_MOD_WORDS;
-
-         if (f == NFCB200_W_PULSE)
-         {
-            u32 n = L.fInc0[r];
-            u32 hi = pa[w] > pb[w] ? pa[w] : pb[w];
-            u32 lo = pa[w] > pb[w] ? pb[w] : pa[w];
-            if (n == 0 || hi + n <= 94 || lo >= 94)
-               continue;
-            return false;
-         }
-
-         if (f == NFCB200_W_THR)
-         {
-            if (!((L.fThrRead >> r) & 1))
-               continue;
-            float sv = L.fThrSync[r], a = u32_as_float(pa[w]), t = u32_as_float(pb[w]);
-            if ((sv < a) == (sv < t) && (sv > a) == (sv > t))
-               continue;
-            return false;
-         }
-      }
-
-      return false;
-   }
 
    return true;
+}
+
+/*
+ * Word w of carry group g after the last run of a lane, given the true carry word before it (n), the word the run
+ * retired with (o) and the word it started from (i): a word the run left unchanged passes the (corrected) incoming value
+ * through, any other keeps the run's value; the three special values follow their own bookkeeping.
+ */
+NFC_HD u32 compose_word(const LaneObs &L, int g, u32 w, u32 n, u32 o, u32 i)
+{
+   if (g >= 4 && g < 8 && w == 0)
+      return ((L.lcWritten >> (g - 4)) & 1) ? o : n;
+
+   if (g == 2)
+   {
+      u32 r = w / NFCB200_MOD_WORDS, f = w % NFCB200_MOD_WORDS;
+
+      if (f == NFCB200_W_PULSE)
+         return ((L.fZeroed >> r) & 1) ? o : n + (o - i);
+
+      if (f == NFCB200_W_THR)
+         return ((L.fThrWritten >> r) & 1) ? o : n;
+   }
+
+   return o != i ? o : n;
 }
 
 // carry after the last run of L, given the true carry `cur` before it (exact when the run is valid, a prediction else)
 NFC_HD void carry_compose(LaneRec &L, Carry &cur, Carry &next, u32 touched)
 {
    next = cur;
+   const LaneObs obs = lane_obs(L);
 
    for (int g = 0; g < NFCB200_GROUPS; g++)
    {
@@ -330,36 +377,7 @@ NFC_HD void carry_compose(LaneRec &L, Carry &cur, Carry &next, u32 touched)
       carry_group(L.in, g, pi, wi);
 
       for (u32 w = 0; w < wn; w++)
-      {
-         if (g >= 4 && g < 8 && w == 0)
-         {
-            if ((L.lcWritten >> (g - 4)) & 1)
-               pn[w] = po[w];
-            continue;
-         }
-
-         if (g == 2)
-         {
-            u32 r = w / NFCB200_MOD_WORDS, f = w % NFCB200_MOD_WORDS;
-
-            if (f == NFCB200_W_PULSE)
-            {
-               pn[w] = ((L.fZeroed >> r) & 1) ? po[w] : pn[w] + (po[w] - pi[w]);
-               continue;
-            }
-
-            if (f == NFCB200_W_THR)
-            {
-               if ((L.fThrWritten >> r) & 1)
-                  pn[w] = po[w];
-               continue;
-            }
-         }
-
-         // a word the run left unchanged passes the (corrected) incoming value through, any other keeps the run's value
-         if (po[w] != pi[w])
-            pn[w] = po[w];
-      }
+         pn[w] = compose_word(obs, g, w, pn[w], po[w], pi[w]);
    }
 }
 

@@ -519,6 +519,155 @@ __global__ void chain_kernel(ChainConfig c, const __grid_constant__ Params dP)
    }
 }
 
+/*
+ * The same walk, one WARP per stream: the sequential part is the loop over the lanes of the stream, but everything done
+ * per lane is word-parallel -- 246 carry words compared (word_observed_equal) and composed (compose_word) -- and the lane
+ * records are read with coalesced loads instead of one thread chasing 2 kB per lane.  The true carry lives in shared
+ * memory.  Control flow is uniform across the warp (every thread evaluates the same scalar fields); lane 0 writes the
+ * scalar results.  Must stay equivalent to chain_walk() (nfc_chain.h), which the CPU tests exercise.
+ */
+#define CHAIN_WARPS 4
+#define CARRY_WORDS (sizeof(Carry) / 4)
+
+__device__ __forceinline__ void carry_word_group(u32 w, int &g, u32 &wi)
+{
+   const u32 mod = NFCB200_MOD_WORDS, tech = sizeof(TechSt) / 4;
+   if (w < 3 * mod) { g = 0; wi = w; }
+   else if (w < 5 * mod) { g = 1; wi = w - 3 * mod; }
+   else if (w < 7 * mod) { g = 2; wi = w - 5 * mod; }
+   else if (w < 8 * mod) { g = 3; wi = w - 7 * mod; }
+   else if (w < 8 * mod + 4 * tech) { g = 4 + (int) ((w - 8 * mod) / tech); wi = (w - 8 * mod) % tech; }
+   else { g = 8; wi = w - 8 * mod - 4 * tech; }
+}
+
+__global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_warp_kernel(ChainConfig c, const __grid_constant__ Params dP)
+{
+   static_assert(sizeof(Carry) == (8 * sizeof(Mod) + 4 * sizeof(TechSt) + 8), "carry groups must tile the Carry");
+
+   __shared__ u32 carry[CHAIN_WARPS][2][CARRY_WORDS];
+
+   const u32 lane = threadIdx.x & 31;
+   const u32 wib = threadIdx.x >> 5;
+   const u32 s = blockIdx.x * CHAIN_WARPS + wib;
+   if (s >= c.n_streams)
+      return;
+
+   const u32 off = c.offsets[s];
+   const u32 n = c.counts[s];
+   LaneRec *lanes = c.lanes + off;
+
+   u32 *cur = carry[wib][0];
+   u32 *next = carry[wib][1];
+
+   {
+      Carry pon;
+      carry_init(pon, dP);
+      carry_canon(pon);
+      const u32 *raw = (const u32 *) &pon;
+      for (u32 w = lane; w < CARRY_WORDS; w += 32)
+         cur[w] = raw[w];
+   }
+   __syncwarp();
+
+   u32 ndirty = 0;
+   int prev = -1;
+
+   for (u32 j = 0; j < n; j++)
+   {
+      LaneRec &L = lanes[j];
+
+      if (L.dead)
+         continue;
+
+      if (prev >= 0)
+      {
+         LaneRec &Q = lanes[prev];
+         const u32 qStop = Q.stop, qEnd = Q.end, qGen = Q.gen, qDirty = Q.dirty;
+         const u32 reach = qStop > qEnd ? qStop : qEnd;
+
+         if (qGen > 0 && (!qDirty || qStop < qEnd) && reach > L.first)
+         {
+            const u32 lEnd = L.end;
+            const u32 newEnd = qEnd < lEnd ? lEnd : qEnd;
+            const bool wake = qStop < newEnd && !qDirty;
+            __syncwarp();
+            if (lane == 0)
+            {
+               L.dead = 1;
+               L.dirty = 0;
+               Q.end = newEnd;
+               if (wake)
+                  Q.dirty = 1;
+            }
+            if (wake)
+               ndirty++;
+            __syncwarp();
+            continue;
+         }
+      }
+
+      const bool ran = L.gen > 0;
+      const u32 touched = 0x10F | ((L.lockedMask & 0xF) << 4);
+      const u32 wasDirty = L.dirty;
+      const LaneObs obs = lane_obs(L);
+      const u32 *in = (const u32 *) &L.in;
+      const u32 *out = (const u32 *) &L.out;
+
+      bool bad = false;
+      for (u32 w = lane; w < CARRY_WORDS; w += 32)
+      {
+         int g;
+         u32 wi;
+         carry_word_group(w, g, wi);
+         const u32 t = cur[w];
+         u32 nx = t;
+         if (ran && ((touched >> g) & 1))
+         {
+            const u32 a = in[w];
+            if (!word_observed_equal(obs, g, wi, a, t))
+               bad = true;
+            nx = compose_word(obs, g, wi, t, out[w], a);
+         }
+         next[w] = nx;
+      }
+
+      const bool ok = ran && !__any_sync(0xffffffffu, bad);
+
+      if (!ok)
+      {
+         if (ran)
+         {
+            u32 *inw = (u32 *) &L.in; // a lane that never ran keeps the carry it was created with
+            for (u32 w = lane; w < CARRY_WORDS; w += 32)
+               inw[w] = cur[w];
+         }
+         if (lane == 0)
+            L.dirty = 1;
+      }
+
+      if (!ok || wasDirty)
+         ndirty++;
+
+      __syncwarp();
+
+      u32 *tmp = cur;
+      cur = next;
+      next = tmp;
+      prev = (int) j;
+   }
+
+   if (!ndirty)
+      return;
+
+   __syncwarp();
+   for (u32 j = lane; j < n; j += 32)
+   {
+      LaneRec &L = lanes[j];
+      if (L.dirty && !L.dead)
+         c.queue[atomicAdd(c.queue_count, 1u)] = off + j;
+   }
+}
+
 // length of every lane's own region + halo (the host orders the first-round queue by it: lanes of similar length share a
 // warp, long lanes start first)
 __global__ void lane_length_kernel(const LaneRec *lanes, uint32_t n, uint32_t *length)

@@ -170,6 +170,7 @@ struct nfcb200_handle
 
    int laneTaps = 2;   // lanes_kernel variant: ring tap fetch mode (NFCB200_LANE_TAPS overrides, development knob)
    int laneBlocks = 4; // resident lane blocks per SM (NFCB200_LANE_BLOCKS overrides)
+   int chainWarp = 0;  // NFCB200_CHAIN_WARP=1: one warp per stream walks the carry chain word-parallel (chain_warp_kernel)
    int shortHalo = 1;  // NFCB200_HALO_SHORT=0 forces the long warm-up for every lane (measurement knob)
    int laneCg = 0;     // ring accesses bypass L1 (NFCB200_LANE_CG overrides; measured neutral, profiles/)
 
@@ -385,6 +386,8 @@ int nfcb200_create(const nfcb200_config *cfg, nfcb200_handle **out)
       h->laneTaps = std::max(0, std::min(2, atoi(e)));
    if (const char *e = getenv("NFCB200_LANE_BLOCKS"))
       h->laneBlocks = atoi(e) >= 8 ? 8 : atoi(e) >= 6 ? 6 : 4;
+   if (const char *e = getenv("NFCB200_CHAIN_WARP"))
+      h->chainWarp = atoi(e) ? 1 : 0;
    if (const char *e = getenv("NFCB200_HALO_SHORT"))
       h->shortHalo = atoi(e) ? 1 : 0;
    if (const char *e = getenv("NFCB200_LANE_CG"))
@@ -739,7 +742,10 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       rounds++;
 
       CUDA_TRY(cudaMemsetAsync(&dC->queueCount, 0, sizeof(u32), st));
-      chain_kernel<<<sgrid, 64, 0, st>>>(cc, h->P);
+      if (h->chainWarp)
+         chain_warp_kernel<<<(n_streams + CHAIN_WARPS - 1) / CHAIN_WARPS, CHAIN_WARPS * 32, 0, st>>>(cc, h->P);
+      else
+         chain_kernel<<<sgrid, 64, 0, st>>>(cc, h->P);
       launches++;
       CUDA_TRY(cudaGetLastError());
 
