@@ -170,7 +170,7 @@ struct nfcb200_handle
 
    int laneTaps = 2;   // lanes_kernel variant: ring tap fetch mode (NFCB200_LANE_TAPS overrides, development knob)
    int laneBlocks = 4; // resident lane blocks per SM (NFCB200_LANE_BLOCKS overrides)
-   int chainWarp = 0;  // NFCB200_CHAIN_WARP=1: one warp per stream walks the carry chain word-parallel (chain_warp_kernel)
+   int chainWarp = 1;  // one warp per stream walks the carry chain word-parallel (chain_warp_kernel); NFCB200_CHAIN_WARP=0: scalar walk
    int shortHalo = 1;  // NFCB200_HALO_SHORT=0 forces the long warm-up for every lane (measurement knob)
    int laneCg = 0;     // ring accesses bypass L1 (NFCB200_LANE_CG overrides; measured neutral, profiles/)
 
