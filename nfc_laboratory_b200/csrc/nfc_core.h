@@ -213,8 +213,8 @@ NFC_HD bool odd_parity_ok(u32 value, u32 parity)
 // ---------------------------------------------------------------------------------------------------------------------
 // TAPS selects how the search-mode detectors fetch their ring taps (device latency hiding, no semantics):
 //   0  where the reference reads them (one dependent ring access after the other)
-//   1  same, after prefetch hints for the NEXT step's taps were issued at the top of the step
-//   2  all taps of the step are loaded up front (independent loads in flight together) and handed to the detectors
+//   2  all taps of the step are loaded up front (independent loads in flight together) and handed to the detectors;
+//      locked lanes other than NFC-A poll frames get prefetch hints for their next step
 struct SearchTaps
 {
    float xa0[3], xa1[3], ca2[3], ca3[3]; // NFC-A: x[t-sdd], x[t-sdd-p2], C[fp2], C[fp3] per rate
@@ -3425,7 +3425,7 @@ struct Machine
    // line (32 lanes x 4 bytes).  All taps of search mode are at least one step old when they are read (the smallest
    // delay is period2 of the 424k detectors; slot c - 1 of a correlation ring was written by the previous step), so they
    // can be fetched before the front end runs: TAPS == 2 loads them into registers back to back (one round trip for
-   // all instead of one each), TAPS == 1 issues prefetch hints for the next step.
+   // all instead of one each).
    // ------------------------------------------------------------------------------------------------------------------
    NFC_HD void prefetch_slot(u32 off, u32 index)
    {
@@ -3484,40 +3484,6 @@ struct Machine
       T.xa1[0] = RG(NFCB200_OFF_X, slot_at(b.sdd + b.p2, 0));
       T.ca2[0] = RG(b.corr, wrap(c + b.p2, b.p1));
       T.ca3[0] = RG(b.corr, c ? c - 1 : b.p1 - 1);
-   }
-
-   // hints for the taps of the NEXT step (ring phases advance by one; slot c of a correlation ring, read as c - 1 by the
-   // next step, is written by this one and stays cached)
-   NFC_HD void prefetch_next_taps()
-   {
-#if defined(__CUDA_ARCH__)
-      if (F.lock == LOCK_NONE)
-      {
-         for (int r = 0; r < 3; r++)
-         {
-            const RateParams &b = P.A[r];
-            if (b.sdd)
-               prefetch_slot(NFCB200_OFF_X, slot_at(b.sdd, 1));
-            prefetch_slot(NFCB200_OFF_X, slot_at(b.sdd + b.p2, 1));
-            prefetch_slot(b.corr, wrap(wrap(F.cA[r] + 1, b.p1) + b.p2, b.p1));
-         }
-         if (P.B[1].sdd)
-            prefetch_slot(NFCB200_OFF_W, slot_at(P.B[1].sdd, 1));
-         for (int r = 1; r <= 2; r++)
-         {
-            const RateParams &b = P.F[r];
-            prefetch_slot(NFCB200_OFF_X, slot_at(b.sdd + b.p2, 1));
-            prefetch_slot(b.corr, wrap(wrap(F.cF[r - 1] + 1, b.p1) + b.p2, b.p1));
-         }
-         prefetch_slot(NFCB200_OFF_X, slot_at(P.V.sdd, 1));
-         prefetch_slot(NFCB200_OFF_X, slot_at(P.V.sdd + P.V.p2, 1));
-         prefetch_slot(P.V.corr, wrap(wrap(F.cV1 + 1, P.V.p1) + P.V.p2, P.V.p1));
-      }
-      else
-      {
-         prefetch_locked_taps(1);
-      }
-#endif
    }
 
    // the symbol decoders of a locked lane read a handful of taps at fixed delays of their own rate
@@ -3581,11 +3547,6 @@ struct Machine
             load_poll_taps();
          else if (F.lock != LOCK_NONE)
             prefetch_locked_taps(1);
-      }
-      else if (TAPS == 1)
-      {
-         if (F.lock != LOCK_NONE || !(F.k < F.gate))
-            prefetch_next_taps();
       }
 
       front(x);

@@ -169,3 +169,38 @@ def test_synthetic_workloads_equal_reference(decoder, config):
         total += sum(1 for f in ref if f[1] in (0x102, 0x103))
         assert [f.key() for f in frames if f.stream == s] == ref, (config, s)
     assert total >= 8 * 10
+
+
+@pytest.mark.skipif(U.ref_lib() is None, reason="oracle/_ref/libnfcref.so not built")
+@pytest.mark.parametrize("name", ["test_NFC-A_106kbps_001", "test_NFC-B_106kbps_001", "test_NFC-F_212kbps_002"])
+def test_int16_iq_ingest_equals_reference(decoder, name):
+    """2-channel int16 PCM (a stereo WAV as RecordDevice reads it: x / 32768.f per channel, RecordDevice.cpp:281-311) decoded
+    on the device == the oracle on sqrtf(I*I+Q*Q) of the same converted samples"""
+    import nfc_laboratory_b200 as N
+    mag, rate, _ = U.fixture_wav(name)
+    rng = np.random.default_rng(11)
+    phi = rng.uniform(0, 2 * np.pi) + np.cumsum(rng.normal(0, 1e-4, mag.size))
+    pcm = np.stack([np.round(mag * np.cos(phi) * 32767.0), np.round(mag * np.sin(phi) * 32767.0)], axis=-1).astype(np.int16)
+    iq = pcm.astype(np.float32) / np.float32(32768.0)
+    refmag = np.empty(mag.size, dtype=np.float32)
+    U.ref_lib().nfcref_iq_magnitude(np.ascontiguousarray(iq).ctypes.data, mag.size, refmag.ctypes.data)
+    ref = U.ref_decode(refmag, rate)
+    assert sum(1 for f in ref if f[1] in (0x102, 0x103)) >= 4
+    frames = decoder.decode_batch(pcm[None], N.SIG_IQ_S16, rate)
+    assert keys(frames) == ref
+
+
+def test_frames_export_roundtrip_from_the_device(decoder, tmp_path):
+    """frames decoded on the device -> TRZ container and the regression tool's JSON (export.py) -> the golden file"""
+    import json
+    import os
+    import nfc_laboratory_b200 as N
+    from nfc_laboratory_b200 import export as X
+    name = "test_NFC-A_424kbps_002"
+    mag, rate, _ = U.fixture_wav(name)
+    frames = decoder.decode_batch(mag[None, :], N.SIG_MAG_F32, rate)
+    X.write_frames_json(tmp_path / "out.json", frames, rate)
+    with open(tmp_path / "out.json") as f, open(os.path.join(U.GOLDEN, name + ".json")) as g:
+        assert json.load(f) == json.load(g)
+    X.write_trz(tmp_path / "out.trz", frames, rate)
+    assert X.read_trz(tmp_path / "out.trz") == keys(frames)
