@@ -181,11 +181,11 @@ struct ScreenSmem
 {
    // raw staging, two stages, 16-byte aligned; sized for the widest format (float2)
    unsigned char raw[2][SCR_SPAN * 8];
-   float P[SCR_SPAN + 1];       // inclusive prefix sum of the staged magnitudes, P[0] = 0
+   float P[2][SCR_SPAN + 1];    // inclusive prefix sum of the staged magnitudes, P[.][0] = 0 (two buffers: DB variant)
    float warpAgg[SCR_WARPS];    // sum of every warp's 544 samples
    float warpW[SCR_WARPS];      // IIR state at the end of every warp's span
    float warpMin[SCR_WARPS], warpMax[SCR_WARPS];
-   uint32_t blockHit[SCR_TILE_BLOCKS + 1];
+   uint32_t blockHit[2][SCR_TILE_BLOCKS + 1];
    uint64_t bar[2];
 };
 
@@ -223,12 +223,13 @@ __device__ __forceinline__ float block_env(const float *P, int b)
  * |C[t] - C[t - q]| can undergo between evaluations (2 xmax per sample).  Chunk-relative phases keep every warp uniform.
  * The chunk spans at most two screening blocks: their envelope-scaled thresholds are formed once and selected per sample.
  */
-__device__ __forceinline__ void screen_tests(ScreenSmem &s, const ScreenTaps &tp, int first, float wCarry, const float (&wl)[SCR_PER_THREAD])
+__device__ __forceinline__ void screen_tests(const float *Pbase, uint32_t *blockHit, const ScreenTaps &tp, int first, float wCarry,
+                                             const float (&wl)[SCR_PER_THREAD])
 {
    const int blkA = (first - SCR_HALO) >> 8;
    const int blkB = (first + SCR_PER_THREAD - 1 - SCR_HALO) >> 8;
    const int split = SCR_HALO + (blkB << 8) - first; // samples i < split belong to blkA (split >= 17 when blkA == blkB)
-   const float envA = block_env(s.P, blkA), envB = blkB == blkA ? envA : block_env(s.P, blkB);
+   const float envA = block_env(Pbase, blkA), envB = blkB == blkA ? envA : block_env(Pbase, blkB);
 
    const float bA = tp.tb * envA, bB = tp.tb * envB;
    const float a2A = tp.t2 * envA, a2B = tp.t2 * envB;
@@ -236,7 +237,7 @@ __device__ __forceinline__ void screen_tests(ScreenSmem &s, const ScreenTaps &tp
    const float a0A = tp.t0 * envA, a0B = tp.t0 * envB;
    const float avA = tp.tv * envA, avB = tp.tv * envB;
 
-   const float *P = s.P + first + 1; // P[i] = inclusive prefix at the chunk's i-th sample
+   const float *P = Pbase + first + 1; // P[i] = inclusive prefix at the chunk's i-th sample
 
    bool hitA = false, hitB = false;
 
@@ -264,9 +265,9 @@ __device__ __forceinline__ void screen_tests(ScreenSmem &s, const ScreenTaps &tp
    }
 
    if (hitA)
-      s.blockHit[blkA] = 1; // benign race: all writers store 1
+      blockHit[blkA] = 1; // benign race: all writers store 1
    if (hitB)
-      s.blockHit[blkB] = 1;
+      blockHit[blkB] = 1;
 }
 
 // work item -> (stream, tile); staged range in samples [lo, hi) clipped to the stream, `base` = index of smem slot 0
@@ -320,7 +321,32 @@ __device__ __forceinline__ void tile_issue(const ScreenConfig &c, ScreenSmem &s,
  * previous and the next one, so with hi / lo taken over those three spans no test can fire when hi - lo <= quiet * lo
  * (quiet = 0.999 min(kB, thrA[r] / p2[r], thrV / vp2), host side).  On an idle carrier that is every warp.
  */
-template <int SIG>
+// phase 4: block flags and block sums of one tile (15 threads)
+__device__ __forceinline__ void screen_write_blocks(const ScreenConfig &c, const TileGeom &g, const float *P, uint32_t *blockHit, int tid)
+{
+   if (tid < SCR_TILE_BLOCKS)
+   {
+      const uint32_t b = g.tile * SCR_TILE_BLOCKS + tid;
+      const uint32_t hit = blockHit[tid];
+      blockHit[tid] = 0; // the next tests into this buffer are at least two barriers away
+      if (b < c.n_blocks)
+      {
+         const int bslot = SCR_HALO + (tid << 8);
+         c.flags[(uint64_t) g.stream * c.n_blocks + b] = hit ? SCR_TRIGGER : 0;
+         // block sum of x over the samples that exist (the replicated tail contributes nothing real: the last block
+         // of a stream is always active through the trailing margin, so its sum is only used for the envelope)
+         c.bsum[(uint64_t) g.stream * c.n_blocks + b] = P[bslot + NFCB200_BLOCK] - P[bslot];
+      }
+   }
+}
+
+/*
+ * DB = true: the prefix sums and block hits are double buffered, so the barrier between the tests of a tile (phase 3) and
+ * its block output (phase 4) disappears -- phase 4 of tile i runs after the first barrier of tile i + 1, which every
+ * thread reaches only after its phase 3 of tile i.  Warps that are quiet start the next tile while the warps inside a
+ * frame are still testing (that barrier was 23 % of the kernel's stall samples).
+ */
+template <int SIG, bool DB>
 __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, uint32_t n_items)
 {
    extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -338,7 +364,10 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    if (tid <= SCR_TILE_BLOCKS)
-      s.blockHit[tid] = 0;
+   {
+      s.blockHit[0][tid] = 0;
+      s.blockHit[1][tid] = 0;
+   }
    __syncthreads();
 
    // (stream, tile) of the current item, advanced without divisions
@@ -368,9 +397,14 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
    tp.tv = c.thrV;
    tp.tb = c.kB;
 
+   TileGeom prevG = tile_geom(c, stream, tile); // DB: the tile whose block output is still pending
+   bool havePrev = false;
+
    for (; item < n_items; item += gridDim.x, stage ^= 1)
    {
       const TileGeom g = tile_geom(c, stream, tile);
+      float *P = s.P[DB ? stage : 0];
+      uint32_t *blockHit = s.blockHit[DB ? stage : 0];
 
       // next item
       uint32_t nstream = stream + stepS, ntile = tile + stepT;
@@ -491,6 +525,9 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
 
       __syncthreads();
 
+      if (DB && havePrev)
+         screen_write_blocks(c, prevG, s.P[stage ^ 1], s.blockHit[stage ^ 1], tid); // every warp is past its tests of that tile
+
       // ---- phase 2: carries across warps, prefix to shared memory, quiet test ---------------------------------------
       float prefBase = 0;
 #pragma unroll
@@ -501,9 +538,9 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
 
 #pragma unroll
       for (int i = 0; i < SCR_PER_THREAD; i++)
-         s.P[first + i + 1] = exclPref + loc[i];
+         P[first + i + 1] = exclPref + loc[i];
       if (tid == 0)
-         s.P[0] = 0;
+         P[0] = 0;
 
       // IIR state entering this thread's chunk: the warp scan's value of the previous lane plus what is left of the state
       // that entered the warp, 0.9^(17 lane) (exp2 of lane * log2(0.9^17); approximate like everything in this screen)
@@ -536,7 +573,7 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
          if (first >= SCR_HALO && lastSlot < ownEnd)
          {
             // whole chunk inside the tile's own samples: branch-free tests
-            screen_tests(s, tp, first, wCarry, wl);
+            screen_tests(P, blockHit, tp, first, wCarry, wl);
          }
          else if (lastSlot >= SCR_HALO && first < ownEnd)
          {
@@ -548,42 +585,43 @@ __global__ void __launch_bounds__(SCR_THREADS, 2) screen_kernel(ScreenConfig c, 
                if (slot < SCR_HALO || slot >= ownEnd)
                   continue;
                const int blk = (slot - SCR_HALO) >> 8;
-               const float env = block_env(s.P, blk);
+               const float env = block_env(P, blk);
                const int t = slot + 1;
-               const float Pt = s.P[t];
+               const float Pt = P[t];
                bool hit = fabsf(__fmaf_rn(iir_decay(i), wCarry, wl[i])) > tp.tb * env;
-               hit |= fabsf((Pt - s.P[t - tp.p20]) - (s.P[t - tp.q0] - s.P[t - tp.q0 - tp.p20])) > tp.t0 * env;
-               hit |= fabsf((Pt - s.P[t - tp.p21]) - (s.P[t - tp.q1] - s.P[t - tp.q1 - tp.p21])) > tp.t1 * env;
-               hit |= fabsf((Pt - s.P[t - tp.p22]) - (s.P[t - tp.q2] - s.P[t - tp.q2 - tp.p22])) > tp.t2 * env;
-               hit |= fabsf((Pt - s.P[t - tp.pv]) - (s.P[t - tp.qv] - s.P[t - tp.qv - tp.pv])) > tp.tv * env;
+               hit |= fabsf((Pt - P[t - tp.p20]) - (P[t - tp.q0] - P[t - tp.q0 - tp.p20])) > tp.t0 * env;
+               hit |= fabsf((Pt - P[t - tp.p21]) - (P[t - tp.q1] - P[t - tp.q1 - tp.p21])) > tp.t1 * env;
+               hit |= fabsf((Pt - P[t - tp.p22]) - (P[t - tp.q2] - P[t - tp.q2 - tp.p22])) > tp.t2 * env;
+               hit |= fabsf((Pt - P[t - tp.pv]) - (P[t - tp.qv] - P[t - tp.qv - tp.pv])) > tp.tv * env;
                if (hit)
-                  s.blockHit[blk] = 1;
+                  blockHit[blk] = 1;
             }
          }
       }
 
-      __syncthreads();
-
-      // ---- phase 4: block flags and block sums of the tile ------------------------------------------------------------
-      if (tid < SCR_TILE_BLOCKS)
+      if (!DB)
       {
-         const uint32_t b = g.tile * SCR_TILE_BLOCKS + tid;
-         const uint32_t hit = s.blockHit[tid];
-         s.blockHit[tid] = 0; // phase 3 of the next tile is two barriers away
-         if (b < c.n_blocks)
-         {
-            const int bslot = SCR_HALO + (tid << 8);
-            c.flags[(uint64_t) g.stream * c.n_blocks + b] = hit ? SCR_TRIGGER : 0;
-            // block sum of x over the samples that exist (the replicated tail contributes nothing real: the last block
-            // of a stream is always active through the trailing margin, so its sum is only used for the envelope)
-            c.bsum[(uint64_t) g.stream * c.n_blocks + b] = s.P[bslot + NFCB200_BLOCK] - s.P[bslot];
-         }
+         __syncthreads();
+
+         // ---- phase 4: block flags and block sums of the tile ---------------------------------------------------------
+         screen_write_blocks(c, g, P, blockHit, tid);
+      }
+      else
+      {
+         prevG = g;
+         havePrev = true;
       }
 
       stream = nstream;
       tile = ntile;
       // no barrier here: P, blockHit and the warp aggregates are rewritten in phase 2 / after the first barrier of the
       // next iteration, which every thread reaches only after this phase 4
+   }
+
+   if (DB && havePrev)
+   {
+      __syncthreads();
+      screen_write_blocks(c, prevG, s.P[stage ^ 1], s.blockHit[stage ^ 1], tid); // `stage` was flipped once more by the loop
    }
 }
 

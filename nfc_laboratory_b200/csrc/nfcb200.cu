@@ -170,6 +170,7 @@ struct nfcb200_handle
 
    int laneTaps = 2;   // lanes_kernel variant: ring tap fetch mode (NFCB200_LANE_TAPS overrides, development knob)
    int laneBlocks = 4; // resident lane blocks per SM (NFCB200_LANE_BLOCKS overrides)
+   int screenDb = 0;   // NFCB200_SCREEN_DB=1: K1 with double-buffered prefix sums (one CTA barrier less per tile)
    int chainWarp = 1;  // one warp per stream walks the carry chain word-parallel (chain_warp_kernel); NFCB200_CHAIN_WARP=0: scalar walk
    int shortHalo = 1;  // NFCB200_HALO_SHORT=0 forces the long warm-up for every lane (measurement knob)
    int laneCg = 0;     // ring accesses bypass L1 (NFCB200_LANE_CG overrides; measured neutral, profiles/)
@@ -242,25 +243,34 @@ static void launch_lanes(const nfcb200_handle *h, const LaneConfig &lc, u32 bloc
 #undef NFCB200_LANES
 }
 
-// K1 launch: one instantiation per sample format, persistent grid of 2 CTAs per SM
-static void launch_screen(const nfcb200_handle *h, const ScreenConfig &sc, uint32_t items, cudaStream_t st)
+// K1 launch: one instantiation per sample format (x double-buffered prefix variant), persistent grid of 2 CTAs per SM
+template <bool DB>
+static void launch_screen_variant(const ScreenConfig &sc, uint32_t items, u32 grid, cudaStream_t st)
 {
-   const u32 grid = std::min<u32>(items, (u32) h->smCount * 2);
    switch (sc.sigtype)
    {
       case SIG_IQ_F32:
-         screen_kernel<SIG_IQ_F32><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
+         screen_kernel<SIG_IQ_F32, DB><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
          break;
       case SIG_MAG_F32:
-         screen_kernel<SIG_MAG_F32><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
+         screen_kernel<SIG_MAG_F32, DB><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
          break;
       case SIG_MAG_S16:
-         screen_kernel<SIG_MAG_S16><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
+         screen_kernel<SIG_MAG_S16, DB><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
          break;
       default:
-         screen_kernel<SIG_IQ_S16><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
+         screen_kernel<SIG_IQ_S16, DB><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
          break;
    }
+}
+
+static void launch_screen(const nfcb200_handle *h, const ScreenConfig &sc, uint32_t items, cudaStream_t st)
+{
+   const u32 grid = std::min<u32>(items, (u32) h->smCount * 2);
+   if (h->screenDb)
+      launch_screen_variant<true>(sc, items, grid, st);
+   else
+      launch_screen_variant<false>(sc, items, grid, st);
 }
 
 static void fill_screen_config(const nfcb200_handle *h, ScreenConfig &sc)
@@ -386,6 +396,8 @@ int nfcb200_create(const nfcb200_config *cfg, nfcb200_handle **out)
       h->laneTaps = std::max(0, std::min(2, atoi(e)));
    if (const char *e = getenv("NFCB200_LANE_BLOCKS"))
       h->laneBlocks = atoi(e) >= 8 ? 8 : atoi(e) >= 6 ? 6 : 4;
+   if (const char *e = getenv("NFCB200_SCREEN_DB"))
+      h->screenDb = atoi(e) ? 1 : 0;
    if (const char *e = getenv("NFCB200_CHAIN_WARP"))
       h->chainWarp = atoi(e) ? 1 : 0;
    if (const char *e = getenv("NFCB200_HALO_SHORT"))
@@ -395,10 +407,16 @@ int nfcb200_create(const nfcb200_config *cfg, nfcb200_handle **out)
    if (h->laneTaps == 1)
       h->laneTaps = 2;
 
-   cudaFuncSetAttribute(screen_kernel<SIG_IQ_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem));
-   cudaFuncSetAttribute(screen_kernel<SIG_MAG_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem));
-   cudaFuncSetAttribute(screen_kernel<SIG_MAG_S16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem));
-   cudaFuncSetAttribute(screen_kernel<SIG_IQ_S16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem));
+#define NFCB200_SMEM_ATTR(K) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem))
+   NFCB200_SMEM_ATTR((screen_kernel<SIG_IQ_F32, false>));
+   NFCB200_SMEM_ATTR((screen_kernel<SIG_MAG_F32, false>));
+   NFCB200_SMEM_ATTR((screen_kernel<SIG_MAG_S16, false>));
+   NFCB200_SMEM_ATTR((screen_kernel<SIG_IQ_S16, false>));
+   NFCB200_SMEM_ATTR((screen_kernel<SIG_IQ_F32, true>));
+   NFCB200_SMEM_ATTR((screen_kernel<SIG_MAG_F32, true>));
+   NFCB200_SMEM_ATTR((screen_kernel<SIG_MAG_S16, true>));
+   NFCB200_SMEM_ATTR((screen_kernel<SIG_IQ_S16, true>));
+#undef NFCB200_SMEM_ATTR
 
    *out = h;
    return 0;
