@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle spot check (profiling runs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle spot check of the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="small batch for smoke runs (64 streams x 2e6)")
     return ap.parse_args()
 
@@ -274,25 +274,7 @@ def main():
         allf = ND.gather_frames(flat, dev)
         return nf if allf is None else ND.count_frames(allf)
 
-    # ---- parity spot check against the oracle (untimed): first streams, first 2e6 samples ---------------------------------
-    parity = None
-    if rank == 0 and not args.no_parity:
-        import nfcutil as U
-        if U.ref_lib() is not None:
-            ns = min(2, S)
-            m = min(n, 2_000_000)
-            sub = iq[:ns, :m].contiguous()
-            got = dec.decode_batch(sub, N.SIG_IQ_F32, RATE)
-            host = sub.cpu().numpy()
-            parity = True
-            for s in range(ns):
-                mag = np.empty(m, dtype=np.float32)
-                U.ref_lib().nfcref_iq_magnitude(np.ascontiguousarray(host[s]).ctypes.data, m, mag.ctypes.data)
-                ref = U.ref_decode(mag, RATE)
-                if [f.key() for f in got if f.stream == s] != ref:
-                    parity = False
-            if not parity:
-                raise SystemExit("parity check against the reference oracle FAILED: refusing to report a number")
+    parity = None  # set by the cpu_baseline leg (the only place this arm touches the oracle)
 
     # ---- warm-up, then the timed region -----------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 0)):
@@ -395,6 +377,21 @@ def main():
         nc = min(n, 10_000_000)
         sub = iq[:Sc, :nc].cpu().numpy()
         v, fr = cpu_reference_run(sub, cores)
+        if v is not None and not args.no_parity:
+            # the same leg also checks the GPU arm against the reference (untimed): first streams, first 2e6 samples,
+            # every frame field; a mismatch voids the run
+            import nfcutil as U
+            ns = min(2, Sc)
+            m = min(nc, 2_000_000)
+            got = dec.decode_batch(iq[:ns, :m].contiguous(), N.SIG_IQ_F32, RATE)
+            parity = True
+            for s_ in range(ns):
+                mag = np.empty(m, dtype=np.float32)
+                U.ref_lib().nfcref_iq_magnitude(np.ascontiguousarray(sub[s_, :m]).ctypes.data, m, mag.ctypes.data)
+                if [f.key() for f in got if f.stream == s_] != U.ref_decode(mag, RATE):
+                    parity = False
+            if not parity:
+                raise SystemExit("parity check against the reference oracle FAILED: refusing to report a number")
         if v is not None:
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
                    "sample": "%d of the batch's streams x %d samples, one NfcDecoder per host thread on %d threads, IQ->magnitude included" % (Sc, nc, cores)}
