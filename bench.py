@@ -189,6 +189,12 @@ def cpu_reference_run(iq_host, threads):
     return S * n / sec / 1e6, int(frames.value)
 
 
+def workload_name(workload, S, n, bytes_per_step):
+    """config.workload: the same text for both arms (the reference arm times a bounded sample of it, named in config.sample)"""
+    return "%s: %d synthetic 10 MS/s x %.1f s float2 IQ streams per GPU (BASELINE.json configs[1] shape), input %.1f GB per GPU, " \
+           "larger than L2 (no flush needed)" % (workload, S, n / RATE, bytes_per_step / 1e9)
+
+
 def reference_arm(args, rank, world):
     """--impl reference: the reference CPU implementation of the path on this box's host cores (rank 0 only)"""
     if rank != 0:
@@ -215,7 +221,8 @@ def reference_arm(args, rank, world):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: synthetic 10 MS/s float2 IQ, bounded sample of the GPU arm's batch" % args.workload, "sample": sample},
+        "config": {"workload": workload_name(args.workload, args.streams, args.samples, args.streams * args.samples * 8), "sample": sample,
+                   "streams_per_gpu": args.streams, "samples_per_stream": args.samples, "sample_rate": RATE},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frames_per_step": frames // max(1, args.steps),
@@ -402,8 +409,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s: %d synthetic 10 MS/s x %.1f s float2 IQ streams per GPU (BASELINE.json configs[1] shape), input %.1f GB per GPU, "
-                                   "larger than L2 (no flush needed)" % (args.workload, S, n / RATE, bytes_per_step / 1e9),
+            "config": {"workload": workload_name(args.workload, S, n, bytes_per_step),
                        "streams_per_gpu": S, "samples_per_stream": n, "sample_rate": RATE, "sharding": "streams, block partition, NCCL frame gather" if world > 1 else "single GPU"},
             "e2e": e2e,
             "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),

@@ -1,0 +1,44 @@
+"""The benchmark's reference arm (`bench.py --impl reference`) runs on host cores only, so its JSON contract is checked here
+on a small sample; the GPU arm prints the same keys plus roofline / gpu_launches (driver-side check on the B200)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import nfcutil as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(U.ref_lib() is None, reason="oracle/_ref/libnfcref.so not built")
+def test_reference_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--samples", "400000"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "IQ MSamples/s decoded" and d["unit"] == "MSamples/s"
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["workload"].startswith("nfca106: 1024 synthetic 10 MS/s") and "sample" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["frames_per_step"] > 0
+
+
+def test_host_limits_are_read_from_the_cgroup(tmp_path):
+    sys.path.insert(0, ROOT)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert 1 <= b.host_cores() <= (os.cpu_count() or 1)
+    assert b.host_memory_budget() > 0
+    s = b.ClockSampler(0)   # no NVML / nvidia-smi here: the sampler must still start, stop and report
+    s.start()
+    r = s.summary()
+    assert set(r) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples", "source"}
