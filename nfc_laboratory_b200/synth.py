@@ -335,6 +335,16 @@ def schedule(config, n_streams, n_samples, seed, fs=10_000_000, gap_ms=(1.0, 5.0
     return tmpl, np.array(places, dtype=np.int64).reshape(-1, 3)
 
 
+def expected_frame_count(config, n_streams, n_samples, seed, fs=10_000_000):
+    """number of poll + listen frames the batch of synth_batch(config, n_streams, n_samples, seed) is built to contain
+    (every placed exchange is complete), or None when a template of the config has no recorded expectation"""
+    tmpl, places = schedule(config, n_streams, n_samples, seed, fs)
+    per = [None if t[1] is None else len(t[1]) for t in tmpl]
+    if any(p is None for p in per):
+        return None
+    return int(sum(per[int(k)] for k in places[:, 2])) if places.size else 0
+
+
 def synth_batch(config, n_streams, n_samples, seed=1, device="cpu", fs=10_000_000, iq=True, amplitude=(0.25, 0.40), sigma=(1e-3, 4e-3),
                 chunk_streams=32, out=None):
     """[n_streams, n_samples, 2] float32 IQ (or [n_streams, n_samples] magnitude when iq=False) on `device`.

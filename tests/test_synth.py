@@ -41,3 +41,16 @@ def test_pipeline_on_synthetic_streams(config, group):
         out, st = U.sim_pipeline(mag, S.block_flags_device_model(mag, S.ScreenParams(FS)), FS, group=group)
         assert out == ref
         assert st["work"] < 1.2 * mag.size
+
+
+@pytest.mark.parametrize("config", ["nfca106", "nfcb106", "nfca424"])
+def test_expected_frame_count_is_what_the_reference_decodes(config):
+    """the full-size property bench.py checks: the number of poll + listen frames follows from the schedule alone"""
+    iq = Y.synth_batch(config, 3, 900_000, seed=21).numpy()
+    total = 0
+    for s in range(iq.shape[0]):
+        mag = np.empty(iq.shape[1], np.float32)
+        U.ref_lib().nfcref_iq_magnitude(np.ascontiguousarray(iq[s]).ctypes.data, mag.size, mag.ctypes.data)
+        total += sum(1 for f in U.ref_decode(mag, FS) if f[1] in (0x102, 0x103))
+    assert total == Y.expected_frame_count(config, 3, 900_000, seed=21) > 0
+    assert Y.expected_frame_count("mixed", 3, 900_000, seed=21) is None
