@@ -195,6 +195,43 @@ def workload_name(workload, S, n, bytes_per_step):
            "larger than L2 (no flush needed)" % (workload, S, n / RATE, bytes_per_step / 1e9)
 
 
+def full_size_check(frames, S, n, workload, seed, iq, max_streams=4):
+    """size-independent property of the whole batch: the number of poll + listen frames of every stream follows from the
+    generator's schedule.  Streams that deviate (noise can cost the reference itself a frame) are decoded by the reference
+    on the host -- part of the cpu_baseline leg, untimed -- and compared frame for frame with the GPU's.  Never fatal:
+    the result is reported as it is."""
+    try:
+        import nfcutil as U
+        from nfc_laboratory_b200 import synth
+        exp = synth.expected_frames_per_stream(workload, S, n, seed)
+        if exp is None:
+            return None
+        data = (frames["frame_type"] == 0x102) | (frames["frame_type"] == 0x103)
+        got = np.bincount(frames["stream"][data].astype(np.int64), minlength=S)[:S]
+        off = np.nonzero(got != exp)[0]
+        res = {"expected_poll_listen_frames": int(exp.sum()), "decoded_poll_listen_frames": int(got.sum()), "streams_off_schedule": int(off.size)}
+        if off.size and U.ref_lib() is not None:
+            agree = True
+            checked = []
+            for s_ in off[:max_streams]:
+                one = np.ascontiguousarray(iq[int(s_)].cpu().numpy())
+                mag = np.empty(n, dtype=np.float32)
+                U.ref_lib().nfcref_iq_magnitude(one.ctypes.data, n, mag.ctypes.data)
+                ref = U.ref_decode(mag, RATE)
+                rows = frames[frames["stream"] == s_]
+                mine = [(int(r["tech_type"]), int(r["frame_type"]), int(r["frame_flags"]), int(r["frame_phase"]), int(r["frame_rate"]),
+                         int(r["sample_start"]), int(r["sample_end"]), bytes(r["data"][: int(r["length"])])) for r in rows]
+                same = mine == [tuple(f) for f in ref]
+                agree = agree and same
+                checked.append({"stream": int(s_), "expected": int(exp[s_]), "decoded": int(got[s_]),
+                                "reference": sum(1 for f in ref if f[1] in (0x102, 0x103)), "gpu_equals_reference": bool(same)})
+            res["deviating_streams_checked"] = checked
+            res["gpu_equals_reference_on_them"] = bool(agree)
+        return res
+    except Exception as e:  # a diagnostic must not cost the run its number
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def reference_arm(args, rank, world):
     """--impl reference: the reference CPU implementation of the path on this box's host cores (rank 0 only)"""
     if rank != 0:
@@ -309,6 +346,7 @@ def main():
 
     # digest of the last resident decode (frames of this rank): the host-input decode below must reproduce it
     digest_resident = ND.frames_digest(ND.frames_as_array(buf, nf))
+    frames_last = ND.frames_as_array(buf, nf).copy() if (rank == 0 and world == 1 and not args.no_cpu and not args.no_parity) else None
 
     tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
@@ -378,6 +416,7 @@ def main():
 
     # ---- CPU baseline: the reference decoder on this box's cores, bounded sample of the same batch -------------------------
     cpu = None
+    fullcheck = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = host_cores()
         Sc = min(S, max(cores, min(2 * cores, 32)))
@@ -399,6 +438,8 @@ def main():
                     parity = False
             if not parity:
                 raise SystemExit("parity check against the reference oracle FAILED: refusing to report a number")
+        if v is not None and frames_last is not None:
+            fullcheck = full_size_check(frames_last, S, n, args.workload, args.seed + 1000 * rank, iq)
         if v is not None:
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
                    "sample": "%d of the batch's streams x %d samples, one NfcDecoder per host thread on %d threads, IQ->magnitude included" % (Sc, nc, cores)}
@@ -421,7 +462,7 @@ def main():
             "phases_ms": {k: statistics.mean(s[k] for s in stats) for k in ("ms_screen", "ms_segment", "ms_lanes", "ms_gather", "ms_total", "ms_wall")},
             "decode": {"frames_per_step": frames_total // max(1, args.steps), "segments": st["segments"], "lanes": st["lanes"], "rounds": st["rounds"],
                        "lane_runs": st["lane_runs"], "lane_samples_frac": st["lane_samples"] / max(1, st["samples"])},
-            "parity_spot_check": parity, "frames_digest": "%016x" % digest_resident,
+            "parity_spot_check": parity, "frames_digest": "%016x" % digest_resident, "full_size_check": fullcheck,
         }
         print(json.dumps(line))
 

@@ -345,6 +345,18 @@ def expected_frame_count(config, n_streams, n_samples, seed, fs=10_000_000):
     return int(sum(per[int(k)] for k in places[:, 2])) if places.size else 0
 
 
+def expected_frames_per_stream(config, n_streams, n_samples, seed, fs=10_000_000):
+    """per-stream version of expected_frame_count: int64 array [n_streams], or None"""
+    tmpl, places = schedule(config, n_streams, n_samples, seed, fs)
+    per = [None if t[1] is None else len(t[1]) for t in tmpl]
+    if any(p is None for p in per):
+        return None
+    out = np.zeros(n_streams, dtype=np.int64)
+    if places.size:
+        np.add.at(out, places[:, 0], np.array(per, dtype=np.int64)[places[:, 2]])
+    return out
+
+
 def synth_batch(config, n_streams, n_samples, seed=1, device="cpu", fs=10_000_000, iq=True, amplitude=(0.25, 0.40), sigma=(1e-3, 4e-3),
                 chunk_streams=32, out=None):
     """[n_streams, n_samples, 2] float32 IQ (or [n_streams, n_samples] magnitude when iq=False) on `device`.

@@ -42,3 +42,41 @@ def test_host_limits_are_read_from_the_cgroup(tmp_path):
     s.start()
     r = s.summary()
     assert set(r) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples", "source"}
+
+
+@pytest.mark.skipif(U.ref_lib() is None, reason="oracle/_ref/libnfcref.so not built")
+def test_full_size_check_finds_and_explains_a_deviating_stream():
+    """bench.py's schedule check, fed with reference-decoded frames standing in for the GPU's: clean batch -> nothing off;
+    one frame removed -> that stream is decoded by the reference and reported as different from the 'GPU'"""
+    import importlib.util
+    import numpy as np
+    import torch
+    from nfc_laboratory_b200 import synth as Y, dist as ND
+    spec = importlib.util.spec_from_file_location("bench_under_test2", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+
+    S, n, seed = 3, 900_000, 21
+    iq = Y.synth_batch("nfca106", S, n, seed=seed)
+    recs = []
+    for s in range(S):
+        mag = np.empty(n, np.float32)
+        U.ref_lib().nfcref_iq_magnitude(np.ascontiguousarray(iq[s].numpy()).ctypes.data, n, mag.ctypes.data)
+        for f in U.ref_decode(mag, 10_000_000):
+            recs.append((s,) + tuple(f))
+    a = np.zeros(len(recs), dtype=ND.FRAME_DTYPE)
+    for i, r in enumerate(recs):
+        a[i]["stream"], a[i]["tech_type"], a[i]["frame_type"], a[i]["frame_flags"], a[i]["frame_phase"], a[i]["frame_rate"] = r[:6]
+        a[i]["sample_start"], a[i]["sample_end"], a[i]["length"] = r[6], r[7], len(r[8])
+        a[i]["data"][: len(r[8])] = np.frombuffer(r[8], dtype=np.uint8)
+
+    res = b.full_size_check(a, S, n, "nfca106", seed, iq)
+    assert res["streams_off_schedule"] == 0 and res["expected_poll_listen_frames"] == res["decoded_poll_listen_frames"] > 0
+
+    victim = np.nonzero((a["stream"] == 1) & (a["frame_type"] == 0x103))[0][2]
+    res = b.full_size_check(np.delete(a, victim), S, n, "nfca106", seed, iq)
+    assert res["streams_off_schedule"] == 1 and res["decoded_poll_listen_frames"] == res["expected_poll_listen_frames"] - 1
+    chk = res["deviating_streams_checked"]
+    assert len(chk) == 1 and chk[0]["stream"] == 1 and chk[0]["reference"] == chk[0]["expected"] and chk[0]["gpu_equals_reference"] is False
+    assert res["gpu_equals_reference_on_them"] is False
+    assert b.full_size_check(a, S, n, "mixed", seed, iq) is None
