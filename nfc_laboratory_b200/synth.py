@@ -335,9 +335,17 @@ def schedule(config, n_streams, n_samples, seed, fs=10_000_000, gap_ms=(1.0, 5.0
     return tmpl, np.array(places, dtype=np.int64).reshape(-1, 3)
 
 
+# configs whose schedule alone fixes the frame count (checked against the reference in tests/test_synth.py, and on all
+# 1024 x 1e7 streams of the benchmark batch).  Not among them: NFC-B (the reference misses exchanges that come within the
+# first ~90 000 samples of a stream) and NFC-A 424 kbps (it loses an occasional BPSK listen frame to the noise).
+SCHEDULE_FIXES_FRAME_COUNT = ("nfca106",)
+
+
 def expected_frame_count(config, n_streams, n_samples, seed, fs=10_000_000):
     """number of poll + listen frames the batch of synth_batch(config, n_streams, n_samples, seed) is built to contain
-    (every placed exchange is complete), or None when a template of the config has no recorded expectation"""
+    (every placed exchange is complete), or None when the config gives no such guarantee"""
+    if config not in SCHEDULE_FIXES_FRAME_COUNT:
+        return None
     tmpl, places = schedule(config, n_streams, n_samples, seed, fs)
     per = [None if t[1] is None else len(t[1]) for t in tmpl]
     if any(p is None for p in per):
@@ -347,6 +355,8 @@ def expected_frame_count(config, n_streams, n_samples, seed, fs=10_000_000):
 
 def expected_frames_per_stream(config, n_streams, n_samples, seed, fs=10_000_000):
     """per-stream version of expected_frame_count: int64 array [n_streams], or None"""
+    if config not in SCHEDULE_FIXES_FRAME_COUNT:
+        return None
     tmpl, places = schedule(config, n_streams, n_samples, seed, fs)
     per = [None if t[1] is None else len(t[1]) for t in tmpl]
     if any(p is None for p in per):
