@@ -202,11 +202,24 @@ NFC_HD bool lane_iterate(MACH &M, Lane &L, const Params &P, u32 &pos, u32 end, u
       {
          Carry carry = L.c;
          carry_canon(carry);
-         u32 locked = L.lockedMask;
+         // what the run has recorded so far about its use of the INCOMING carry (chain_walk reads it) survives the restart:
+         // the run goes on from its own exact carry, it does not start a new dependency history
+         const u32 locked = L.lockedMask, lcWritten = L.lcWritten, lcLive = L.lcLive, fZeroed = L.fZeroed, fThrWritten = L.fThrWritten,
+                   fThrRead = L.fThrRead, fInc00 = L.fInc0[0], fInc01 = L.fInc0[1];
+         const float fThrSync0 = L.fThrSync[0], fThrSync1 = L.fThrSync[1];
          u32 target = begin - NFCB200_HALO;
          zero();
          lane_begin(L, P, carry, target, NFCB200_HALO);
          L.lockedMask = locked;
+         L.lcWritten = lcWritten;
+         L.lcLive = lcLive;
+         L.fZeroed = fZeroed;
+         L.fThrWritten = fThrWritten;
+         L.fThrRead = fThrRead;
+         L.fInc0[0] = fInc00;
+         L.fInc0[1] = fInc01;
+         L.fThrSync[0] = fThrSync0;
+         L.fThrSync[1] = fThrSync1;
          L.fe.kbase = kw;
          M.reload_front();
          pos = target;
@@ -474,6 +487,12 @@ NFC_HD u32 chain_walk(LaneRec *lanes, u32 n, const Params &P)
 
       if (L.dirty)
          ndirty++;
+
+#ifdef NFCB200_CHAIN_DEBUG
+      printf("   lane %u [%u,%u) first %u gen %u ran %d ok %d locked %x lcW %x lcL %x: lastCommand in %02x/%02x out %02x/%02x -> carry %02x/%02x (A/B)\n", j, L.begin,
+             L.end, L.first, L.gen, (int) ran, (int) ok, L.lockedMask, L.lcWritten, L.lcLive, L.in.t[0].fs.lastCommand, L.in.t[1].fs.lastCommand,
+             L.out.t[0].fs.lastCommand, L.out.t[1].fs.lastCommand, next.t[0].fs.lastCommand, next.t[1].fs.lastCommand);
+#endif
 
       cur = next;
       prev = (int) j;

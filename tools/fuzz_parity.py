@@ -1,0 +1,97 @@
+#!/usr/bin/env python3
+"""Development aid: randomised differential test of the lane pipeline (host build of the device code + numpy screen model)
+against the compiled reference.  Streams are random sequences of exchanges of all four technologies (the benchmark templates
+plus tests/extra_signals.py) with random gaps -- including gaps far shorter than the benchmark's, so that segments merge --
+random carrier level, noise, carrier dropouts and level steps.
+
+usage: python tools/fuzz_parity.py [streams] [seed]      prints every stream whose frames differ and a summary
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+import nfcutil as U  # noqa: E402
+import screen_ref as S  # noqa: E402
+import extra_signals as X  # noqa: E402
+from nfc_laboratory_b200 import synth as Y  # noqa: E402
+
+FS = 10_000_000
+
+
+def templates():
+    t = []
+    for cfg in ("nfca106", "nfcb106", "nfca424", "mixed"):
+        t += [m for m, _ in Y.session_templates(cfg, FS)]
+    w = Y.Wave(FS)
+    t.append(w.render(X.nfcb_poll(w, 4000.0, bytes([0x05, 0x00, 0x00]), 1) + 4000.0))
+    for rate in (1, 2):
+        w = Y.Wave(FS)
+        e = X.nfcf_frame(w, 4000.0, X.REQC, rate, 0.40)
+        e = X.nfcf_frame(w, e + 6000.0, X.RESC, rate, 0.25)
+        t.append(w.render(e + 4000.0))
+    return t
+
+
+def stream(rng, tmpl, n):
+    m = np.ones(n, np.float32)
+    pos = int(rng.integers(3000, 60000))
+    while True:
+        k = int(rng.integers(0, len(tmpl)))
+        L = tmpl[k].size
+        if pos + L + 3000 >= n:
+            break
+        m[pos:pos + L] = tmpl[k]
+        gap = int(np.exp(rng.uniform(np.log(300), np.log(60000))))
+        pos += L + gap
+    A = rng.uniform(0.05, 0.6)
+    level = np.full(n, A, np.float32)
+    for _ in range(int(rng.integers(0, 3))):                # level steps
+        p = int(rng.integers(0, n))
+        level[p:] *= np.float32(rng.uniform(0.7, 1.4))
+    if rng.random() < 0.3:                                   # carrier dropout
+        p = int(rng.integers(0, n - 40000))
+        level[p:p + int(rng.integers(2000, 40000))] = 0.0
+    sigma = A * np.exp(rng.uniform(np.log(0.002), np.log(0.02)))
+    x = m * level + rng.normal(0, sigma, n).astype(np.float32)
+    return np.abs(x).astype(np.float32)
+
+
+def main():
+    streams = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    rng = np.random.default_rng(seed)
+    tmpl = templates()
+    sp = S.ScreenParams(FS)
+    bad = 0
+    frames = 0
+    t0 = time.time()
+    for i in range(streams):
+        n = int(rng.integers(300_000, 1_500_000))
+        x = stream(rng, tmpl, n)
+        ref = U.ref_decode(x, FS)
+        out, st = U.sim_pipeline(x, S.block_flags_device_model(x, sp), FS)
+        frames += len(ref)
+        if out != ref:
+            bad += 1
+            single, _, _ = U.sim_run(x, FS)
+            print("stream %d: single sequential lane == reference: %s; lanes %d, rounds %d" % (i, single == ref, st["lanes"], st["rounds"]))
+            d = [(a, b) for a, b in zip(ref, out) if a != b][:2]
+            print("stream %d (n=%d): %d vs %d frames; first differences:" % (i, n, len(ref), len(out)))
+            for a, b in d:
+                print("    ref ", U.describe(a))
+                print("    ours", U.describe(b))
+            if len(ref) != len(out):
+                sa, sb = set(ref), set(out)
+                for f in sorted(sa - sb, key=lambda f: f[5])[:3]:
+                    print("    only ref ", U.describe(f))
+                for f in sorted(sb - sa, key=lambda f: f[5])[:3]:
+                    print("    only ours", U.describe(f))
+    print("streams %d, frames %d, differing streams %d, %.0f s" % (streams, frames, bad, time.time() - t0))
+
+
+if __name__ == "__main__":
+    main()
