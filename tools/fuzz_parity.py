@@ -78,7 +78,12 @@ def main():
         if out != ref:
             bad += 1
             single, _, _ = U.sim_run(x, FS)
-            print("stream %d: single sequential lane == reference: %s; lanes %d, rounds %d" % (i, single == ref, st["lanes"], st["rounds"]))
+            port = U.port_decode(x, FS)
+            # pipeline != reference but single lane == reference: the speculation / carry chain is wrong.  Single lane != reference
+            # while the independent C restatement agrees with the lane: the reference read frame bytes beyond the frame length
+            # (recycled pool memory, rt/Buffer.h:656-668) on a truncated frame -- not reproducible by design
+            print("stream %d: single lane == reference: %s; C restatement == single lane: %s; pipeline == single lane: %s; lanes %d, rounds %d"
+                  % (i, single == ref, port == single, out == single, st["lanes"], st["rounds"]))
             d = [(a, b) for a, b in zip(ref, out) if a != b][:2]
             print("stream %d (n=%d): %d vs %d frames; first differences:" % (i, n, len(ref), len(out)))
             for a, b in d:
