@@ -4,7 +4,7 @@ against the compiled reference.  Streams are random sequences of exchanges of al
 plus tests/extra_signals.py) with random gaps -- including gaps far shorter than the benchmark's, so that segments merge --
 random carrier level, noise, carrier dropouts and level steps.
 
-usage: python tools/fuzz_parity.py [streams] [seed]      prints every stream whose frames differ and a summary
+usage: python tools/fuzz_parity.py [streams] [seed] [segments per lane]     prints every stream whose frames differ and a summary
 """
 import os
 import sys
@@ -63,6 +63,7 @@ def stream(rng, tmpl, n):
 def main():
     streams = int(sys.argv[1]) if len(sys.argv) > 1 else 50
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    group = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     rng = np.random.default_rng(seed)
     tmpl = templates()
     sp = S.ScreenParams(FS)
@@ -73,7 +74,7 @@ def main():
         n = int(rng.integers(300_000, 1_500_000))
         x = stream(rng, tmpl, n)
         ref = U.ref_decode(x, FS)
-        out, st = U.sim_pipeline(x, S.block_flags_device_model(x, sp), FS)
+        out, st = U.sim_pipeline(x, S.block_flags_device_model(x, sp), FS, group=group)
         frames += len(ref)
         if out != ref:
             bad += 1
