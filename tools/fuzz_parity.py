@@ -47,7 +47,7 @@ def stream(rng, tmpl, n):
         m[pos:pos + L] = tmpl[k]
         gap = int(np.exp(rng.uniform(np.log(300), np.log(60000))))
         pos += L + gap
-    A = rng.uniform(0.05, 0.6)
+    A = rng.uniform(float(os.environ.get("FUZZ_AMP_LO", 0.05)), float(os.environ.get("FUZZ_AMP_HI", 0.6)))
     level = np.full(n, A, np.float32)
     for _ in range(int(rng.integers(0, 3))):                # level steps
         p = int(rng.integers(0, n))
@@ -55,7 +55,7 @@ def stream(rng, tmpl, n):
     if rng.random() < 0.3:                                   # carrier dropout
         p = int(rng.integers(0, n - 40000))
         level[p:p + int(rng.integers(2000, 40000))] = 0.0
-    sigma = A * np.exp(rng.uniform(np.log(0.002), np.log(0.02)))
+    sigma = A * np.exp(rng.uniform(np.log(0.002), np.log(float(os.environ.get("FUZZ_NOISE_HI", 0.02)))))
     x = m * level + rng.normal(0, sigma, n).astype(np.float32)
     return np.abs(x).astype(np.float32)
 
