@@ -293,7 +293,10 @@ def main():
     if flow_test:
         dev = "cpu"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        if flow_test:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device(dev))
 
     S, n = args.streams, args.samples
     free, total_mem = torch.cuda.mem_get_info()

@@ -94,42 +94,7 @@ def test_gpu_arm_flow_with_a_stand_in_decoder(monkeypatch, capsys):
     import nfc_laboratory_b200 as N
     from nfc_laboratory_b200 import binding as B
 
-    class StandIn:
-        def __init__(self, device=0, **kw):
-            self._buf = None
-            self._st = {}
-
-        def _decode(self, a, rate):
-            out = []
-            for s in range(a.shape[0]):
-                mag = np.empty(a.shape[1], np.float32)
-                U.ref_lib().nfcref_iq_magnitude(np.ascontiguousarray(a[s]).ctypes.data, a.shape[1], mag.ctypes.data)
-                out += [(s,) + tuple(f) for f in U.ref_decode(mag, rate)]
-            self._st = {"ms_screen": 1.0, "ms_segment": 0.1, "ms_lanes": 5.0, "ms_gather": 0.1, "ms_total": 6.2, "ms_wall": 6.3, "kernel_launches": 9,
-                        "segments": 10, "lanes": 10, "rounds": 1, "lane_runs": 10, "lane_samples": a.shape[0] * a.shape[1] // 4, "samples": a.shape[0] * a.shape[1]}
-            return out
-
-        def decode_batch_ptr(self, ptr, on_device, sigtype, S, n, rate, cap=1 << 16, raw=False):
-            a = np.ctypeslib.as_array((C.c_float * (S * n * 2)).from_address(ptr)).reshape(S, n, 2)
-            recs = self._decode(a, rate)
-            buf = (B.CFrame * max(cap, len(recs)))()
-            for i, r in enumerate(recs):
-                f = buf[i]
-                f.stream, f.tech_type, f.frame_type, f.frame_flags, f.frame_phase, f.frame_rate = r[:6]
-                f.sample_start, f.sample_end, f.sample_rate, f.length = r[6], r[7], rate, len(r[8])
-                for k, byte in enumerate(r[8]):
-                    f.data[k] = byte
-            self._buf = buf
-            return buf, len(recs)
-
-        def decode_batch(self, t, sigtype, rate, cap=1 << 16):
-            return [B.Frame(r) for r in self._decode(t.numpy(), rate)]
-
-        def stats(self):
-            return dict(self._st)
-
-        def close(self):
-            pass
+    from bench_standin import StandIn
 
     monkeypatch.setenv("NFCB200_BENCH_FLOW_TEST", "1")
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
@@ -154,3 +119,25 @@ def test_gpu_arm_flow_with_a_stand_in_decoder(monkeypatch, capsys):
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["parity_spot_check"] is True
     assert d["full_size_check"]["streams_off_schedule"] == 0
     assert d["config"]["workload"].startswith("nfca106: 3 synthetic")
+
+
+@pytest.mark.skipif(U.ref_lib() is None, reason="oracle/_ref/libnfcref.so not built")
+def test_two_rank_flow_with_a_stand_in_decoder():
+    """the N > 1 path of bench.main() (one process per rank, barrier, frame gather to rank 0, max-over-ranks time) with gloo
+    in place of NCCL and the stand-in decoder: rank 0 prints ONE line for the whole job"""
+    port = 32500 + (os.getpid() % 2000)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "tests"), os.environ.get("PYTHONPATH", "")]))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "bench_standin.py"), "--gpus", "2", "--streams", "2", "--samples", "600000",
+                                       "--steps", "1", "--warmup", "1"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT))
+    outs = [p.communicate(timeout=600) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-3000:]
+    lines0 = [l for l in outs[0][0].splitlines() if l.startswith("{")]
+    lines1 = [l for l in outs[1][0].splitlines() if l.startswith("{")]
+    assert len(lines0) == 1 and lines1 == []
+    d = json.loads(lines0[0])
+    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["cpu_baseline"] is None and d["config"]["sharding"].startswith("streams")
+    assert d["decode"]["frames_per_step"] > 0 and d["e2e"]["streams"] == 2 and d["value"] > 0
