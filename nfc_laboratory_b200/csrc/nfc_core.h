@@ -138,6 +138,9 @@ struct Front
    u32 lockRate;  // rate index of the locked modulation
    u32 gate;      // local steps during which the detectors are off (reference: signalClock < BUFFER_SIZE)
    u32 warm;      // local steps during which carrier detection is suppressed (cold-started lanes)
+   u32 gateSum;   // local steps before which not even the detectors' running sums advance (<= gate).  Between gateSum and
+                  // gate only the sums and their correlation rings run (sums_only()): a lane that skipped an idle stretch with
+                  // its sums carried exactly (nfc_wlane.h) refills the rings this way before its detectors open
 };
 
 enum { LOCK_NONE = 0, LOCK_A = 1, LOCK_B = 2, LOCK_F = 3, LOCK_V = 4 };
@@ -207,6 +210,22 @@ NFC_HD bool odd_parity_ok(u32 value, u32 parity)
    return parity != 0;
 }
 
+// NfcTech.cpp:39-42: abs(x - env) / env < 0.05f.  The IEEE division is only executed when the quotient is within 2 % of the
+// threshold; outside that band the comparison is decided by a / env <= 0.049 (1 + ulp) < 0.05 resp. >= 0.051 (1 - ulp) > 0.05.
+// The shortcut needs a positive envelope: a negative one (mono input with negative samples) makes the reference's quotient
+// negative, i.e. "open", and env == 0 gives inf / NaN, which compare false there as well as here.
+NFC_HD bool gate_open(float adiff, float env)
+{
+   if (env > 0.0f)
+   {
+      if (adiff < 0.049f * env)
+         return true;
+      if (adiff > 0.051f * env)
+         return false;
+   }
+   return (adiff / env) < 0.05f;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // lane machine.  STRIDE = 1 on the host, 32 on the device (scratch words of the 32 lanes of a warp are interleaved).
 // SINK must provide: void frame(const FrameOut &f, const u8 *payload)
@@ -266,9 +285,14 @@ struct Machine
    bool pollTaps;     // TAPS == 2: slots [0] of T hold the taps of the locked NFC-A poll symbol decoder for this step
    float curX, curW;  // sample and edge value of the current step (ring slot of delay 0)
    bool slow;         // a detector left its idle fast path during this step: F.busy must be rebuilt
+   // feature-fed front end (nfc_wlane.h): the recurrences of nextSample were evaluated by the front pass, the sample rings
+   // are already filled for this step; only the scalars the detectors read are taken over
+   bool featMode;
+   float featAvg;
 
    NFC_HD Machine(const Params &p, Lane &l, Front &f, float *r, u8 *s, SINK &k)
-      : P(p), L(l), F(f), rg(r), sb(s), sink(k), tapsValid(false), pollTaps(false), curX(0), curW(0), slow(false)
+      : P(p), L(l), F(f), rg(r), sb(s), sink(k), tapsValid(false), pollTaps(false), curX(0), curW(0), slow(false), featMode(false),
+        featAvg(0)
    {
    }
 
@@ -473,13 +497,7 @@ struct Machine
       // executed when the quotient is within 2 % of the threshold; outside that band the comparison is decided by
       // a / env <= 0.049 (1 + ulp) < 0.05 resp. >= 0.051 (1 - ulp) > 0.05 (inf / NaN at env == 0 compare false, as there)
       const float adiff = fabsf(x - f.env);
-      bool open;
-      if (adiff < 0.049f * f.env)
-         open = true;
-      else if (adiff > 0.051f * f.env)
-         open = false;
-      else
-         open = (adiff / f.env) < 0.05f;
+      const bool open = gate_open(adiff, f.env);
 
       // retirement bookkeeping: while the gate stays closed the envelope is stale and thresholds derived from it
       // differ from what the screening pass assumes, so such a lane is never dormant
@@ -518,7 +536,14 @@ struct Machine
       SMP(NFCB200_OFF_D, 0) = f.dev;
       SMP(NFCB200_OFF_M, 0) = f.env;
 
-      float rect = fabsf(w); // :77-92
+      edge_track(w); // :77-92
+   }
+
+   // the carrier-edge tracker of nextSample (NfcTech.cpp:77-92) on the edge value of the current step
+   NFC_HD void edge_track(float w)
+   {
+      Front &f = F;
+      float rect = fabsf(w);
 
       if (rect > P.highThr)
       {
@@ -531,6 +556,53 @@ struct Machine
       else if (rect < P.lowThr)
       {
          f.edgePeak = 0;
+      }
+   }
+
+   // feature mode: x / w / dev / envelope of this step already sit in the sample rings (slot of delay 0)
+   NFC_HD void front_feat()
+   {
+      Front &f = F;
+      curX = SMP(NFCB200_OFF_X, 0);
+      curW = SMP(NFCB200_OFF_W, 0);
+      f.env = SMP(NFCB200_OFF_M, 0);
+      f.avg = featAvg;
+      NFC_TRACE(0, curX);
+      NFC_TRACE(1, curW);
+      NFC_TRACE(2, (float) SMP(NFCB200_OFF_D, 0));
+      NFC_TRACE(3, f.avg);
+      edge_track(curW);
+   }
+
+   // the detectors' running sums and correlation rings of one search-mode sample without any detector logic: what every
+   // detectModulation does on a sample on which nothing can trigger (NfcA.cpp:246-250, NfcF.cpp:240-244, NfcV.cpp:258-270)
+   NFC_HD void sums_only()
+   {
+      if (P.enabled & EN_A)
+         for (int r = 0; r < 3; r++)
+         {
+            const RateParams &b = P.A[r];
+            Mod &m = L.c.mA[r];
+            FI(m) += SMP(NFCB200_OFF_X, b.sdd);
+            FI(m) -= SMP(NFCB200_OFF_X, b.sdd + b.p2);
+            RG(b.corr, F.cA[r]) = FI(m);
+         }
+      if (P.enabled & EN_F)
+         for (int r = 1; r <= 2; r++)
+         {
+            const RateParams &b = P.F[r];
+            Mod &m = L.c.mF[r - 1];
+            FI(m) += SMP(NFCB200_OFF_X, b.sdd);
+            FI(m) -= SMP(NFCB200_OFF_X, b.sdd + b.p2);
+            RG(b.corr, F.cF[r - 1]) = FI(m);
+         }
+      if (P.enabled & EN_V)
+      {
+         const RateParams &b = P.V;
+         Mod &m = L.c.mV;
+         FI(m) += SMP(NFCB200_OFF_X, b.sdd);
+         FI(m) -= SMP(NFCB200_OFF_X, b.sdd + b.p2);
+         RG(b.corr, F.cV1) = FI(m);
       }
    }
 
@@ -3549,7 +3621,10 @@ struct Machine
             prefetch_locked_taps(1);
       }
 
-      front(x);
+      if (featMode)
+         front_feat();
+      else
+         front(x);
 
       if (F.lock == LOCK_NONE)
       {
@@ -3558,7 +3633,11 @@ struct Machine
 
          // `signalClock < BUFFER_SIZE` and `signalEnvelope < powerLevelThreshold` gates of every detectModulation
          if (F.k - 1 < F.gate || F.env < P.power)
+         {
+            if (!(F.k - 1 < F.gateSum) && !(F.env < P.power))
+               sums_only();
             return;
+         }
 
          if ((P.enabled & EN_A) && A_detect())
             L.lockedMask |= 1u << TECH_A;
@@ -3837,6 +3916,7 @@ NFC_HD void lane_begin(Lane &L, const Params &P, const Carry &carry, u32 first, 
    // cold-started lane keeps them off until 512 samples before its own region: enough to refill the correlation rings
    // (longest period 378), while the front end alone converges over the rest of the halo
    L.fe.gate = (first && warm > NFCB200_RING + 512) ? warm - 512 : NFCB200_RING;
+   L.fe.gateSum = L.fe.gate;
 }
 
 }

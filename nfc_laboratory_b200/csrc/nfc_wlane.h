@@ -1,0 +1,794 @@
+/*
+ * nfc_wlane.h -- the warp lane: one WARP decodes one lane (a run of consecutive capture segments of one stream) from
+ * tiles in shared memory (host + device; tests/native/host_sim.cpp runs the same code with a one-lane "warp").
+ *
+ * Round 1 ran the per-sample machine of nfc_core.h one THREAD per segment with 26 kB of delay lines per thread in global
+ * memory: every tap was a DRAM round trip (1.6 % of the HBM roofline).  Here the work is split by what is sequential in
+ * the reference's arithmetic and what is not:
+ *
+ *   front pass   (front_pass, one THREAD per segment, registers only)   the four float recurrences of nextSample
+ *                (NfcTech.cpp:39-68: gated envelope, DC-removal IIR, deviation and mean EMAs) are sequential by
+ *                construction -- every step rounds -- but touch no history: they run thread-per-segment at full SIMT
+ *                width and leave w / envelope / deviation / mean per sample in a FEATURE pool in HBM.
+ *   warp lane    (WLane, one WARP per lane, all history in SHARED memory)  reads the features 32 samples at a time
+ *                (coalesced), and advances the decoder:
+ *                  - search mode with every detector idle (85 % of the reference's CPU time): the six
+ *                    running sums (NfcA.cpp:246-250, NfcF.cpp:240-244, NfcV.cpp:258-270) advance as six sequential float
+ *                    chains on six threads -- the reference's own recurrence, add then subtract, same rounding -- and
+ *                    the 32 threads evaluate every detector's trigger condition for 32 samples at once (ff_search);
+ *                    only a sample on which some detector would leave its idle state goes to
+ *                  - the exact per-sample machine (nfc_core.h Machine::step) on one thread, rings in shared memory.
+ *   exact carry  a lane that skips the idle stretch between two segments keeps its running sums EXACT: when no add
+ *                in between can round and the detectors run throughout (decided from the screening
+ *                pass's block means, 16-bit mono input) the sum moves by the exact change of its window sum; on float
+ *                input the lane walks the stretch with the sums alone (WALK), the reference's own add / subtract.  A stream decoded by ONE lane therefore carries the reference's
+ *                float state across the whole capture: no cold start, no speculation, bit-exact on float input.
+ *
+ * Nothing here has a counterpart in the reference (one CPU thread per stream, one sample at a time).
+ */
+#ifndef NFCB200_WLANE_H
+#define NFCB200_WLANE_H
+
+#include "nfc_chain.h"
+
+namespace nfcb200 {
+
+struct Feat
+{
+   float w, env, dev, avg; // filteredValue, signalEnvelope, meanDeviation, signalAverage after the sample (NfcTech.cpp:53-68)
+};
+
+// one segment with its feature range [first, end)
+struct SegRec
+{
+   u32 stream;
+   u32 first;  // first sample of the front pass (its warm-up starts here)
+   u32 begin;  // own region [begin, end), block aligned
+   u32 end;
+   unsigned long long featOff; // index of the feature of sample `first` in the pool
+   float tEnv, tAvg, tDev, tF1; // front-end state after sample end - 1: a lane that runs past the range continues from it
+   u32 tPulse;
+   u32 band;   // the warm-up was the long one (carrier average exact)
+};
+
+#define NFCB200_PREROLL 400u /* samples of sums + rings before the detectors of a skipped-to segment open (> longest period) */
+
+// gated envelope, DC-removal IIR, deviation and mean EMAs of NfcDecoderStatus::nextSample (NfcTech.cpp:39-68) over
+// [first, end) from a zero state: expression for expression what Machine::front() computes (nfc_core.h)
+template <class LOADX, class STORE>
+NFC_HD void front_pass(const Params &P, u32 first, u32 end, LOADX loadx, STORE store, SegRec &S)
+{
+   float env = 0, avg = 0, dev = 0, f1 = 0;
+   u32 pulse = 0;
+   const u32 etu = (u32) P.etu, hold = (u32) (P.etu * 10);
+
+   for (u32 pos = first; pos < end; pos++)
+   {
+      const float x = loadx(pos);
+
+      ++pulse;
+
+      const float adiff = fabsf(x - env);
+      const bool open = gate_open(adiff, env);
+
+      if (open || pulse > hold)
+      {
+         pulse = 0;
+         env = env * P.envW0 + x * P.envW1;
+      }
+      else if (pos - first < etu)
+      {
+         env = x;
+      }
+
+      float n0 = x + f1 * P.iirA;
+      float w = n0 - f1;
+      f1 = n0;
+
+      dev = dev * P.mdevW0 + fabsf(w) * P.mdevW1;
+      avg = avg * P.meanW0 + x * P.meanW1;
+
+      store(pos - first, w, env, dev, avg);
+   }
+
+   S.tEnv = env;
+   S.tAvg = avg;
+   S.tDev = dev;
+   S.tF1 = f1;
+   S.tPulse = pulse;
+}
+
+// a "warp" of one thread: the host build runs every strided loop to completion and every collective is the identity
+struct HostWarp
+{
+   static NFC_HD u32 lane() { return 0; }
+   static NFC_HD u32 width() { return 1; }
+   static NFC_HD void sync() {}
+   static NFC_HD u32 min_u32(u32 v) { return v; }
+   static NFC_HD u32 add_u32(u32 v) { return v; }
+   static NFC_HD float add_f32(float v) { return v; }
+   static NFC_HD u32 or_u32(u32 v) { return v; }
+};
+
+// per-warp scratch next to the rings (shared memory on the device)
+struct WShared
+{
+   float lin[6][40]; // running sums of the current fast-forward span, entry a = after a samples (a = 1 .. 32)
+   float cavg[32];   // carrier average of the chunk's samples
+   u32 act;          // control: what the warp does next (WLANE_*)
+   u32 pos, n, mode, si, j, stepped;
+   u32 jumpTa, jumpGs, jumpT, jumpG, jumpBegin, jumpSeg;
+   float delta[6];
+};
+
+enum { WLANE_DONE = 0, WLANE_CHUNK = 1, WLANE_JUMP = 2 };
+enum { WMODE_FEAT = 0, WMODE_SCAL = 1, WMODE_WALK = 2 };
+
+// the six running-sum chains: NFC-A 106 / 212 / 424, NFC-F 212 / 424, NFC-V
+struct SumChain
+{
+   u32 corr, p1, p2, sdd, fi, tech;
+};
+
+NFC_HD SumChain sum_chain(const Params &P, u32 d)
+{
+   SumChain c;
+   const RateParams &b = d < 3 ? P.A[d] : (d < 5 ? P.F[d - 2] : P.V);
+   c.corr = b.corr;
+   c.p1 = b.p1;
+   c.p2 = b.p2;
+   c.sdd = b.sdd;
+   c.fi = d < 3 ? d : (d < 5 ? d + 2 : 7); // index of the Mod inside Carry (nfc_core.h FI())
+   c.tech = d < 3 ? EN_A : (d < 5 ? EN_F : EN_V);
+   return c;
+}
+
+NFC_HD int float_exponent(float v)
+{
+   union
+   {
+      float f;
+      u32 u;
+   } c;
+   c.f = v;
+   return (int) ((c.u >> 23) & 0xff) - 127;
+}
+
+NFC_HD float pow2f(int e)
+{
+   union
+   {
+      float f;
+      u32 u;
+   } c;
+   c.u = (u32) (e + 127) << 23;
+   return c.f;
+}
+
+/*
+ * SRC (per lane):  float x(u32 pos)            magnitude of sample pos (reference operation order)
+ *                  Feat feat(u64 index)        feature pool entry
+ *                  bool active(u32 pos)        the block of pos is active
+ *                  float bmean(u32 b)          mean sample of block b (screening pass)
+ *                  const SegRec &seg(u32 i), u32 nseg()      the segment table (all streams, ordered by stream, time)
+ *                  bool exact_int()            samples are small integers over a power of two (16-bit mono): adds never round
+ */
+template <class W, class SINK, class SRC>
+struct WLane
+{
+   typedef Machine<1, SINK, 0, false> Mach;
+
+   const Params &P;
+   Lane &L;
+   Front &F;
+   float *rg;
+   WShared &sh;
+   const SRC &src;
+   Mach M;
+   bool noff; // self-check: every sample goes through the per-sample machine
+
+   NFC_HD WLane(const Params &p, Lane &l, float *r, u8 *s, SINK &k, WShared &w, const SRC &sr) : P(p), L(l), F(l.fe), rg(r), sh(w), src(sr), M(p, l, l.fe, r, s, k), noff(false)
+   {
+   }
+
+   NFC_HD u32 slot(u32 k, u32 delay) const
+   {
+      return (k + F.kbase - delay) & (NFCB200_RING - 1);
+   }
+
+   // ------------------------------------------------------------------------------------------------------------------
+   // ring fill: features of the chunk [pos, pos + n) into the sample rings; chunk sample i gets local step k0 + 1 + i
+   // ------------------------------------------------------------------------------------------------------------------
+   NFC_HD void fill_feat(u32 pos, u32 n, u32 k0, const SegRec &S)
+   {
+      u32 closedCnt = 0, openCnt = 0;
+
+      for (u32 i = W::lane(); i < n; i += W::width())
+      {
+         const u32 s = slot(k0 + 1 + i, 0);
+         const float x = src.x(pos + i);
+         const Feat f = src.feat(S.featOff + (pos + i - S.first));
+         rg[NFCB200_OFF_X + s] = x;
+         rg[NFCB200_OFF_W + s] = f.w;
+         rg[NFCB200_OFF_D + s] = f.dev;
+         rg[NFCB200_OFF_M + s] = f.env;
+         sh.cavg[i] = f.avg;
+      }
+
+      W::sync();
+
+      // gate state of the chunk's samples for the retirement heuristic (Front::closed): the envelope before a sample is
+      // the envelope feature of the previous one
+      for (u32 i = W::lane(); i < n; i += W::width())
+      {
+         const float x = rg[NFCB200_OFF_X + slot(k0 + 1 + i, 0)];
+         const float envPrev = rg[NFCB200_OFF_M + slot(k0 + i, 0)];
+         if (gate_open(fabsf(x - envPrev), envPrev))
+            openCnt++;
+         else
+            closedCnt++;
+      }
+
+      closedCnt = W::add_u32(closedCnt);
+      openCnt = W::add_u32(openCnt);
+
+      if (W::lane() == 0)
+      {
+         u32 c = F.closed + closedCnt;
+         c = c > openCnt ? c - openCnt : 0;
+         F.closed = c > 4096 ? 4096 : c;
+      }
+   }
+
+   NFC_HD void fill_x(u32 pos, u32 n, u32 k0)
+   {
+      for (u32 i = W::lane(); i < n; i += W::width())
+         rg[NFCB200_OFF_X + slot(k0 + 1 + i, 0)] = src.x(pos + i);
+   }
+
+   // ------------------------------------------------------------------------------------------------------------------
+   // running sums of `cnt` samples following local step k (F.k): six sequential chains, results in sh.lin[d][1 .. cnt]
+   // ------------------------------------------------------------------------------------------------------------------
+   NFC_HD void sum_chains(u32 cnt)
+   {
+      for (u32 d = W::lane(); d < 6; d += W::width())
+      {
+         const SumChain c = sum_chain(P, d);
+         if (!(P.enabled & c.tech))
+            continue;
+         float s = F.fi[c.fi];
+         u32 s0 = slot(F.k + 1, c.sdd), s1 = slot(F.k + 1, c.sdd + c.p2);
+         float *lin = sh.lin[d];
+         lin[0] = s;
+         for (u32 a = 1; a <= cnt; a++)
+         {
+            s += rg[NFCB200_OFF_X + s0];
+            s -= rg[NFCB200_OFF_X + s1];
+            lin[a] = s;
+            s0 = (s0 + 1) & (NFCB200_RING - 1);
+            s1 = (s1 + 1) & (NFCB200_RING - 1);
+         }
+      }
+   }
+
+   // value of chain d's correlation ring as seen by the sample `a` steps after F.k, `back` samples before it
+   NFC_HD float corr_at(u32 d, const SumChain &c, u32 phase0, u32 a, u32 back) const
+   {
+      if (back < a)
+         return sh.lin[d][a - back];
+      // older than this span: still in the ring (the span's own values are committed afterwards)
+      u32 ph = (phase0 + a + c.p1 * 2 - back) % c.p1;
+      return rg[c.corr + ph];
+   }
+
+   NFC_HD u32 phase_of(u32 d) const
+   {
+      return d < 3 ? F.cA[d] : (d < 5 ? F.cF[d - 3] : F.cV1);
+   }
+
+   // commit m samples of a fast-forward span: rings, sums, clocks, ring phases
+   NFC_HD void commit(u32 m, bool sums)
+   {
+      if (sums)
+      {
+         for (u32 d = 0; d < 6; d++)
+         {
+            const SumChain c = sum_chain(P, d);
+            if (!(P.enabled & c.tech))
+               continue;
+            const u32 ph0 = phase_of(d);
+            for (u32 a = 1 + W::lane(); a <= m; a += W::width())
+               rg[c.corr + (ph0 + a) % c.p1] = sh.lin[d][a];
+         }
+      }
+
+      W::sync();
+
+      if (W::lane() == 0)
+      {
+         if (sums)
+            for (u32 d = 0; d < 6; d++)
+            {
+               const SumChain c = sum_chain(P, d);
+               if (P.enabled & c.tech)
+                  F.fi[c.fi] = sh.lin[d][m];
+            }
+         F.k += m;
+         F.clk += m;
+         F.pulseFilter += m;
+         for (int r = 0; r < 3; r++)
+            F.cA[r] = (F.cA[r] + m) % P.A[r].p1;
+         for (int r = 0; r < 2; r++)
+            F.cF[r] = (F.cF[r] + m) % P.F[r + 1].p1;
+         F.cV1 = (F.cV1 + m) % P.V.p1;
+         F.cV0 = (F.cV0 + m) % P.V.p0;
+      }
+
+      W::sync();
+   }
+
+   /*
+    * Search mode, every detector idle (F.lock == LOCK_NONE, F.busy == 0): advance over the samples of the chunk from
+    * index j on which nothing but the running sums moves.  Returns the number of samples consumed; the sample after them
+    * (if inside the chunk) needs the scalar machine: a carrier event, a carrier edge, or a detector leaving its idle state
+    * (the conditions are the idle fast paths of A_detect / B_detect / F_detect / V_detect, nfc_core.h).
+    */
+   NFC_HD u32 ff_search(u32 j, u32 n, u32 carrierOn, u32 carrierOff)
+   {
+      const u32 k = F.k, gate = F.gate, gateSum = F.gateSum, warm = F.warm;
+      const u32 rem = n - j;
+
+      // ---- regime of every sample (0 off, 1 sums only, 2 detectors) and the events the machine must see ---------------
+      u32 regime0 = 0;
+      {
+         const float env = rg[NFCB200_OFF_M + slot(k + 1, 0)];
+         regime0 = (k < gateSum || env < P.power) ? 0 : (k < gate ? 1 : 2);
+      }
+
+      u32 cut = rem; // samples [0, cut) of the span are event-free and share regime0
+      u32 below = 0; // bit a-1: |w| < low threshold (edge peak reset)
+
+      for (u32 a = 1 + W::lane(); a <= rem; a += W::width())
+      {
+         const u32 ka = k + a;
+         const u32 s = slot(ka, 0);
+         const float env = rg[NFCB200_OFF_M + s];
+         const float rect = fabsf(rg[NFCB200_OFF_W + s]);
+         const float avg = sh.cavg[j + a - 1];
+         const u32 regime = (ka - 1 < gateSum || env < P.power) ? 0 : (ka - 1 < gate ? 1 : 2);
+         bool ev = regime != regime0;
+         ev |= rect > P.highThr;
+         if (ka > warm)
+            ev |= (avg > P.highThr && !carrierOn) || (!(avg > P.highThr) && avg < P.lowThr && !carrierOff);
+         if (ev && a - 1 < cut)
+            cut = a - 1;
+         if (rect < P.lowThr)
+            below |= 1u << (a - 1);
+      }
+
+      cut = W::min_u32(cut);
+      below = W::or_u32(below);
+
+      if (cut == 0)
+         return 0;
+
+      u32 m = cut;
+
+      if (regime0 != 0)
+      {
+         sum_chains(cut);
+         W::sync();
+      }
+
+      if (regime0 == 2)
+      {
+         // ---- trigger conditions, one sample per thread --------------------------------------------------------------
+         u32 first = cut + 1; // first a whose sample must go to the machine
+
+         for (u32 a = 1 + W::lane(); a <= cut; a += W::width())
+         {
+            const u32 ka = k + a;
+            const float env = rg[NFCB200_OFF_M + slot(ka, 0)];
+            bool trig = false;
+
+            if (P.enabled & EN_A)
+            {
+               const float thr = env * P.thr[TECH_A].corr;
+               for (u32 d = 0; d < 3; d++)
+               {
+                  const SumChain c = sum_chain(P, d);
+                  const float c1 = sh.lin[d][a];
+                  const float c2 = corr_at(d, c, F.cA[d], a, c.p1 - c.p2);
+                  const float c3 = corr_at(d, c, F.cA[d], a, 1);
+                  const float s0 = c1 - c2, s1 = c2 - c3;
+                  trig |= !((s0 - s1) > -0.5f * thr * (float) c.p2);
+               }
+            }
+
+            if (P.enabled & EN_B)
+            {
+               const float thr = env * P.thr[TECH_B].modMin;
+               for (u32 r = 0; r < 2; r++)
+               {
+                  const float edge = rg[NFCB200_OFF_W + slot(ka, P.B[r].sdd)];
+                  trig |= edge < -thr;
+               }
+            }
+
+            if (P.enabled & EN_F)
+            {
+               const float thr = env * P.thr[TECH_F].corr;
+               for (u32 d = 3; d < 5; d++)
+               {
+                  const SumChain c = sum_chain(P, d);
+                  const float c1 = sh.lin[d][a];
+                  const float c2 = corr_at(d, c, F.cF[d - 3], a, c.p1 - c.p2);
+                  const float c3 = corr_at(d, c, F.cF[d - 3], a, 1);
+                  const float q0 = c1 - c2, q1 = c2 - c3;
+                  trig |= !(fabsf(q0 - q1) < 0.5f * thr * (float) c.p2);
+               }
+            }
+
+            if (P.enabled & EN_V)
+            {
+               const SumChain c = sum_chain(P, 5);
+               const float c1 = sh.lin[5][a];
+               const float c2 = corr_at(5, c, F.cV1, a, c.p1 - c.p2);
+               const float s0 = (c2 - c1) / (float) c.p2;
+               trig |= s0 > env * P.thr[TECH_V].corr;
+            }
+
+            if (trig && a < first)
+               first = a;
+         }
+
+         first = W::min_u32(first);
+         m = first - 1;
+      }
+
+      if (m == 0)
+         return 0;
+
+      // edge peak: no sample of the span exceeds the high threshold; any sample below the low one clears the peak
+      if (W::lane() == 0)
+      {
+         const u32 mask = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
+         if (below & mask)
+            F.edgePeak = 0;
+         F.env = rg[NFCB200_OFF_M + slot(k + m, 0)];
+         F.avg = sh.cavg[j + m - 1];
+      }
+
+      commit(m, regime0 != 0);
+      return m;
+   }
+
+   // WALK: the idle stretch between two segments, sums only (no features exist there)
+   NFC_HD void walk_chunk(u32 n)
+   {
+      sum_chains(n);
+      W::sync();
+      commit(n, true);
+   }
+
+   // ------------------------------------------------------------------------------------------------------------------
+   // exact carry of the running sums over an idle stretch (ta = last sample consumed, gs = first sample of the pre-roll)
+   // ------------------------------------------------------------------------------------------------------------------
+   // 1: the detectors run on every sample between ta and gs AND every add is exact (16-bit mono input: the sums are small
+   //    integers over 2^15) -> the sums move by the change of their window sums; 2: detectors off throughout (envelope below
+   //    the power threshold: sums frozen); 3: detectors run, adds may round (float input: even on an idle carrier the sum
+   //    crosses into the next binade often enough) -> the stretch is walked with the sums alone; 0: cannot tell, keep stepping.
+   // The level test uses the block means of the screening pass: an inactive block holds no level shift (nfc_decode.cuh
+   // segment_flags_kernel), so its mean is the envelope to within the noise.
+   NFC_HD int gap_class(u32 ta, u32 gs) const
+   {
+      const u32 lookback = P.V.sdd + P.V.p2 + 8;
+      const u32 b0 = (ta > lookback ? ta - lookback : 0) / NFCB200_BLOCK, b1 = gs / NFCB200_BLOCK;
+      float mn = 3.0e38f, mx = -3.0e38f;
+
+      for (u32 b = b0; b <= b1; b++)
+      {
+         const float m = src.bmean(b);
+         mn = m < mn ? m : mn;
+         mx = m > mx ? m : mx;
+      }
+
+      if (mx < 0.5f * P.power)
+         return 2;
+
+      if (!(mn > 2.0f * P.power))
+         return 0;
+
+      return src.exact_int() ? 1 : 3;
+   }
+
+   // change of the six window sums between ta and gs - 1 (every partial sum is exact under gap_class == 1)
+   NFC_HD void gap_delta(u32 ta, u32 gs)
+   {
+      for (u32 d = 0; d < 6; d++)
+      {
+         const SumChain c = sum_chain(P, d);
+         float acc = 0;
+         if (P.enabled & c.tech)
+            for (u32 i = W::lane(); i < c.p2; i += W::width())
+               acc += src.x(gs - 1 - c.sdd - i) - src.x(ta - c.sdd - i);
+         acc = W::add_f32(acc);
+         if (W::lane() == 0)
+            sh.delta[d] = acc;
+      }
+      W::sync();
+   }
+
+   // ------------------------------------------------------------------------------------------------------------------
+   // control (one thread): what comes next at sh.pos
+   // ------------------------------------------------------------------------------------------------------------------
+   NFC_HD bool seg_of_lane(u32 i, const LaneRec &R) const
+   {
+      if (i >= src.nseg())
+         return false;
+      const SegRec &S = src.seg(i);
+      return S.stream == R.stream && S.begin < R.end;
+   }
+
+   NFC_HD void enter_scalar(const SegRec &S)
+   {
+      // the lane ran past its feature range without settling: it continues with the per-sample front end from the state
+      // the front pass left at the end of the range
+      F.env = S.tEnv;
+      F.avg = S.tAvg;
+      F.dev = S.tDev;
+      F.f1 = S.tF1;
+      F.pulseFilter = S.tPulse;
+      sh.mode = WMODE_SCAL;
+   }
+
+   NFC_HD void control(const LaneRec &R, u32 nsamples)
+   {
+      u32 pos = sh.pos;
+
+      sh.act = WLANE_CHUNK;
+
+      if (pos >= nsamples)
+      {
+         sh.act = WLANE_DONE;
+         return;
+      }
+
+      if (sh.mode == WMODE_WALK)
+      {
+         const SegRec &S = src.seg(sh.si);
+         if (pos >= S.first)
+            sh.mode = WMODE_FEAT;
+         else
+         {
+            u32 n = 32 - (pos & 31);
+            if (n > S.first - pos)
+               n = S.first - pos;
+            sh.n = n;
+            return;
+         }
+      }
+
+      const SegRec &S = src.seg(sh.si);
+
+      if (sh.mode == WMODE_FEAT && pos < S.end)
+      {
+         u32 n = 32 - (pos & 31);
+         if (n > S.end - pos)
+            n = S.end - pos;
+         sh.n = n;
+         return;
+      }
+
+      // past the feature range: retire, skip ahead, or go on with the scalar front end
+      if ((pos & 31) == 0 && !src.active(pos) && M.dormant())
+      {
+         if (pos >= R.end)
+         {
+            sh.act = WLANE_DONE;
+            return;
+         }
+
+         // the next segment with samples left (a lane that ran past its range may already be inside a later one)
+         u32 ni = sh.si;
+         while (seg_of_lane(ni, R) && src.seg(ni).end <= pos)
+            ni++;
+
+         if (seg_of_lane(ni, R) && src.seg(ni).first < pos)
+         {
+            // inside that segment's feature range: its features are exact once the front pass has converged (the same
+            // contraction a lane start relies on), and they continue the lane's own rings without a seam
+            const SegRec &N = src.seg(ni);
+            if (pos >= N.first + NFCB200_HALO_SHORT)
+            {
+               sh.mode = WMODE_FEAT;
+               sh.si = ni;
+               u32 n = 32;
+               if (n > N.end - pos)
+                  n = N.end - pos;
+               sh.n = n;
+               return;
+            }
+         }
+         else if (seg_of_lane(ni, R))
+         {
+            const SegRec &N = src.seg(ni);
+            const u32 g = N.begin - 512 > N.first + NFCB200_RING ? N.begin - 512 : N.first + NFCB200_RING; // detectors open (lane_begin)
+            const u32 gs = g - NFCB200_PREROLL;
+            const int cls = gs > pos + 64 ? gap_class(pos - 1, gs) : 0;
+
+            if (cls == 1 || cls == 2)
+            {
+               sh.act = WLANE_JUMP;
+               sh.jumpTa = pos - 1;
+               sh.jumpGs = gs;
+               sh.jumpT = N.first;
+               sh.jumpG = g;
+               sh.jumpBegin = N.begin;
+               sh.jumpSeg = ni;
+               sh.n = cls; // 1: sums move by the window change, 2: frozen
+#if defined(NFCB200_WLANE_DEBUG)
+               std::fprintf(stderr, "jump cls %d from %u to first %u begin %u (g %u gs %u) k %u\n", cls, pos, N.first, N.begin, g, gs, F.k);
+#endif
+               return;
+            }
+
+            if (cls == 3)
+            {
+               // adds may round: walk the stretch with the sums alone
+               sh.mode = WMODE_WALK;
+               sh.si = ni;
+               F.gateSum = F.k;
+               F.gate = F.k + (g - pos);
+               F.warm = F.k + (N.begin - pos);
+               u32 n = 32;
+               if (n > N.first - pos)
+                  n = N.first - pos;
+               sh.n = n;
+               return;
+            }
+         }
+      }
+
+      if (sh.mode == WMODE_FEAT)
+         enter_scalar(S);
+
+      {
+         u32 n = 32 - (pos & 31);
+         if (n > nsamples - pos)
+            n = nsamples - pos;
+         sh.n = n;
+      }
+   }
+
+   // ------------------------------------------------------------------------------------------------------------------
+   // one lane run
+   // ------------------------------------------------------------------------------------------------------------------
+   NFC_HD void run(const LaneRec &R, u32 seg0, u32 nsamples)
+   {
+      if (W::lane() == 0)
+      {
+         lane_begin(L, P, R.in, R.first, R.begin - R.first);
+         M.reload_front();
+         sh.pos = R.first;
+         sh.mode = WMODE_FEAT;
+         sh.si = seg0;
+         sh.stepped = 0;
+      }
+      W::sync();
+
+      for (;;)
+      {
+         if (W::lane() == 0)
+            control(R, nsamples);
+         W::sync();
+
+         const u32 act = sh.act;
+
+         if (act == WLANE_DONE)
+            break;
+
+         if (act == WLANE_JUMP)
+         {
+            const bool moving = sh.n == 1;
+            if (moving)
+               gap_delta(sh.jumpTa, sh.jumpGs);
+            if (W::lane() == 0)
+            {
+               if (moving)
+                  for (u32 d = 0; d < 6; d++)
+                  {
+                     const SumChain c = sum_chain(P, d);
+                     if (P.enabled & c.tech)
+                        F.fi[c.fi] += sh.delta[d];
+                  }
+               const u32 T = sh.jumpT;
+               F.clk = T - 1;
+               F.gate = F.k + (sh.jumpG - T);
+               F.gateSum = F.k + (sh.jumpGs - T);
+               F.warm = F.k + (sh.jumpBegin - T);
+               F.closed = 0;
+               sh.si = sh.jumpSeg;
+               sh.mode = WMODE_FEAT;
+               sh.pos = T;
+            }
+            W::sync();
+            continue;
+         }
+
+         const u32 pos = sh.pos, n = sh.n, mode = sh.mode;
+         const u32 k0 = F.k;
+
+         if (mode == WMODE_FEAT)
+         {
+            fill_feat(pos, n, k0, src.seg(sh.si));
+            W::sync();
+            chunk_feat(n);
+         }
+         else if (mode == WMODE_WALK)
+         {
+            fill_x(pos, n, k0);
+            W::sync();
+            walk_chunk(n);
+         }
+         else
+         {
+            if (W::lane() == 0)
+            {
+               M.featMode = false;
+               for (u32 i = 0; i < n; i++)
+                  M.step(src.x(pos + i));
+            }
+         }
+
+         if (W::lane() == 0)
+         {
+            sh.pos = pos + n;
+            sh.stepped += n;
+         }
+         W::sync();
+      }
+   }
+
+   // the samples of one filled chunk
+   NFC_HD void chunk_feat(u32 n)
+   {
+      u32 j = 0;
+
+      while (j < n)
+      {
+         const bool idle = F.lock == LOCK_NONE && F.busy == 0 && !noff;
+         const u32 carrierOn = L.c.carrierOn, carrierOff = L.c.carrierOff;
+         W::sync();
+
+         if (idle)
+         {
+            const u32 m = ff_search(j, n, carrierOn, carrierOff);
+            j += m;
+            if (j >= n)
+               break;
+         }
+
+         // the machine, until it is idle again (or the chunk ends); after a fast-forward span at least one sample
+         if (W::lane() == 0)
+         {
+            M.featMode = true;
+            u32 i = j;
+            do
+            {
+               M.featAvg = sh.cavg[i];
+               M.step(0.0f);
+               i++;
+            } while (i < n && (noff || !(F.lock == LOCK_NONE && F.busy == 0)));
+            sh.j = i;
+         }
+         W::sync();
+         j = sh.j;
+         W::sync();
+      }
+   }
+};
+
+}
+
+#endif

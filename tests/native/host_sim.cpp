@@ -31,7 +31,7 @@ static inline void nfcb200_trace_value(int channel, float value)
       g_trace_row[channel] = value;
 }
 
-#include "../../nfc_laboratory_b200/csrc/nfc_chain.h"
+#include "../../nfc_laboratory_b200/csrc/nfc_wlane.h"
 
 // tap fetch variant of the lane machine under test: the one the device library ships (nfcb200.cu laneTaps)
 #ifndef NFCB200_SIM_TAPS
@@ -345,6 +345,181 @@ long hostsim_pipeline(const float *mag, uint64_t n, uint32_t sampleRate, uint32_
    }
 
    return count;
+}
+
+
+/*
+ * Whole-stream model of the round-2 product pipeline (nfc_wlane.h): segments from the screening flags, the front pass per
+ * segment into a feature pool, one WARP LANE (here: a one-thread warp) per group of segments, carry chain to the fixed point.
+ * group == 0: ONE lane for the whole stream (exact running sums, no speculation).  noff != 0: every sample goes through the
+ * per-sample machine (fast-forward paths off) -- the self-check of the fast paths.
+ * stats: [0] lanes [1] live lanes [2] rounds [3] lane runs [4] samples stepped [5] active blocks [6] segments [7] feature samples
+ */
+struct HostSrc
+{
+   const float *mag;
+   const Feat *pool;
+   const uint8_t *flags;
+   const float *bmeans;
+   const SegRec *segs;
+   uint32_t nsegs;
+   bool exactInt;
+
+   float x(uint32_t pos) const { return mag[pos]; }
+   Feat feat(unsigned long long i) const { return pool[i]; }
+   bool active(uint32_t pos) const { return (flags[pos / NFCB200_BLOCK] & SCR_ACTIVE) != 0; }
+   float bmean(uint32_t b) const { return bmeans[b]; }
+   const SegRec &seg(uint32_t i) const { return segs[i]; }
+   uint32_t nseg() const { return nsegs; }
+   bool exact_int() const { return exactInt; }
+};
+
+int g_hostsim_noff = 0;
+
+long hostsim_pipeline2(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t enabled, uint8_t *flags, uint32_t nb, sim_frame *out, long cap,
+                       uint64_t *stats, uint32_t group, uint32_t exactInt)
+{
+   Params P;
+   if (!hostsim_params(sampleRate, enabled, &P))
+      return -1;
+
+   blocks_activate(flags, nb);
+
+   // block means (the device takes them from the screening pass)
+   std::vector<float> bmeans(nb);
+   for (uint32_t b = 0; b < nb; b++)
+   {
+      double acc = 0;
+      uint64_t cnt = 0;
+      for (uint64_t i = (uint64_t) b * NFCB200_BLOCK; i < n && i < (uint64_t) (b + 1) * NFCB200_BLOCK; i++, cnt++)
+         acc += mag[i];
+      bmeans[b] = cnt ? (float) (acc / cnt) : 0.0f;
+   }
+
+   // segments and their feature ranges
+   uint32_t nseg = blocks_segments(flags, nb, (uint32_t) n, 0, nullptr, 0, 1);
+   std::vector<LaneRec> segl(nseg);
+   blocks_segments(flags, nb, (uint32_t) n, 0, segl.data(), nseg, 1);
+   std::vector<SegRec> segs(nseg);
+   uint64_t total = 0;
+   for (uint32_t i = 0; i < nseg; i++)
+   {
+      SegRec &S = segs[i];
+      std::memset(&S, 0, sizeof(S));
+      S.stream = 0;
+      S.first = segl[i].first;
+      S.begin = segl[i].begin;
+      S.end = segl[i].end;
+      S.featOff = total;
+      total += S.end - S.first;
+   }
+   std::vector<Feat> pool(total);
+   for (uint32_t i = 0; i < nseg; i++)
+   {
+      SegRec &S = segs[i];
+      Feat *dst = pool.data() + S.featOff;
+      front_pass(P, S.first, S.end, [&](uint32_t p) { return mag[p]; },
+                 [&](uint32_t i, float w, float env, float dev, float avg) { dst[i] = Feat {w, env, dev, avg}; }, S);
+   }
+
+   // lanes
+   const uint32_t grp = group ? group : (nseg ? nseg : 1);
+   uint32_t nlanes = blocks_segments(flags, nb, (uint32_t) n, 0, nullptr, 0, grp);
+   std::vector<LaneRec> lanes(nlanes);
+   blocks_segments(flags, nb, (uint32_t) n, 0, lanes.data(), nlanes, grp);
+   std::vector<uint32_t> seg0(nlanes);
+   for (uint32_t j = 0, i = 0; j < nlanes; j++)
+   {
+      while (i < nseg && segs[i].begin != lanes[j].begin)
+         i++;
+      seg0[j] = i;
+      if (lanes[j].first == 0)
+      {
+         carry_init(lanes[j].in, P);
+         carry_canon(lanes[j].in);
+      }
+      else
+         carry_speculate(lanes[j].in, P);
+   }
+
+   HostSrc src {mag, pool.data(), flags, bmeans.data(), segs.data(), nseg, exactInt != 0};
+
+   std::vector<std::vector<sim_frame>> frames(nlanes);
+   std::vector<float> scratch(NFCB200_SCRATCH_FLOATS);
+   std::vector<u8> sb(512);
+   uint64_t rounds = 0, runs = 0, work = 0;
+
+   for (;;)
+   {
+      bool any = false;
+
+      for (uint32_t j = 0; j < nlanes; j++)
+      {
+         LaneRec &R = lanes[j];
+         if (R.dead || !R.dirty)
+            continue;
+         any = true;
+
+         std::fill(scratch.begin(), scratch.end(), 0.0f);
+         std::fill(sb.begin(), sb.end(), 0);
+         std::vector<sim_frame> buf(65536);
+         Sink sink {buf.data(), (long) buf.size(), 0};
+
+         Lane L;
+         WShared sh;
+         std::memset(&sh, 0, sizeof(sh));
+         WLane<HostWarp, Sink, HostSrc> WL(P, L, scratch.data(), sb.data(), sink, sh, src);
+         WL.noff = g_hostsim_noff != 0;
+         WL.run(R, seg0[j], (uint32_t) n);
+
+         lane_record(R, L, sh.pos, R.gen + 1, (uint32_t) sink.count);
+         buf.resize(std::min<long>(sink.count, (long) buf.size()));
+         frames[j] = buf;
+         runs++;
+         work += sh.stepped;
+      }
+
+      if (!any)
+         break;
+      rounds++;
+      chain_walk(lanes.data(), nlanes, P);
+   }
+
+   long count = 0;
+   uint64_t live = 0;
+   for (uint32_t j = 0; j < nlanes; j++)
+   {
+      if (lanes[j].dead)
+         continue;
+      live++;
+      for (const sim_frame &f: frames[j])
+      {
+         if (count < cap)
+            out[count] = f;
+         count++;
+      }
+   }
+
+   if (stats)
+   {
+      uint64_t act = 0;
+      for (uint32_t b = 0; b < nb; b++)
+         act += (flags[b] & SCR_ACTIVE) ? 1 : 0;
+      stats[0] = nlanes;
+      stats[1] = live;
+      stats[2] = rounds;
+      stats[3] = runs;
+      stats[4] = work;
+      stats[5] = act;
+      stats[6] = nseg;
+      stats[7] = total;
+   }
+   return count;
+}
+
+void hostsim_set_noff(int v)
+{
+   g_hostsim_noff = v;
 }
 
 }

@@ -190,7 +190,7 @@ def port_decode(mag, rate=10000000, enabled=0xF, cap=65536):
 
 def build_hostsim():
     src = os.path.join(ROOT, "tests", "native", "host_sim.cpp")
-    deps = [src] + [os.path.join(ROOT, "nfc_laboratory_b200", "csrc", h) for h in ("nfc_core.h", "nfc_params.h", "nfc_chain.h")]
+    deps = [src] + [os.path.join(ROOT, "nfc_laboratory_b200", "csrc", h) for h in ("nfc_core.h", "nfc_params.h", "nfc_chain.h", "nfc_wlane.h")]
     if os.path.exists(HOSTSIM_SO) and all(os.path.getmtime(HOSTSIM_SO) >= os.path.getmtime(d) for d in deps):
         return
     os.makedirs(os.path.dirname(HOSTSIM_SO), exist_ok=True)
@@ -213,6 +213,10 @@ def sim_lib():
         lib.hostsim_pipeline.restype = C.c_long
         lib.hostsim_pipeline.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(SimFrame), C.c_long,
                                          C.POINTER(C.c_uint64), C.c_uint32]
+        lib.hostsim_pipeline2.restype = C.c_long
+        lib.hostsim_pipeline2.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(SimFrame), C.c_long,
+                                          C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32]
+        lib.hostsim_set_noff.argtypes = [C.c_int]
         _sim = lib
     return _sim
 
@@ -245,6 +249,23 @@ def sim_pipeline(mag, trigger_blocks, rate=10000000, enabled=0xF, cap=65536, gro
     assert 0 <= n <= cap
     frames = [frame_tuple(f.tech, f.type, f.flags, f.phase, f.rate, f.start, f.end, bytes(f.data[:f.len])) for f in buf[:n]]
     st = dict(lanes=stats[0], live=stats[1], rounds=stats[2], runs=stats[3], work=stats[4], active_blocks=stats[5])
+    return frames, st
+
+
+def sim_pipeline2(mag, trigger_blocks, rate=10000000, enabled=0xF, cap=65536, group=0, exact_int=False, noff=False):
+    """round-2 pipeline on the host (front pass -> feature pool -> warp lanes, nfc_wlane.h); group=0: one lane per stream"""
+    lib = sim_lib()
+    mag = np.ascontiguousarray(mag, dtype=np.float32)
+    flags = np.ascontiguousarray(trigger_blocks, dtype=np.uint8).copy()
+    buf = (SimFrame * cap)()
+    stats = (C.c_uint64 * 8)()
+    lib.hostsim_set_noff(1 if noff else 0)
+    n = lib.hostsim_pipeline2(mag.ctypes.data, mag.size, rate, enabled, flags.ctypes.data, flags.size, buf, cap, stats, group, 1 if exact_int else 0)
+    lib.hostsim_set_noff(0)
+    assert 0 <= n <= cap
+    frames = [frame_tuple(f.tech, f.type, f.flags, f.phase, f.rate, f.start, f.end, bytes(f.data[:f.len])) for f in buf[:n]]
+    st = dict(lanes=stats[0], live=stats[1], rounds=stats[2], runs=stats[3], work=stats[4], active_blocks=stats[5], segments=stats[6],
+              feature_samples=stats[7])
     return frames, st
 
 
