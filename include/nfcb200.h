@@ -96,11 +96,14 @@ typedef struct nfcb200_stats
    uint64_t kernel_launches;  /* kernels of this library launched by the call   */
    float ms_h2d;              /* host -> device copy of the samples (0 when the input is device resident) */
    float ms_screen;           /* K1 screening kernel                            */
-   float ms_segment;          /* segment construction                           */
+   float ms_segment;          /* segment construction + front pass              */
    float ms_lanes;            /* all lane + chain kernels                       */
    float ms_gather;           /* frame gather incl. device -> host copy         */
    float ms_total;            /* whole call, device events                      */
    float ms_wall;             /* whole call, host clock                         */
+   float ms_front;            /* front pass (part of ms_segment .. ms_lanes: own event pair) */
+   float reserved0;
+   uint64_t feature_samples;  /* samples the front pass wrote to the feature pool */
 } nfcb200_stats;
 
 void nfcb200_config_default(nfcb200_config *cfg);

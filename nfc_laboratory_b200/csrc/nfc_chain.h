@@ -48,7 +48,7 @@ struct LaneRec
    u32 lcWritten, lcLive, fZeroed, fThrWritten, fThrRead;
    u32 fInc0[2];
    float fThrSync[2];
-   u32 pad;
+   u32 seg0;       // index of the lane's first segment in the segment table (nfc_wlane.h)
    Carry in;       // carry the last run started from
    Carry out;      // canonical carry the last run retired with
 };

@@ -16,6 +16,7 @@
 #define NFCB200_DECODE_CUH
 
 #include "nfc_screen.cuh"
+#include "nfc_wlane.h"
 
 namespace nfcb200 {
 
@@ -178,6 +179,10 @@ struct SegmentConfig
    uint32_t group;      // segments per lane
    uint32_t *segTotal;  // total number of segments (statistics / group sizing)
    uint32_t shortHalo;  // lanes may use the short warm-up (nfc_chain.h lane_first_sample)
+   const uint32_t *segCounts;  // [n_streams] segments per stream (counts[] holds LANES per stream once grouped)
+   const uint32_t *segOffsets; // [n_streams] exclusive prefix of segCounts
+   SegRec *segs;               // segment table, ordered by (stream, time)
+   unsigned long long *featTotal; // feature samples allocated so far (every segment takes end - first)
 };
 
 // ---- block-granular part of the screen, parallel over all blocks ---------------------------------------------------------
@@ -271,7 +276,8 @@ __global__ void segment_group_kernel(SegmentConfig c)
    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
    if (s >= c.n_streams)
       return;
-   c.counts[s] = (c.counts[s] + c.group - 1) / c.group;
+   const uint32_t n = c.counts[s];
+   c.counts[s] = n ? (n - 1) / c.group + 1 : 0;
 }
 
 // one warp per stream: walk the start / active bits 32 blocks at a time and emit the lane records in time order
@@ -291,6 +297,15 @@ __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Par
    uint32_t inGroup = 0;     // segments already in the open lane
    uint32_t lastActive = 0;  // highest active block seen so far
    bool open = false;
+   const uint32_t segOff = c.segOffsets[s];
+   uint32_t segIdx = 0;      // next segment record of this stream
+
+   // close segment record i at sample e and give it its feature range
+   auto close_seg = [&](uint32_t i, uint32_t e) {
+      SegRec &S = c.segs[segOff + i];
+      S.end = e;
+      S.featOff = atomicAdd(c.featTotal, (unsigned long long) (e - S.first));
+   };
 
    for (uint32_t base = 0; base < c.n_blocks; base += 32)
    {
@@ -313,7 +328,20 @@ __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Par
             if (open)
             {
                uint32_t e = (lastActive + 1) * NFCB200_BLOCK;
-               c.lanes[off + laneIdx - 1].end = e > nsamples ? nsamples : e;
+               e = e > nsamples ? nsamples : e;
+               c.lanes[off + laneIdx - 1].end = e;
+               close_seg(segIdx - 1, e);
+            }
+
+            const uint32_t segFirst = lane_first_sample(flags, c.n_blocks, base + p, c.shortHalo != 0);
+            {
+               SegRec &S = c.segs[segOff + segIdx];
+               S.stream = s;
+               S.begin = (base + p) * NFCB200_BLOCK;
+               S.first = segFirst;
+               S.end = S.begin;
+               S.band = S.begin - segFirst > NFCB200_HALO_SHORT ? 1u : 0u;
+               segIdx++;
             }
 
             if (inGroup == 0 && laneIdx < nLanes)
@@ -322,7 +350,8 @@ __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Par
                l.stream = s;
                l.begin = (base + p) * NFCB200_BLOCK;
                l.end = l.begin;
-               l.first = lane_first_sample(flags, c.n_blocks, base + p, c.shortHalo != 0);
+               l.first = segFirst;
+               l.seg0 = segOff + segIdx - 1;
                l.stop = 0;
                l.lockedMask = 0;
                l.gen = 0;
@@ -347,7 +376,9 @@ __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Par
       if (open && laneIdx > 0)
       {
          uint32_t e = (lastActive + 1) * NFCB200_BLOCK;
-         c.lanes[off + laneIdx - 1].end = e > nsamples ? nsamples : e;
+         e = e > nsamples ? nsamples : e;
+         c.lanes[off + laneIdx - 1].end = e;
+         close_seg(segIdx - 1, e);
       }
 
       Carry spec, pon;
@@ -365,124 +396,169 @@ __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Par
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// lanes
+// front pass: one THREAD per segment, registers only (nfc_wlane.h front_pass) -> feature pool
 // ---------------------------------------------------------------------------------------------------------------------
-struct LaneConfig
+struct FrontConfig
+{
+   const void *samples;
+   uint64_t n_samples;
+   int sigtype;
+   SegRec *segs;
+   uint32_t n_segs;
+   float4 *pool;
+};
+
+#define FRONT_THREADS 64
+
+template <int SIG>
+__global__ void __launch_bounds__(FRONT_THREADS) front_kernel(FrontConfig c, const __grid_constant__ Params dP)
+{
+   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= c.n_segs)
+      return;
+
+   SegRec S = c.segs[i];
+   const uint64_t streamBase = (uint64_t) S.stream * c.n_samples;
+   float4 *dst = c.pool + S.featOff;
+
+   front_pass(
+      dP, S.first, S.end, [&](uint32_t p) { return load_sample(c.samples, SIG, streamBase + p); },
+      [&](uint32_t k, float w, float env, float dev, float avg) { __stcs(dst + k, make_float4(w, env, dev, avg)); }, S);
+
+   SegRec &O = c.segs[i];
+   O.tEnv = S.tEnv;
+   O.tAvg = S.tAvg;
+   O.tDev = S.tDev;
+   O.tF1 = S.tF1;
+   O.tPulse = S.tPulse;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// warp lanes: one WARP per lane, rings + lane state in shared memory (nfc_wlane.h WLane)
+// ---------------------------------------------------------------------------------------------------------------------
+struct WLaneConfig
 {
    const void *samples;
    uint64_t n_samples;
    int sigtype;
    const uint8_t *flags;
+   const float *bsum;
    uint32_t n_blocks;
    LaneRec *lanes;
    const uint32_t *queue;
    uint32_t queue_count;
    uint32_t *cursor;         // work-stealing cursor over the queue
-   float *scratch;           // [n_warps][NFCB200_SCRATCH_FLOATS][32]
-   uint8_t *sbuf;            // [n_warps * 32][512]
-   FramePool pool;
-   unsigned long long *work; // samples stepped (statistics)
+   const SegRec *segs;
+   uint32_t n_segs;
+   const float4 *pool;
+   FramePool frames;
+   unsigned long long *work; // samples consumed (statistics)
 };
 
-#define LANE_THREADS 128
-
-// TAPS: how the detectors fetch their ring taps (nfc_core.h); MINB: resident blocks per SM the register budget is cut for
-template <int TAPS, int MINB, bool CG>
-__global__ void __launch_bounds__(LANE_THREADS, MINB) lanes_kernel(LaneConfig c, const __grid_constant__ Params dP)
+struct DevWarp
 {
-   const uint32_t lane = threadIdx.x & 31;
-   const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   static __device__ __forceinline__ u32 lane() { return threadIdx.x & 31; }
+   static __device__ __forceinline__ u32 width() { return 32; }
+   static __device__ __forceinline__ void sync() { __syncwarp(); }
+   static __device__ __forceinline__ u32 min_u32(u32 v) { return __reduce_min_sync(0xffffffffu, v); }
+   static __device__ __forceinline__ u32 add_u32(u32 v) { return __reduce_add_sync(0xffffffffu, v); }
+   static __device__ __forceinline__ u32 or_u32(u32 v) { return __reduce_or_sync(0xffffffffu, v); }
+   static __device__ __forceinline__ float add_f32(float v)
+   {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1)
+         v += __shfl_xor_sync(0xffffffffu, v, d);
+      return v;
+   }
+};
 
-   float *rg = c.scratch + (size_t) wg * NFCB200_SCRATCH_FLOATS * 32 + lane;
-   u8 *sb = c.sbuf + ((size_t) wg * 32 + lane) * 512;
+struct DevSrc
+{
+   const void *samples;
+   int sigtype;
+   uint64_t streamBase;
+   const float4 *pool;
+   const uint8_t *flags; // this stream's block flags
+   const float *bsum;    // this stream's block sums
+   const SegRec *segs;
+   uint32_t nsegs;
 
-   // the per-sample state of every lane (nfc_core.h Front): 31 words per thread, odd stride
-   static_assert(sizeof(Front) % 4 == 0, "Front is copied word-wise");
-   __shared__ u32 hot[LANE_THREADS * (sizeof(Front) / 4)];
-   Front &F = *reinterpret_cast<Front *>(&hot[threadIdx.x * (sizeof(Front) / 4)]);
+   __device__ __forceinline__ float x(u32 pos) const { return load_sample(samples, sigtype, streamBase + pos); }
+   __device__ __forceinline__ Feat feat(unsigned long long i) const
+   {
+      const float4 v = __ldcs(pool + i);
+      Feat f;
+      f.w = v.x;
+      f.env = v.y;
+      f.dev = v.z;
+      f.avg = v.w;
+      return f;
+   }
+   __device__ __forceinline__ bool active(u32 pos) const { return (flags[pos >> 8] & SCR_ACTIVE) != 0; }
+   __device__ __forceinline__ float bmean(u32 b) const { return bsum[b] * (1.0f / NFCB200_BLOCK); }
+   __device__ __forceinline__ const SegRec &seg(u32 i) const { return segs[i]; }
+   __device__ __forceinline__ u32 nseg() const { return nsegs; }
+   __device__ __forceinline__ bool exact_int() const { return sigtype == SIG_MAG_S16; }
+};
+
+// shared memory of one warp lane: sample / integration / correlation rings, the lane state, the stream byte buffer, scratch
+struct WLaneSmem
+{
+   float rg[NFCB200_SCRATCH_FLOATS];
+   Lane L;
+   WShared sh;
+   u8 sb[512];
+};
+
+__global__ void __launch_bounds__(32) wlanes_kernel(WLaneConfig c, const __grid_constant__ Params dP)
+{
+   extern __shared__ __align__(16) unsigned char wl_smem[];
+   WLaneSmem &sm = *reinterpret_cast<WLaneSmem *>(wl_smem);
+   const u32 lane = threadIdx.x;
 
    for (;;)
    {
-      uint32_t base = 0;
+      u32 qi = 0;
       if (lane == 0)
-         base = atomicAdd(c.cursor, 32u);
-      base = __shfl_sync(0xffffffffu, base, 0);
-
-      if (base >= c.queue_count)
+         qi = atomicAdd(c.cursor, 1u);
+      qi = __shfl_sync(0xffffffffu, qi, 0);
+      if (qi >= c.queue_count)
          break;
 
-      const uint32_t qi = base + lane;
-      const bool have = qi < c.queue_count;
-
-      // correlation rings must read as zero until written (a fresh reference decoder); the sample rings are only read
-      // after 1024 steps (detector gate) and the integration ring only after clear_for_listen(), so they need no wipe
-      for (uint32_t i = NFCB200_OFF_CA; i < NFCB200_SCRATCH_FLOATS; i++)
-         rg[(size_t) i * 32] = 0.0f;
-
-      const uint32_t li = have ? c.queue[qi] : 0;
+      const u32 li = c.queue[qi];
       LaneRec &R = c.lanes[li];
 
-      Lane L;
-      if (!have)
-      {
-         u32 *raw = (u32 *) &L.fe;
-         for (u32 i = 0; i < sizeof(Front) / 4; i++)
-            raw[i] = 0;
-         for (u32 i = 0; i < sizeof(Carry) / 4; i++)
-            ((u32 *) &L.c)[i] = 0;
-      }
+      // correlation rings must read as zero until written (a fresh reference decoder); the sample rings are only read after
+      // the detector gate, the integration ring only after clear_for_listen()
+      for (u32 i = NFCB200_OFF_CA + lane; i < NFCB200_SCRATCH_FLOATS; i += 32)
+         sm.rg[i] = 0.0f;
+      __syncwarp();
+
       DeviceSink sink;
-      sink.pool = c.pool;
+      sink.pool = c.frames;
       sink.lane = li;
-      sink.gen = have ? R.gen + 1 : 0;
+      sink.gen = R.gen + 1;
       sink.seq = 0;
 
-      if (have)
-         lane_begin(L, dP, R.in, R.first, R.begin - R.first);
+      DevSrc src;
+      src.samples = c.samples;
+      src.sigtype = c.sigtype;
+      src.streamBase = (uint64_t) R.stream * c.n_samples;
+      src.pool = c.pool;
+      src.flags = c.flags + (size_t) R.stream * c.n_blocks;
+      src.bsum = c.bsum + (size_t) R.stream * c.n_blocks;
+      src.segs = c.segs;
+      src.nsegs = c.n_segs;
 
-      Machine<32, DeviceSink, TAPS, CG> M(dP, L, F, rg, sb, sink);
-      M.reload_front();
+      WLane<DevWarp, DeviceSink, DevSrc> WL(dP, sm.L, sm.rg, sm.sb, sink, sm.sh, src);
+      WL.run(R, R.seg0, (u32) c.n_samples);
 
-      const uint64_t streamBase = have ? (uint64_t) R.stream * c.n_samples : 0;
-      const uint8_t *flags = c.flags + (have ? (size_t) R.stream * c.n_blocks : 0);
-      const uint32_t end = have ? R.end : 0;
-      const uint32_t n = (uint32_t) c.n_samples;
-
-      uint32_t pos = have ? R.first : 0;
-      uint32_t stepped = 0;
-      bool running = have;
-
-      // the raw sample of the next step is requested one step ahead: every lane walks its own stream, so a warp touches 32
-      // different lines and some lane misses the cache on almost every step
-      float2 pend = make_float2(0.0f, 0.0f);
-      uint32_t pendPos = 0xFFFFFFFFu;
-      auto load = [&](uint32_t p) {
-         const float2 raw = p == pendPos ? pend : load_raw(c.samples, c.sigtype, streamBase + p);
-         if (p + 1 < n)
-         {
-            pend = load_raw(c.samples, c.sigtype, streamBase + p + 1);
-            pendPos = p + 1;
-         }
-         return mag_from_raw(c.sigtype, raw);
-      };
-      auto active = [&](uint32_t p) { return (flags[p >> 8] & SCR_ACTIVE) != 0; };
-      auto zero = [&]() {
-         for (uint32_t i = NFCB200_OFF_CA; i < NFCB200_SCRATCH_FLOATS; i++)
-            rg[(size_t) i * 32] = 0.0f;
-      };
-
-      // warp-synchronous stepping: kw is the same in all lanes, so is every ring slot label (k + kbase == kw + 1)
-      for (uint32_t kw = 0; __any_sync(0xffffffffu, running); kw++)
+      if (lane == 0)
       {
-         if (running)
-            running = lane_iterate(M, L, dP, pos, end, n, kw, stepped, load, active, zero);
+         lane_record(R, sm.L, sm.sh.pos, sink.gen, sink.seq);
+         atomicAdd(c.work, (unsigned long long) sm.sh.stepped);
       }
-
-      if (have)
-      {
-         lane_record(R, L, pos, sink.gen, sink.seq);
-         atomicAdd(c.work, (unsigned long long) stepped);
-      }
+      __syncwarp();
    }
 }
 
@@ -499,28 +575,8 @@ struct ChainConfig
    uint32_t *queue_count;
 };
 
-__global__ void chain_kernel(ChainConfig c, const __grid_constant__ Params dP)
-{
-   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-   if (s >= c.n_streams)
-      return;
-
-   uint32_t off = c.offsets[s];
-   uint32_t n = c.counts[s];
-
-   if (!chain_walk(c.lanes + off, n, dP))
-      return;
-
-   for (uint32_t j = 0; j < n; j++)
-   {
-      LaneRec &L = c.lanes[off + j];
-      if (L.dirty && !L.dead)
-         c.queue[atomicAdd(c.queue_count, 1u)] = off + j;
-   }
-}
-
 /*
- * The same walk, one WARP per stream: the sequential part is the loop over the lanes of the stream, but everything done
+ * chain_walk() (nfc_chain.h), one WARP per stream: the sequential part is the loop over the lanes of the stream, but everything done
  * per lane is word-parallel -- 246 carry words compared (word_observed_equal) and composed (compose_word) -- and the lane
  * records are read with coalesced loads instead of one thread chasing 2 kB per lane.  The true carry lives in shared
  * memory.  Control flow is uniform across the warp (every thread evaluates the same scalar fields); lane 0 writes the
@@ -666,15 +722,6 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_warp_kernel(ChainConfi
       if (L.dirty && !L.dead)
          c.queue[atomicAdd(c.queue_count, 1u)] = off + j;
    }
-}
-
-// length of every lane's own region + halo (the host orders the first-round queue by it: lanes of similar length share a
-// warp, long lanes start first)
-__global__ void lane_length_kernel(const LaneRec *lanes, uint32_t n, uint32_t *length)
-{
-   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n)
-      length[i] = lanes[i].end - lanes[i].first;
 }
 
 // (generation << 1 | dead) per lane, plus the stream of the lane: what the host needs to gather frames

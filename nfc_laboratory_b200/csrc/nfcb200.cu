@@ -136,6 +136,7 @@ struct Counters
    unsigned long long live;
    u32 segTotal;
    u32 pad;
+   unsigned long long featTotal;
 };
 
 // host-side milestones of a call, printed when NFCB200_TRACE is set (debug aid)
@@ -166,18 +167,14 @@ struct nfcb200_handle
    cudaStream_t stream = nullptr;
    cudaStream_t copyStream = nullptr;
    cudaEvent_t copied[2] = {};
-   cudaEvent_t ev[8] = {};
+   cudaEvent_t ev[12] = {};
 
-   int laneTaps = 2;   // lanes_kernel variant: ring tap fetch mode (NFCB200_LANE_TAPS overrides, development knob)
-   int laneBlocks = 4; // resident lane blocks per SM (NFCB200_LANE_BLOCKS overrides)
-   int screenDb = 0;   // NFCB200_SCREEN_DB=1: K1 with double-buffered prefix sums (one CTA barrier less per tile)
-   int chainWarp = 1;  // one warp per stream walks the carry chain word-parallel (chain_warp_kernel); NFCB200_CHAIN_WARP=0: scalar walk
-   int shortHalo = 1;  // NFCB200_HALO_SHORT=0 forces the long warm-up for every lane (measurement knob)
-   int laneCg = 0;     // ring accesses bypass L1 (NFCB200_LANE_CG overrides; measured neutral, profiles/)
+   int wlanesPerSm = 7; // resident warp lanes per SM (shared memory: sizeof(WLaneSmem) each)
+   int shortHalo = 1;   // NFCB200_HALO_SHORT=0 forces the long warm-up for every segment (measurement knob)
 
    HostBuf hRecs, hExt, hMeta, hStreamOf; // gather staging
 
-   DevBuf samples, flags, bsum, counts, offsets, lanes, queue, scratch, sbuf, pool, ext, meta, streamOf, counters;
+   DevBuf samples, flags, bsum, counts, offsets, segCounts, segOffsets, segs, feats, lanes, queue, pool, ext, meta, streamOf, counters;
    nfcb200_stats stats;
 
    // last batch geometry (for the flag tap)
@@ -222,55 +219,46 @@ static int setup_params(nfcb200_handle *h, u32 sampleRate)
    return 0;
 }
 
-// K2 launch: tap fetch mode x resident blocks per SM (register budget) x ring cache policy, chosen at create time
-static void launch_lanes(const nfcb200_handle *h, const LaneConfig &lc, u32 blocks, cudaStream_t st)
-{
-#define NFCB200_LANES(T, B, G) lanes_kernel<T, B, G><<<blocks, LANE_THREADS, 0, st>>>(lc, h->P)
-   const int b = h->laneBlocks;
-   if (h->laneTaps == 0)
-   {
-      if (h->laneCg) { if (b >= 6) NFCB200_LANES(0, 6, true); else NFCB200_LANES(0, 4, true); }
-      else NFCB200_LANES(0, 4, false);
-   }
-   else if (h->laneCg)
-   {
-      if (b >= 8) NFCB200_LANES(2, 8, true); else if (b >= 6) NFCB200_LANES(2, 6, true); else NFCB200_LANES(2, 4, true);
-   }
-   else
-   {
-      if (b >= 6) NFCB200_LANES(2, 6, false); else NFCB200_LANES(2, 4, false);
-   }
-#undef NFCB200_LANES
-}
-
-// K1 launch: one instantiation per sample format (x double-buffered prefix variant), persistent grid of 2 CTAs per SM
-template <bool DB>
-static void launch_screen_variant(const ScreenConfig &sc, uint32_t items, u32 grid, cudaStream_t st)
-{
-   switch (sc.sigtype)
-   {
-      case SIG_IQ_F32:
-         screen_kernel<SIG_IQ_F32, DB><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
-         break;
-      case SIG_MAG_F32:
-         screen_kernel<SIG_MAG_F32, DB><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
-         break;
-      case SIG_MAG_S16:
-         screen_kernel<SIG_MAG_S16, DB><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
-         break;
-      default:
-         screen_kernel<SIG_IQ_S16, DB><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
-         break;
-   }
-}
-
+// K1 launch: one instantiation per sample format, persistent grid of 2 CTAs per SM
 static void launch_screen(const nfcb200_handle *h, const ScreenConfig &sc, uint32_t items, cudaStream_t st)
 {
    const u32 grid = std::min<u32>(items, (u32) h->smCount * 2);
-   if (h->screenDb)
-      launch_screen_variant<true>(sc, items, grid, st);
-   else
-      launch_screen_variant<false>(sc, items, grid, st);
+   switch (sc.sigtype)
+   {
+      case SIG_IQ_F32:
+         screen_kernel<SIG_IQ_F32, false><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
+         break;
+      case SIG_MAG_F32:
+         screen_kernel<SIG_MAG_F32, false><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
+         break;
+      case SIG_MAG_S16:
+         screen_kernel<SIG_MAG_S16, false><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
+         break;
+      default:
+         screen_kernel<SIG_IQ_S16, false><<<grid, SCR_THREADS, sizeof(ScreenSmem), st>>>(sc, items);
+         break;
+   }
+}
+
+// front pass: one instantiation per sample format
+static void launch_front(const FrontConfig &fc, const Params &P, cudaStream_t st)
+{
+   const u32 grid = (fc.n_segs + FRONT_THREADS - 1) / FRONT_THREADS;
+   switch (fc.sigtype)
+   {
+      case SIG_IQ_F32:
+         front_kernel<SIG_IQ_F32><<<grid, FRONT_THREADS, 0, st>>>(fc, P);
+         break;
+      case SIG_MAG_F32:
+         front_kernel<SIG_MAG_F32><<<grid, FRONT_THREADS, 0, st>>>(fc, P);
+         break;
+      case SIG_MAG_S16:
+         front_kernel<SIG_MAG_S16><<<grid, FRONT_THREADS, 0, st>>>(fc, P);
+         break;
+      default:
+         front_kernel<SIG_IQ_S16><<<grid, FRONT_THREADS, 0, st>>>(fc, P);
+         break;
+   }
 }
 
 static void fill_screen_config(const nfcb200_handle *h, ScreenConfig &sc)
@@ -392,31 +380,22 @@ int nfcb200_create(const nfcb200_config *cfg, nfcb200_handle **out)
    for (auto &ev: h->ev)
       cudaEventCreate(&ev);
 
-   if (const char *e = getenv("NFCB200_LANE_TAPS"))
-      h->laneTaps = std::max(0, std::min(2, atoi(e)));
-   if (const char *e = getenv("NFCB200_LANE_BLOCKS"))
-      h->laneBlocks = atoi(e) >= 8 ? 8 : atoi(e) >= 6 ? 6 : 4;
-   if (const char *e = getenv("NFCB200_SCREEN_DB"))
-      h->screenDb = atoi(e) ? 1 : 0;
-   if (const char *e = getenv("NFCB200_CHAIN_WARP"))
-      h->chainWarp = atoi(e) ? 1 : 0;
    if (const char *e = getenv("NFCB200_HALO_SHORT"))
       h->shortHalo = atoi(e) ? 1 : 0;
-   if (const char *e = getenv("NFCB200_LANE_CG"))
-      h->laneCg = atoi(e) ? 1 : 0;
-   if (h->laneTaps == 1)
-      h->laneTaps = 2;
 
 #define NFCB200_SMEM_ATTR(K) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem))
    NFCB200_SMEM_ATTR((screen_kernel<SIG_IQ_F32, false>));
    NFCB200_SMEM_ATTR((screen_kernel<SIG_MAG_F32, false>));
    NFCB200_SMEM_ATTR((screen_kernel<SIG_MAG_S16, false>));
    NFCB200_SMEM_ATTR((screen_kernel<SIG_IQ_S16, false>));
-   NFCB200_SMEM_ATTR((screen_kernel<SIG_IQ_F32, true>));
-   NFCB200_SMEM_ATTR((screen_kernel<SIG_MAG_F32, true>));
-   NFCB200_SMEM_ATTR((screen_kernel<SIG_MAG_S16, true>));
-   NFCB200_SMEM_ATTR((screen_kernel<SIG_IQ_S16, true>));
 #undef NFCB200_SMEM_ATTR
+   cudaFuncSetAttribute(wlanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(WLaneSmem));
+   {
+      // resident warp lanes per SM: what the shared memory of one SM holds
+      int perSm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, wlanes_kernel, 32, sizeof(WLaneSmem)) == cudaSuccess && perSm > 0)
+         h->wlanesPerSm = perSm;
+   }
 
    *out = h;
    return 0;
@@ -428,7 +407,7 @@ void nfcb200_destroy(nfcb200_handle *h)
       return;
    cudaSetDevice(h->device);
    cudaStreamSynchronize(h->stream);
-   DevBuf *bufs[] = {&h->samples, &h->flags, &h->bsum, &h->counts, &h->offsets, &h->lanes, &h->queue, &h->scratch, &h->sbuf, &h->pool, &h->ext, &h->meta,
+   DevBuf *bufs[] = {&h->samples, &h->flags, &h->bsum, &h->counts, &h->offsets, &h->lanes, &h->queue, &h->segCounts, &h->segOffsets, &h->segs, &h->feats, &h->pool, &h->ext, &h->meta,
                      &h->streamOf, &h->counters, &h->sState, &h->sScratch, &h->sSbuf, &h->sSamples, &h->sFlags, &h->sBsum, &h->sCounts};
    for (DevBuf *b: bufs)
       b->release();
@@ -546,6 +525,8 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       rc = rc ? rc : h->bsum.reserve((size_t) n_streams * n_blocks * sizeof(float));
       rc = rc ? rc : h->counts.reserve((size_t) n_streams * sizeof(u32));
       rc = rc ? rc : h->offsets.reserve((size_t) n_streams * sizeof(u32));
+      rc = rc ? rc : h->segCounts.reserve((size_t) n_streams * sizeof(u32));
+      rc = rc ? rc : h->segOffsets.reserve((size_t) n_streams * sizeof(u32));
       rc = rc ? rc : h->counters.reserve(sizeof(Counters));
       if (rc)
          return rc;
@@ -609,43 +590,51 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       CUDA_TRY(cudaGetLastError());
    }
 
-   // segments per lane: enough lanes to fill the machine a few times over, no more (every lane pays a warm-up halo and
-   // longer lanes keep more of the carry chain inside one sequential run)
+   // Lanes.  On float input ONE lane decodes the whole stream: the detectors' running sums carry their rounding history
+   // (NfcA.cpp:246-250), which only a run over the whole capture reproduces bit for bit (nfc_wlane.h).  16-bit mono input
+   // adds exactly whatever the history, so a stream may be cut into several lanes (cold starts + carry chain): as many as
+   // fill the machine a few times over, no more (every lane boundary costs a speculation).
    u32 segTotal = 0;
    CUDA_TRY(cudaMemcpyAsync(&segTotal, &dC->segTotal, sizeof(u32), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaMemcpyAsync(h->segCounts.ptr, h->counts.ptr, (size_t) n_streams * sizeof(u32), cudaMemcpyDeviceToDevice, st));
    CUDA_TRY(cudaStreamSynchronize(st));
    {
-      const uint64_t residentLanes = (uint64_t) h->smCount * (uint64_t) h->laneBlocks * (LANE_THREADS / 32) * 32;
-      const uint64_t target = residentLanes * 2;
-      u32 group = h->cfg.segments_per_lane ? h->cfg.segments_per_lane : (u32) std::max<uint64_t>(1, segTotal / std::max<uint64_t>(1, target));
-      sg.group = std::min<u32>(group, 64);
-      if (sg.group > 1)
-      {
-         segment_group_kernel<<<sgrid, 64, 0, st>>>(sg);
-         launches++;
-         CUDA_TRY(cudaGetLastError());
-      }
+      const uint64_t resident = (uint64_t) h->smCount * (uint64_t) h->wlanesPerSm;
+      u32 group = 0xFFFFFFFFu; // one lane per stream
+      if (h->cfg.segments_per_lane)
+         group = h->cfg.segments_per_lane;
+      else if (sigtype == SIG_MAG_S16 && (uint64_t) n_streams < resident * 2)
+         group = (u32) std::max<uint64_t>(1, segTotal / (resident * 2));
+      sg.group = group;
+      segment_group_kernel<<<sgrid, 64, 0, st>>>(sg);
+      launches++;
+      CUDA_TRY(cudaGetLastError());
    }
    S.segments = segTotal;
    tr.mark("screen + segments");
 
-   std::vector<u32> counts(n_streams), offsets(n_streams);
+   std::vector<u32> counts(n_streams), offsets(n_streams), segCounts(n_streams), segOffsets(n_streams);
    CUDA_TRY(cudaMemcpyAsync(counts.data(), h->counts.ptr, n_streams * sizeof(u32), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaMemcpyAsync(segCounts.data(), h->segCounts.ptr, n_streams * sizeof(u32), cudaMemcpyDeviceToHost, st));
    CUDA_TRY(cudaStreamSynchronize(st));
 
-   uint64_t nLanes64 = 0;
+   uint64_t nLanes64 = 0, nSegs64 = 0;
    for (u32 s = 0; s < n_streams; s++)
    {
       offsets[s] = (u32) nLanes64;
       nLanes64 += counts[s];
+      segOffsets[s] = (u32) nSegs64;
+      nSegs64 += segCounts[s];
    }
-   if (nLanes64 >= 0x7FFFFFFFull)
-      return fail(NFCB200_ERR_CAPACITY, "too many segments (%llu)", (unsigned long long) nLanes64);
+   if (nLanes64 >= 0x7FFFFFFFull || nSegs64 >= 0x7FFFFFFFull)
+      return fail(NFCB200_ERR_CAPACITY, "too many segments (%llu)", (unsigned long long) nSegs64);
    const u32 nLanes = (u32) nLanes64;
+   const u32 nSegs = (u32) nSegs64;
    S.lanes = nLanes;   // this chunk; accumulated with the previous chunks at the end
 
    {
       int rc = h->lanes.reserve((size_t) nLanes * sizeof(LaneRec));
+      rc = rc ? rc : h->segs.reserve((size_t) std::max<u32>(nSegs, 1) * sizeof(SegRec));
       rc = rc ? rc : h->queue.reserve((size_t) nLanes * sizeof(u32));
       rc = rc ? rc : h->meta.reserve((size_t) nLanes * sizeof(u32));
       rc = rc ? rc : h->streamOf.reserve((size_t) nLanes * sizeof(u32));
@@ -654,34 +643,43 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    }
 
    CUDA_TRY(cudaMemcpyAsync(h->offsets.ptr, offsets.data(), n_streams * sizeof(u32), cudaMemcpyHostToDevice, st));
+   CUDA_TRY(cudaMemcpyAsync(h->segOffsets.ptr, segOffsets.data(), n_streams * sizeof(u32), cudaMemcpyHostToDevice, st));
    sg.lanes = h->lanes.as<LaneRec>();
    sg.queue = h->queue.as<u32>();
+   sg.segCounts = h->segCounts.as<u32>();
+   sg.segOffsets = h->segOffsets.as<u32>();
+   sg.segs = h->segs.as<SegRec>();
+   sg.featTotal = &dC->featTotal;
    segment_fill_kernel<<<n_streams, 32, 0, st>>>(sg, h->P);
    launches++;
    CUDA_TRY(cudaGetLastError());
 
-   // first-round queue ordered by decreasing lane length (counting sort on the host: the lengths are 4 bytes per lane)
-   if (nLanes > 64)
+   // ---- front pass: the sequential float recurrences of nextSample, one thread per segment -> feature pool ----------
+   unsigned long long featTotal = 0;
+   CUDA_TRY(cudaMemcpyAsync(&featTotal, &dC->featTotal, sizeof(featTotal), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaStreamSynchronize(st));
    {
-      lane_length_kernel<<<(nLanes + 255) / 256, 256, 0, st>>>(h->lanes.as<LaneRec>(), nLanes, h->meta.as<u32>());
+      int rc = h->feats.reserve((size_t) std::max<unsigned long long>(featTotal, 1) * sizeof(float4));
+      if (rc)
+         return rc;
+   }
+   S.feature_samples = featTotal;
+   cudaEventRecord(h->ev[8], st);
+   if (nSegs)
+   {
+      FrontConfig fc;
+      fc.samples = dSamples;
+      fc.n_samples = n_samples;
+      fc.sigtype = sigtype;
+      fc.segs = h->segs.as<SegRec>();
+      fc.n_segs = nSegs;
+      fc.pool = h->feats.as<float4>();
+      launch_front(fc, h->P, st);
       launches++;
-      std::vector<u32> len(nLanes), order(nLanes);
-      CUDA_TRY(cudaMemcpyAsync(len.data(), h->meta.ptr, (size_t) nLanes * sizeof(u32), cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaStreamSynchronize(st));
-      const u32 shift = 8, buckets = 1u << 16;
-      std::vector<u32> hist(buckets + 1, 0);
-      auto key = [&](u32 v) { u32 k = v >> shift; return k >= buckets ? 0u : buckets - 1 - k; }; // descending
-      for (u32 i = 0; i < nLanes; i++)
-         hist[key(len[i]) + 1]++;
-      for (u32 b = 0; b < buckets; b++)
-         hist[b + 1] += hist[b];
-      for (u32 i = 0; i < nLanes; i++)
-         order[hist[key(len[i])]++] = i;
-      CUDA_TRY(cudaMemcpyAsync(h->queue.ptr, order.data(), (size_t) nLanes * sizeof(u32), cudaMemcpyHostToDevice, st));
-      CUDA_TRY(cudaStreamSynchronize(st));
+      CUDA_TRY(cudaGetLastError());
    }
 
-   tr.mark("lane fill + order");
+   tr.mark("lane fill + front pass");
    cudaEventRecord(h->ev[3], st);
 
    // ---- frame pool ----------------------------------------------------------------------------------------------------
@@ -703,20 +701,23 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    pool.extCount = &dC->extCount;
 
    // ---- lanes + chain, to the fixed point -----------------------------------------------------------------------------
-   const u32 warpsPerBlock = LANE_THREADS / 32;
-   const u32 maxWarps = (u32) h->smCount * (u32) h->laneBlocks * warpsPerBlock; // resident warps: the kernel is persistent
+   const u32 maxWarps = (u32) h->smCount * (u32) h->wlanesPerSm; // resident warp lanes: the kernel is persistent
 
-   LaneConfig lc;
+   WLaneConfig lc;
    memset(&lc, 0, sizeof(lc));
    lc.samples = dSamples;
    lc.n_samples = n_samples;
    lc.sigtype = sigtype;
    lc.flags = h->flags.as<uint8_t>();
+   lc.bsum = h->bsum.as<float>();
    lc.n_blocks = n_blocks;
    lc.lanes = h->lanes.as<LaneRec>();
    lc.queue = h->queue.as<u32>();
    lc.cursor = &dC->cursor;
-   lc.pool = pool;
+   lc.segs = h->segs.as<SegRec>();
+   lc.n_segs = nSegs;
+   lc.pool = h->feats.as<float4>();
+   lc.frames = pool;
    lc.work = &dC->work;
 
    ChainConfig cc;
@@ -736,23 +737,11 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       if (rounds >= maxRounds)
          return fail(NFCB200_ERR_CAPACITY, "carry chain did not converge in %u rounds", maxRounds);
 
-      u32 warps = std::min(maxWarps, (queueCount + 31) / 32);
-      u32 blocks = (warps + warpsPerBlock - 1) / warpsPerBlock;
-      warps = blocks * warpsPerBlock;
-
-      {
-         int rc = h->scratch.reserve((size_t) warps * NFCB200_SCRATCH_FLOATS * 32 * sizeof(float));
-         rc = rc ? rc : h->sbuf.reserve((size_t) warps * 32 * 512);
-         if (rc)
-            return rc;
-      }
-
-      lc.scratch = h->scratch.as<float>();
-      lc.sbuf = h->sbuf.as<uint8_t>();
+      const u32 blocks = std::min(maxWarps, queueCount);
       lc.queue_count = queueCount;
 
       CUDA_TRY(cudaMemsetAsync(&dC->cursor, 0, sizeof(u32), st));
-      launch_lanes(h, lc, blocks, st);
+      wlanes_kernel<<<blocks, 32, sizeof(WLaneSmem), st>>>(lc, h->P);
       launches++;
       CUDA_TRY(cudaGetLastError());
 
@@ -760,10 +749,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       rounds++;
 
       CUDA_TRY(cudaMemsetAsync(&dC->queueCount, 0, sizeof(u32), st));
-      if (h->chainWarp)
-         chain_warp_kernel<<<(n_streams + CHAIN_WARPS - 1) / CHAIN_WARPS, CHAIN_WARPS * 32, 0, st>>>(cc, h->P);
-      else
-         chain_kernel<<<sgrid, 64, 0, st>>>(cc, h->P);
+      chain_warp_kernel<<<(n_streams + CHAIN_WARPS - 1) / CHAIN_WARPS, CHAIN_WARPS * 32, 0, st>>>(cc, h->P);
       launches++;
       CUDA_TRY(cudaGetLastError());
 
@@ -888,7 +874,8 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    h->lastBlocks = n_blocks;
 
    // accumulate the statistics over the chunks of one call
-   float msScreen = 0, msSeg = 0, msLanes = 0, msGather = 0;
+   float msScreen = 0, msSeg = 0, msLanes = 0, msGather = 0, msFront = 0;
+   cudaEventElapsedTime(&msFront, h->ev[8], h->ev[3]);
    cudaEventElapsedTime(&msScreen, h->ev[1], h->ev[2]);
    cudaEventElapsedTime(&msSeg, h->ev[2], h->ev[3]);
    cudaEventElapsedTime(&msLanes, h->ev[3], h->ev[4]);
@@ -897,6 +884,8 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    S.ms_segment = prev.ms_segment + msSeg;
    S.ms_lanes = prev.ms_lanes + msLanes;
    S.ms_gather = prev.ms_gather + msGather;
+   S.ms_front = prev.ms_front + msFront;
+   S.feature_samples += prev.feature_samples;
    S.segments += prev.segments;
    S.lanes += prev.lanes;
    S.live_lanes += prev.live_lanes;
