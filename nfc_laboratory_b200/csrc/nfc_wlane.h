@@ -108,6 +108,20 @@ struct HostWarp
    static NFC_HD u32 add_u32(u32 v) { return v; }
    static NFC_HD float add_f32(float v) { return v; }
    static NFC_HD u32 or_u32(u32 v) { return v; }
+
+   // the detectors' running sums over the cnt samples after the current step: the reference's own recurrence
+   template <class WL>
+   static NFC_HD void sum_chains(WL &wl, u32 cnt)
+   {
+      wl.sum_chains_seq(cnt);
+   }
+
+   // an idle stretch [pos, target) with the sums alone
+   template <class WL>
+   static NFC_HD void walk(WL &wl, u32 pos, u32 target)
+   {
+      wl.walk_generic(pos, target);
+   }
 };
 
 // per-warp scratch next to the rings (shared memory on the device)
@@ -116,13 +130,13 @@ struct WShared
    float lin[6][40]; // running sums of the current fast-forward span, entry a = after a samples (a = 1 .. 32)
    float cavg[32];   // carrier average of the chunk's samples
    u32 act;          // control: what the warp does next (WLANE_*)
-   u32 pos, n, mode, si, j, stepped;
-   u32 jumpTa, jumpGs, jumpT, jumpG, jumpBegin, jumpSeg;
+   u32 pos, n, mode, si, j, stepped, blockActive;
+   u32 jumpCls, jumpTa, jumpGs, jumpT, jumpG, jumpB, jumpSeg;
    float delta[6];
 };
 
-enum { WLANE_DONE = 0, WLANE_CHUNK = 1, WLANE_JUMP = 2 };
-enum { WMODE_FEAT = 0, WMODE_SCAL = 1, WMODE_WALK = 2 };
+enum { WLANE_DONE = 0, WLANE_CHUNK = 1, WLANE_JUMP = 2, WLANE_WALK = 3 };
+enum { WMODE_FEAT = 0, WMODE_SCAL = 1 };
 
 // the six running-sum chains: NFC-A 106 / 212 / 424, NFC-F 212 / 424, NFC-V
 struct SumChain
@@ -143,27 +157,16 @@ NFC_HD SumChain sum_chain(const Params &P, u32 d)
    return c;
 }
 
-NFC_HD int float_exponent(float v)
+// (ph + m) mod p for ph < p without a division (m is at most a few periods)
+NFC_HD u32 wrap_add(u32 ph, u32 m, u32 p)
 {
-   union
-   {
-      float f;
-      u32 u;
-   } c;
-   c.f = v;
-   return (int) ((c.u >> 23) & 0xff) - 127;
+   ph += m;
+   while (ph >= p)
+      ph -= p;
+   return ph;
 }
 
-NFC_HD float pow2f(int e)
-{
-   union
-   {
-      float f;
-      u32 u;
-   } c;
-   c.u = (u32) (e + 127) << 23;
-   return c.f;
-}
+#define NFCB200_LEAD (NFCB200_HALO_SHORT) /* a lane re-enters the features this many samples before the next active block */
 
 /*
  * SRC (per lane):  float x(u32 pos)            magnitude of sample pos (reference operation order)
@@ -187,7 +190,8 @@ struct WLane
    Mach M;
    bool noff; // self-check: every sample goes through the per-sample machine
 
-   NFC_HD WLane(const Params &p, Lane &l, float *r, u8 *s, SINK &k, WShared &w, const SRC &sr) : P(p), L(l), F(l.fe), rg(r), sh(w), src(sr), M(p, l, l.fe, r, s, k), noff(false)
+   NFC_HD WLane(const Params &p, Lane &l, float *r, u8 *s, SINK &k, WShared &w, const SRC &sr)
+      : P(p), L(l), F(l.fe), rg(r), sh(w), src(sr), M(p, l, l.fe, r, s, k), noff(false)
    {
    }
 
@@ -201,13 +205,21 @@ struct WLane
    // ------------------------------------------------------------------------------------------------------------------
    NFC_HD void fill_feat(u32 pos, u32 n, u32 k0, const SegRec &S)
    {
-      u32 closedCnt = 0, openCnt = 0;
+      u32 closedCnt = 0;
+      const bool quietBlock = sh.blockActive == 0;
 
       for (u32 i = W::lane(); i < n; i += W::width())
       {
          const u32 s = slot(k0 + 1 + i, 0);
          const float x = src.x(pos + i);
          const Feat f = src.feat(S.featOff + (pos + i - S.first));
+         // gate state for the retirement heuristic (Front::closed): the envelope before the sample is the previous feature
+         if (quietBlock)
+         {
+            const float envPrev = i ? src.feat(S.featOff + (pos + i - 1 - S.first)).env : rg[NFCB200_OFF_M + slot(k0, 0)];
+            if (!gate_open(fabsf(x - envPrev), envPrev))
+               closedCnt++;
+         }
          rg[NFCB200_OFF_X + s] = x;
          rg[NFCB200_OFF_W + s] = f.w;
          rg[NFCB200_OFF_D + s] = f.dev;
@@ -215,28 +227,16 @@ struct WLane
          sh.cavg[i] = f.avg;
       }
 
-      W::sync();
-
-      // gate state of the chunk's samples for the retirement heuristic (Front::closed): the envelope before a sample is
-      // the envelope feature of the previous one
-      for (u32 i = W::lane(); i < n; i += W::width())
-      {
-         const float x = rg[NFCB200_OFF_X + slot(k0 + 1 + i, 0)];
-         const float envPrev = rg[NFCB200_OFF_M + slot(k0 + i, 0)];
-         if (gate_open(fabsf(x - envPrev), envPrev))
-            openCnt++;
-         else
-            closedCnt++;
-      }
-
-      closedCnt = W::add_u32(closedCnt);
-      openCnt = W::add_u32(openCnt);
+      if (quietBlock)
+         closedCnt = W::add_u32(closedCnt);
 
       if (W::lane() == 0)
       {
-         u32 c = F.closed + closedCnt;
-         c = c > openCnt ? c - openCnt : 0;
-         F.closed = c > 4096 ? 4096 : c;
+         // the lane may only retire / skip ahead after two chunks of an inactive block with the envelope gate open throughout
+         if (!quietBlock || closedCnt)
+            F.closed = 64;
+         else
+            F.closed = F.closed >= 32 ? F.closed - 32 : 0;
       }
    }
 
@@ -247,9 +247,10 @@ struct WLane
    }
 
    // ------------------------------------------------------------------------------------------------------------------
-   // running sums of `cnt` samples following local step k (F.k): six sequential chains, results in sh.lin[d][1 .. cnt]
+   // running sums of `cnt` samples following local step F.k: results in sh.lin[d][1 .. cnt]
    // ------------------------------------------------------------------------------------------------------------------
-   NFC_HD void sum_chains(u32 cnt)
+   // the reference's recurrence, one chain per thread (all of them on the one thread of the host build)
+   NFC_HD void sum_chains_seq(u32 cnt)
    {
       for (u32 d = W::lane(); d < 6; d += W::width())
       {
@@ -277,8 +278,7 @@ struct WLane
       if (back < a)
          return sh.lin[d][a - back];
       // older than this span: still in the ring (the span's own values are committed afterwards)
-      u32 ph = (phase0 + a + c.p1 * 2 - back) % c.p1;
-      return rg[c.corr + ph];
+      return rg[c.corr + wrap_add(phase0, a + c.p1 - back, c.p1)];
    }
 
    NFC_HD u32 phase_of(u32 d) const
@@ -286,7 +286,21 @@ struct WLane
       return d < 3 ? F.cA[d] : (d < 5 ? F.cF[d - 3] : F.cV1);
    }
 
-   // commit m samples of a fast-forward span: rings, sums, clocks, ring phases
+   // clocks and ring phases after m more samples
+   NFC_HD void advance(u32 m)
+   {
+      F.k += m;
+      F.clk += m;
+      F.pulseFilter += m;
+      for (int r = 0; r < 3; r++)
+         F.cA[r] = wrap_add(F.cA[r], m % P.A[r].p1, P.A[r].p1);
+      for (int r = 0; r < 2; r++)
+         F.cF[r] = wrap_add(F.cF[r], m % P.F[r + 1].p1, P.F[r + 1].p1);
+      F.cV1 = wrap_add(F.cV1, m % P.V.p1, P.V.p1);
+      F.cV0 = wrap_add(F.cV0, m % P.V.p0, P.V.p0);
+   }
+
+   // commit m (<= 32) samples of a fast-forward span: rings, sums, clocks, ring phases
    NFC_HD void commit(u32 m, bool sums)
    {
       if (sums)
@@ -298,7 +312,7 @@ struct WLane
                continue;
             const u32 ph0 = phase_of(d);
             for (u32 a = 1 + W::lane(); a <= m; a += W::width())
-               rg[c.corr + (ph0 + a) % c.p1] = sh.lin[d][a];
+               rg[c.corr + wrap_add(ph0, a, c.p1)] = sh.lin[d][a];
          }
       }
 
@@ -317,11 +331,11 @@ struct WLane
          F.clk += m;
          F.pulseFilter += m;
          for (int r = 0; r < 3; r++)
-            F.cA[r] = (F.cA[r] + m) % P.A[r].p1;
+            F.cA[r] = wrap_add(F.cA[r], m, P.A[r].p1);
          for (int r = 0; r < 2; r++)
-            F.cF[r] = (F.cF[r] + m) % P.F[r + 1].p1;
-         F.cV1 = (F.cV1 + m) % P.V.p1;
-         F.cV0 = (F.cV0 + m) % P.V.p0;
+            F.cF[r] = wrap_add(F.cF[r], m, P.F[r + 1].p1);
+         F.cV1 = wrap_add(F.cV1, m, P.V.p1);
+         F.cV0 = wrap_add(F.cV0, m, P.V.p0);
       }
 
       W::sync();
@@ -376,7 +390,7 @@ struct WLane
 
       if (regime0 != 0)
       {
-         sum_chains(cut);
+         W::sum_chains(*this, cut);
          W::sync();
       }
 
@@ -463,12 +477,33 @@ struct WLane
       return m;
    }
 
-   // WALK: the idle stretch between two segments, sums only (no features exist there)
-   NFC_HD void walk_chunk(u32 n)
+   // an idle stretch [pos, target), sums alone: no features exist there and nothing else can move (the correlation
+   // rings are not maintained: the lane re-enters the features NFCB200_LEAD samples before the next active block and
+   // refills them before its detectors open)
+   NFC_HD void walk_generic(u32 pos, u32 target)
    {
-      sum_chains(n);
-      W::sync();
-      commit(n, true);
+      while (pos < target)
+      {
+         u32 n = target - pos;
+         if (n > 32)
+            n = 32;
+         fill_x(pos, n, F.k);
+         W::sync();
+         W::sum_chains(*this, n);
+         W::sync();
+         if (W::lane() == 0)
+         {
+            for (u32 d = 0; d < 6; d++)
+            {
+               const SumChain c = sum_chain(P, d);
+               if (P.enabled & c.tech)
+                  F.fi[c.fi] = sh.lin[d][n];
+            }
+            advance(n);
+         }
+         W::sync();
+         pos += n;
+      }
    }
 
    // ------------------------------------------------------------------------------------------------------------------
@@ -502,7 +537,7 @@ struct WLane
       return src.exact_int() ? 1 : 3;
    }
 
-   // change of the six window sums between ta and gs - 1 (every partial sum is exact under gap_class == 1)
+   // change of the six window sums between ta and gs - 1 (exact: gap_class == 1)
    NFC_HD void gap_delta(u32 ta, u32 gs)
    {
       for (u32 d = 0; d < 6; d++)
@@ -542,9 +577,17 @@ struct WLane
       sh.mode = WMODE_SCAL;
    }
 
+   NFC_HD void plain_chunk(u32 pos, u32 limit)
+   {
+      u32 n = 32 - (pos & 31);
+      if (n > limit - pos)
+         n = limit - pos;
+      sh.n = n;
+   }
+
    NFC_HD void control(const LaneRec &R, u32 nsamples)
    {
-      u32 pos = sh.pos;
+      const u32 pos = sh.pos;
 
       sh.act = WLANE_CHUNK;
 
@@ -554,111 +597,87 @@ struct WLane
          return;
       }
 
-      if (sh.mode == WMODE_WALK)
+      const bool inFeat = sh.mode == WMODE_FEAT && pos < src.seg(sh.si).end;
+      const bool active = src.active(pos);
+      sh.blockActive = active ? 1u : 0u;
+
+      // outside the active blocks a settled lane retires, or skips ahead to NFCB200_LEAD samples before the next active block
+      if ((pos & 31) == 0 && !active && F.lock == LOCK_NONE && F.busy == 0 && M.dormant())
       {
-         const SegRec &S = src.seg(sh.si);
-         if (pos >= S.first)
-            sh.mode = WMODE_FEAT;
+         u32 B = 0, ni = sh.si;
+         bool found = false;
+
+         if (inFeat)
+         {
+            const u32 segEnd = src.seg(sh.si).end;
+            for (u32 p = (pos | (NFCB200_BLOCK - 1)) + 1; p < segEnd && !found; p += NFCB200_BLOCK)
+               if (src.active(p))
+               {
+                  B = p;
+                  found = true;
+               }
+         }
          else
          {
-            u32 n = 32 - (pos & 31);
-            if (n > S.first - pos)
-               n = S.first - pos;
-            sh.n = n;
-            return;
+            if (pos >= R.end)
+            {
+               sh.act = WLANE_DONE;
+               return;
+            }
+
+            while (seg_of_lane(ni, R) && src.seg(ni).end <= pos)
+               ni++;
+
+            if (seg_of_lane(ni, R))
+            {
+               const SegRec &N = src.seg(ni);
+               if (N.begin > pos)
+               {
+                  B = N.begin;
+                  found = true;
+               }
+               else if (pos >= N.first + NFCB200_HALO_SHORT)
+               {
+                  // inside that segment's feature range: its features are exact once the front pass has converged (the same
+                  // contraction a lane start relies on), and they continue the lane's own rings without a seam
+                  sh.mode = WMODE_FEAT;
+                  sh.si = ni;
+                  plain_chunk(pos, N.end);
+                  return;
+               }
+            }
+         }
+
+         if (found && B >= NFCB200_LEAD + 512 && B - NFCB200_LEAD >= pos + 512)
+         {
+            const u32 T = B - NFCB200_LEAD, g = B - 512, gs = g - NFCB200_PREROLL;
+            const int cls = gap_class(pos - 1, gs);
+
+            if (cls != 0)
+            {
+               sh.act = cls == 3 ? WLANE_WALK : WLANE_JUMP;
+               sh.jumpCls = (u32) cls;
+               sh.jumpTa = pos - 1;
+               sh.jumpGs = gs;
+               sh.jumpT = T;
+               sh.jumpG = g;
+               sh.jumpB = B;
+               sh.jumpSeg = ni;
+               return;
+            }
          }
       }
 
-      const SegRec &S = src.seg(sh.si);
-
-      if (sh.mode == WMODE_FEAT && pos < S.end)
+      if (inFeat)
       {
-         u32 n = 32 - (pos & 31);
-         if (n > S.end - pos)
-            n = S.end - pos;
-         sh.n = n;
+         plain_chunk(pos, src.seg(sh.si).end);
          return;
       }
 
-      // past the feature range: retire, skip ahead, or go on with the scalar front end
-      if ((pos & 31) == 0 && !src.active(pos) && M.dormant())
-      {
-         if (pos >= R.end)
-         {
-            sh.act = WLANE_DONE;
-            return;
-         }
-
-         // the next segment with samples left (a lane that ran past its range may already be inside a later one)
-         u32 ni = sh.si;
-         while (seg_of_lane(ni, R) && src.seg(ni).end <= pos)
-            ni++;
-
-         if (seg_of_lane(ni, R) && src.seg(ni).first < pos)
-         {
-            // inside that segment's feature range: its features are exact once the front pass has converged (the same
-            // contraction a lane start relies on), and they continue the lane's own rings without a seam
-            const SegRec &N = src.seg(ni);
-            if (pos >= N.first + NFCB200_HALO_SHORT)
-            {
-               sh.mode = WMODE_FEAT;
-               sh.si = ni;
-               u32 n = 32;
-               if (n > N.end - pos)
-                  n = N.end - pos;
-               sh.n = n;
-               return;
-            }
-         }
-         else if (seg_of_lane(ni, R))
-         {
-            const SegRec &N = src.seg(ni);
-            const u32 g = N.begin - 512 > N.first + NFCB200_RING ? N.begin - 512 : N.first + NFCB200_RING; // detectors open (lane_begin)
-            const u32 gs = g - NFCB200_PREROLL;
-            const int cls = gs > pos + 64 ? gap_class(pos - 1, gs) : 0;
-
-            if (cls == 1 || cls == 2)
-            {
-               sh.act = WLANE_JUMP;
-               sh.jumpTa = pos - 1;
-               sh.jumpGs = gs;
-               sh.jumpT = N.first;
-               sh.jumpG = g;
-               sh.jumpBegin = N.begin;
-               sh.jumpSeg = ni;
-               sh.n = cls; // 1: sums move by the window change, 2: frozen
-#if defined(NFCB200_WLANE_DEBUG)
-               std::fprintf(stderr, "jump cls %d from %u to first %u begin %u (g %u gs %u) k %u\n", cls, pos, N.first, N.begin, g, gs, F.k);
-#endif
-               return;
-            }
-
-            if (cls == 3)
-            {
-               // adds may round: walk the stretch with the sums alone
-               sh.mode = WMODE_WALK;
-               sh.si = ni;
-               F.gateSum = F.k;
-               F.gate = F.k + (g - pos);
-               F.warm = F.k + (N.begin - pos);
-               u32 n = 32;
-               if (n > N.first - pos)
-                  n = N.first - pos;
-               sh.n = n;
-               return;
-            }
-         }
-      }
-
       if (sh.mode == WMODE_FEAT)
-         enter_scalar(S);
+         enter_scalar(src.seg(sh.si));
 
-      {
-         u32 n = 32 - (pos & 31);
-         if (n > nsamples - pos)
-            n = nsamples - pos;
-         sh.n = n;
-      }
+      plain_chunk(pos, nsamples);
    }
 
    // ------------------------------------------------------------------------------------------------------------------
@@ -688,29 +707,43 @@ struct WLane
          if (act == WLANE_DONE)
             break;
 
-         if (act == WLANE_JUMP)
+         if (act == WLANE_JUMP || act == WLANE_WALK)
          {
-            const bool moving = sh.n == 1;
-            if (moving)
+            const u32 T = sh.jumpT, from = sh.pos;
+
+            if (act == WLANE_WALK)
+               W::walk(*this, from, T);
+            else if (sh.jumpCls == 1)
                gap_delta(sh.jumpTa, sh.jumpGs);
+
+            W::sync();
+
             if (W::lane() == 0)
             {
-               if (moving)
-                  for (u32 d = 0; d < 6; d++)
-                  {
-                     const SumChain c = sum_chain(P, d);
-                     if (P.enabled & c.tech)
-                        F.fi[c.fi] += sh.delta[d];
-                  }
-               const u32 T = sh.jumpT;
-               F.clk = T - 1;
+               if (act == WLANE_WALK)
+               {
+                  // the sums ran through: they go on with the features' first sample
+                  F.gateSum = F.k;
+               }
+               else
+               {
+                  if (sh.jumpCls == 1)
+                     for (u32 d = 0; d < 6; d++)
+                     {
+                        const SumChain c = sum_chain(P, d);
+                        if (P.enabled & c.tech)
+                           F.fi[c.fi] += sh.delta[d];
+                     }
+                  F.clk = T - 1;
+                  F.gateSum = F.k + (sh.jumpGs - T);
+               }
                F.gate = F.k + (sh.jumpG - T);
-               F.gateSum = F.k + (sh.jumpGs - T);
-               F.warm = F.k + (sh.jumpBegin - T);
-               F.closed = 0;
+               F.warm = F.k + (sh.jumpB - T);
+               F.closed = 64;
                sh.si = sh.jumpSeg;
                sh.mode = WMODE_FEAT;
                sh.pos = T;
+               sh.stepped += T - from;
             }
             W::sync();
             continue;
@@ -724,12 +757,6 @@ struct WLane
             fill_feat(pos, n, k0, src.seg(sh.si));
             W::sync();
             chunk_feat(n);
-         }
-         else if (mode == WMODE_WALK)
-         {
-            fill_x(pos, n, k0);
-            W::sync();
-            walk_chunk(n);
          }
          else
          {
