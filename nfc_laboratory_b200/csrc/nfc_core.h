@@ -1185,6 +1185,15 @@ struct Machine
       if (clk != m.searchEndTime)
          return A_Invalid;
 
+      return A_poll_symbol_tail();
+   }
+
+   // end of the search window of decodePollFrameSymbolAsk (NfcA.cpp:875-932): classify the symbol, open the next window
+   NFC_HD int A_poll_symbol_tail()
+   {
+      const RateParams &b = P.A[F.lockRate];
+      Mod &m = L.c.mA[F.lockRate];
+
       if (m.searchCorrDValue < m.searchValueThreshold) // :877 Pattern-Y
       {
          m.symbolStartTime = m.symbolEndTime;
@@ -1235,6 +1244,12 @@ struct Machine
       if (pattern <= A_No)
          return;
 
+      A_poll_after(pattern);
+   }
+
+   // decodePollFrame once a symbol is complete (NfcA.cpp:438-560)
+   NFC_HD void A_poll_after(int pattern)
+   {
       TechSt &t = L.c.t[TECH_A];
       Bits &st = L.st;
       bool frameEnd = false, truncateError = false;
@@ -1473,6 +1488,15 @@ struct Machine
       if (clk != m.searchEndTime)
          return A_Invalid;
 
+      return A_listen_symbol_ask_tail();
+   }
+
+   // end of the search window of decodeListenFrameSymbolAsk (NfcA.cpp:1150-1212)
+   NFC_HD int A_listen_symbol_ask_tail()
+   {
+      const RateParams &b = P.A[F.lockRate];
+      Mod &m = L.c.mA[F.lockRate];
+
       if (m.searchCorrDValue > m.searchValueThreshold)
       {
          m.symbolStartTime = m.symbolEndTime;
@@ -1644,10 +1668,7 @@ struct Machine
    // one sample of decodeListenFrame, NfcA.cpp:568-807
    NFC_HD void A_listen_step()
    {
-      TechSt &t = L.c.t[TECH_A];
-      FrameSt &fs = t.fs;
-      Bits &st = L.st;
-      bool frameEnd = false, truncateError = false;
+      FrameSt &fs = L.c.t[TECH_A].fs;
 
       if (F.lockRate == 0) // 106k ASK / Manchester
       {
@@ -1668,6 +1689,22 @@ struct Machine
          if (pattern <= A_No)
             return;
 
+         A_listen_ask_after(pattern);
+         return;
+      }
+
+      A_listen_step_bpsk();
+   }
+
+   // decodeListenFrame (106 kbps) once a symbol is complete, NfcA.cpp:598-690
+   NFC_HD void A_listen_ask_after(int pattern)
+   {
+      TechSt &t = L.c.t[TECH_A];
+      FrameSt &fs = t.fs;
+      Bits &st = L.st;
+      bool frameEnd = false, truncateError = false;
+
+      {
          if (pattern == A_F)
             frameEnd = true;
          else if (st.bytes == t.ps.maxFrameSize)
@@ -1716,8 +1753,16 @@ struct Machine
 
          return;
       }
+   }
 
-      // 212k / 424k BPSK
+   // 212k / 424k BPSK listen frames, NfcA.cpp:693-807
+   NFC_HD void A_listen_step_bpsk()
+   {
+      TechSt &t = L.c.t[TECH_A];
+      FrameSt &fs = t.fs;
+      Bits &st = L.st;
+      bool frameEnd = false, truncateError = false;
+
       if (!fs.frameStart)
       {
          int pattern = A_listen_start_bpsk();

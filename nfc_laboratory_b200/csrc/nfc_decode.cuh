@@ -453,7 +453,13 @@ struct WLaneConfig
    const float4 *pool;
    FramePool frames;
    unsigned long long *work; // samples consumed (statistics)
+   unsigned long long *phase; // [16] cycles and samples per phase (development counters)
+   int use_tma;
 };
+
+#define WALK_TILE 512u     /* samples per staged tile                                     */
+#define WALK_STAGES 3u     /* tiles in flight: the W / D / M sample rings are idle during a walk and hold them */
+#define WALK_STAGE_BYTES (NFCB200_RING * 4u)
 
 struct DevWarp
 {
@@ -461,14 +467,135 @@ struct DevWarp
    static __device__ __forceinline__ u32 width() { return 32; }
    static __device__ __forceinline__ void sync() { __syncwarp(); }
    static __device__ __forceinline__ u32 min_u32(u32 v) { return __reduce_min_sync(0xffffffffu, v); }
+   static __device__ __forceinline__ u32 max_u32(u32 v) { return __reduce_max_sync(0xffffffffu, v); }
    static __device__ __forceinline__ u32 add_u32(u32 v) { return __reduce_add_sync(0xffffffffu, v); }
    static __device__ __forceinline__ u32 or_u32(u32 v) { return __reduce_or_sync(0xffffffffu, v); }
+   static __device__ __forceinline__ unsigned long long clock() { return clock64(); }
    static __device__ __forceinline__ float add_f32(float v)
    {
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1)
          v += __shfl_xor_sync(0xffffffffu, v, d);
       return v;
+   }
+
+   // running sums of the cnt (<= 32) samples after the current step: the reference's recurrence (add, then subtract: two
+   // roundings per sample, NfcA.cpp:246-247), one detector per thread on six threads
+   template <class WL>
+   static __device__ __forceinline__ void sum_chains(WL &wl, u32 cnt)
+   {
+      wl.sum_chains_seq(cnt);
+   }
+
+   /*
+    * The idle stretch [pos, target) with the sums alone.  The raw samples are staged by the TMA engine (cp.async.bulk 1-D
+    * under an mbarrier, three tiles of 512 samples in flight per warp -- the sample rings for w / deviation / envelope are
+    * not needed until the lane re-enters the features and serve as the staging buffers), converted to the exact magnitude
+    * into the x ring, and six threads advance the six sums over the tile with the reference's own recurrence.
+    */
+   template <class WL>
+   static __device__ void walk(WL &wl, u32 pos, u32 target)
+   {
+      const auto &src = wl.src;
+      const u32 bs = sig_bytes(src.sigtype);
+
+      if (!src.use_tma || (pos & 31) || (target & 31) || target <= pos)
+      {
+         wl.walk_generic(pos, target);
+         return;
+      }
+
+      const u32 lane = threadIdx.x & 31;
+      const u32 kbase = wl.F.kbase;
+      u32 k = wl.F.k;
+      u32 phase = wl.sh.barPhase;
+
+      // thread d < 6 owns the running sum of detector d for the whole walk
+      const SumChain mine = sum_chain(wl.P, lane < 6 ? lane : 0);
+      const bool chain = lane < 6 && (wl.P.enabled & mine.tech) != 0;
+      float sum = chain ? wl.F.fi[mine.fi] : 0.0f;
+
+      unsigned char *staging = reinterpret_cast<unsigned char *>(wl.rg + NFCB200_OFF_W);
+      uint64_t *bar = reinterpret_cast<uint64_t *>(wl.sh.bar);
+      const unsigned char *gsrc = (const unsigned char *) src.samples + src.streamBase * bs;
+      const float *X = wl.rg + NFCB200_OFF_X;
+      const u32 total = target - pos;
+      const u32 ntiles = (total + WALK_TILE - 1) / WALK_TILE;
+
+      auto issue = [&](u32 i) {
+         const u32 st = i % WALK_STAGES;
+         const u32 p = pos + i * WALK_TILE;
+         const u32 cnt = target - p < WALK_TILE ? target - p : WALK_TILE;
+         mbar_expect_tx(&bar[st], cnt * bs);
+         tma_load_1d(staging + st * WALK_STAGE_BYTES, gsrc + (uint64_t) p * bs, cnt * bs, &bar[st]);
+      };
+
+      // earlier ring fills went through the generic proxy: order them before the bulk copies into the same memory
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+
+      if (lane == 0)
+         for (u32 i = 0; i < WALK_STAGES && i < ntiles; i++)
+            issue(i);
+
+      for (u32 i = 0; i < ntiles; i++)
+      {
+         const u32 st = i % WALK_STAGES;
+         const u32 p = pos + i * WALK_TILE;
+         const u32 cnt = target - p < WALK_TILE ? target - p : WALK_TILE;
+         const unsigned char *raw = staging + st * WALK_STAGE_BYTES;
+
+         mbar_wait(&bar[st], (phase >> st) & 1u);
+         phase ^= 1u << st;
+
+         // exact magnitudes of the tile into the x ring (all threads)
+         for (u32 g = lane; g < cnt; g += 32)
+            wl.rg[NFCB200_OFF_X + ((k + 1 + g + kbase) & (NFCB200_RING - 1))] = sample_from_raw(raw, src.sigtype, g);
+         __syncwarp();
+
+         // the staging buffer is free again
+         if (lane == 0 && i + WALK_STAGES < ntiles)
+            issue(i + WALK_STAGES);
+
+         // the six sums over the tile: s += x[t - sdd]; s -= x[t - sdd - p2] (cnt is a multiple of 32)
+         if (chain)
+         {
+            u32 ia = (k + 1 + kbase - mine.sdd) & (NFCB200_RING - 1);
+            u32 ib = (k + 1 + kbase - mine.sdd - mine.p2) & (NFCB200_RING - 1);
+            for (u32 g = 0; g < cnt; g += 8)
+            {
+               float a[8], b[8];
+#pragma unroll
+               for (u32 q = 0; q < 8; q++)
+               {
+                  a[q] = X[(ia + q) & (NFCB200_RING - 1)];
+                  b[q] = X[(ib + q) & (NFCB200_RING - 1)];
+               }
+#pragma unroll
+               for (u32 q = 0; q < 8; q++)
+               {
+                  sum += a[q];
+                  sum -= b[q];
+               }
+               ia = (ia + 8) & (NFCB200_RING - 1);
+               ib = (ib + 8) & (NFCB200_RING - 1);
+            }
+         }
+
+         k += cnt;
+         __syncwarp();
+      }
+
+      __syncwarp();
+
+      if (chain)
+         wl.F.fi[mine.fi] = sum;
+      if (lane == 0)
+      {
+         wl.advance(total);
+         wl.sh.barPhase = phase;
+      }
+      __syncwarp();
    }
 };
 
@@ -482,6 +609,7 @@ struct DevSrc
    const float *bsum;    // this stream's block sums
    const SegRec *segs;
    uint32_t nsegs;
+   int use_tma;          // stream pitch and base are 16-byte aligned: bulk copies allowed
 
    __device__ __forceinline__ float x(u32 pos) const { return load_sample(samples, sigtype, streamBase + pos); }
    __device__ __forceinline__ Feat feat(unsigned long long i) const
@@ -516,6 +644,17 @@ __global__ void __launch_bounds__(32) wlanes_kernel(WLaneConfig c, const __grid_
    WLaneSmem &sm = *reinterpret_cast<WLaneSmem *>(wl_smem);
    const u32 lane = threadIdx.x;
 
+   if (lane == 0)
+   {
+      for (u32 i = 0; i < WALK_STAGES; i++)
+         mbar_init(reinterpret_cast<uint64_t *>(&sm.sh.bar[i]), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      sm.sh.barPhase = 0;
+      for (u32 i = 0; i < 8; i++)
+         sm.sh.cyc[i] = sm.sh.cnt[i] = 0;
+   }
+   __syncwarp();
+
    for (;;)
    {
       u32 qi = 0;
@@ -549,6 +688,7 @@ __global__ void __launch_bounds__(32) wlanes_kernel(WLaneConfig c, const __grid_
       src.bsum = c.bsum + (size_t) R.stream * c.n_blocks;
       src.segs = c.segs;
       src.nsegs = c.n_segs;
+      src.use_tma = c.use_tma;
 
       WLane<DevWarp, DeviceSink, DevSrc> WL(dP, sm.L, sm.rg, sm.sb, sink, sm.sh, src);
       WL.run(R, R.seg0, (u32) c.n_samples);
@@ -560,6 +700,9 @@ __global__ void __launch_bounds__(32) wlanes_kernel(WLaneConfig c, const __grid_
       }
       __syncwarp();
    }
+
+   if (lane < 16)
+      atomicAdd(c.phase + lane, lane < 8 ? sm.sh.cyc[lane] : sm.sh.cnt[lane - 8]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -62,33 +62,47 @@ NFC_HD void front_pass(const Params &P, u32 first, u32 end, LOADX loadx, STORE s
    u32 pulse = 0;
    const u32 etu = (u32) P.etu, hold = (u32) (P.etu * 10);
 
-   for (u32 pos = first; pos < end; pos++)
+   // the samples are fetched eight at a time, ahead of the recurrences that consume them (a thread walks its own stream:
+   // every load is a cache miss, and the recurrences cannot start before their sample arrives)
+   for (u32 pos0 = first; pos0 < end; pos0 += 8)
    {
-      const float x = loadx(pos);
+      float xs[8];
+      const u32 cnt = end - pos0 < 8 ? end - pos0 : 8;
+      for (u32 i = 0; i < 8; i++)
+         xs[i] = i < cnt ? loadx(pos0 + i) : 0.0f;
 
-      ++pulse;
-
-      const float adiff = fabsf(x - env);
-      const bool open = gate_open(adiff, env);
-
-      if (open || pulse > hold)
+      for (u32 i = 0; i < 8; i++)
       {
-         pulse = 0;
-         env = env * P.envW0 + x * P.envW1;
+         if (i >= cnt)
+            break;
+
+         const u32 pos = pos0 + i;
+         const float x = xs[i];
+
+         ++pulse;
+
+         const float adiff = fabsf(x - env);
+         const bool open = gate_open(adiff, env);
+
+         if (open || pulse > hold)
+         {
+            pulse = 0;
+            env = env * P.envW0 + x * P.envW1;
+         }
+         else if (pos - first < etu)
+         {
+            env = x;
+         }
+
+         float n0 = x + f1 * P.iirA;
+         float w = n0 - f1;
+         f1 = n0;
+
+         dev = dev * P.mdevW0 + fabsf(w) * P.mdevW1;
+         avg = avg * P.meanW0 + x * P.meanW1;
+
+         store(pos - first, w, env, dev, avg);
       }
-      else if (pos - first < etu)
-      {
-         env = x;
-      }
-
-      float n0 = x + f1 * P.iirA;
-      float w = n0 - f1;
-      f1 = n0;
-
-      dev = dev * P.mdevW0 + fabsf(w) * P.mdevW1;
-      avg = avg * P.meanW0 + x * P.meanW1;
-
-      store(pos - first, w, env, dev, avg);
    }
 
    S.tEnv = env;
@@ -105,9 +119,11 @@ struct HostWarp
    static NFC_HD u32 width() { return 1; }
    static NFC_HD void sync() {}
    static NFC_HD u32 min_u32(u32 v) { return v; }
+   static NFC_HD u32 max_u32(u32 v) { return v; }
    static NFC_HD u32 add_u32(u32 v) { return v; }
    static NFC_HD float add_f32(float v) { return v; }
    static NFC_HD u32 or_u32(u32 v) { return v; }
+   static NFC_HD unsigned long long clock() { return 0; }
 
    // the detectors' running sums over the cnt samples after the current step: the reference's own recurrence
    template <class WL>
@@ -131,12 +147,18 @@ struct WShared
    float cavg[32];   // carrier average of the chunk's samples
    u32 act;          // control: what the warp does next (WLANE_*)
    u32 pos, n, mode, si, j, stepped, blockActive;
+   u32 nextB, nextSeg, nextCls, nextFrom; // cached look-ahead of the current inactive run: next active block, its segment, gap class
    u32 jumpCls, jumpTa, jumpGs, jumpT, jumpG, jumpB, jumpSeg;
    float delta[6];
+   unsigned long long cyc[8];   // cycles per phase (WPH_*), samples per phase: development counters, summed into the handle
+   unsigned long long cnt[8];
+   u32 barPhase;                // device walk: parity bits of the staging barriers
+   unsigned long long bar[4];   // device walk: mbarriers of the staging tiles
 };
 
 enum { WLANE_DONE = 0, WLANE_CHUNK = 1, WLANE_JUMP = 2, WLANE_WALK = 3 };
 enum { WMODE_FEAT = 0, WMODE_SCAL = 1 };
+enum { WPH_CONTROL = 0, WPH_FILL = 1, WPH_SEARCH = 2, WPH_MACHINE = 3, WPH_WALK = 4, WPH_JUMP = 5, WPH_SCALAR = 6, WPH_LOCKED = 7 };
 
 // the six running-sum chains: NFC-A 106 / 212 / 424, NFC-F 212 / 424, NFC-V
 struct SumChain
@@ -477,6 +499,342 @@ struct WLane
       return m;
    }
 
+
+   NFC_HD static u32 float_bits(float v)
+   {
+      union
+      {
+         float f;
+         u32 u;
+      } c;
+      c.f = v;
+      return c.u;
+   }
+
+   // carrier-edge tracker (NfcTech.cpp:77-92, Machine::edge_track) over the m samples after local step k, in closed form:
+   // the peak restarts at every sample below the low threshold; inside a stretch without such a sample the tracker records
+   // strictly increasing values above the high threshold, so its last record is the FIRST occurrence of the stretch's maximum
+   NFC_HD void edge_span(u32 k, u32 clk, u32 m)
+   {
+      u32 hi = 0, lo = 0;
+      float mine = 0;
+
+      for (u32 a = 1 + W::lane(); a <= m; a += W::width())
+      {
+         const float rect = fabsf(rg[NFCB200_OFF_W + slot(k + a, 0)]);
+         if (rect > P.highThr)
+            hi |= 1u << (a - 1);
+         else if (rect < P.lowThr)
+            lo |= 1u << (a - 1);
+      }
+
+      hi = W::or_u32(hi);
+      lo = W::or_u32(lo);
+
+      if (!(hi | lo))
+         return;
+
+      if (!hi)
+      {
+         if (W::lane() == 0)
+            F.edgePeak = 0;
+         return;
+      }
+
+      // the stretch that holds the last sample above the high threshold
+      u32 h = 31;
+      while (!((hi >> h) & 1u))
+         h--;
+      const u32 loBelow = lo & ((1u << h) - 1u);
+      u32 segStart = 0; // first bit of that stretch
+      if (loBelow)
+      {
+         segStart = 31;
+         while (!((loBelow >> segStart) & 1u))
+            segStart--;
+         segStart++;
+      }
+      const u32 segMask = hi & ~((1u << segStart) - 1u);
+      const bool firstSeg = loBelow == 0;
+      const bool resetAfter = (lo >> h) > 1u || ((lo >> h) & ~1u) != 0;
+
+      u32 best = 0;
+      for (u32 a = 1 + W::lane(); a <= m; a += W::width())
+         if ((segMask >> (a - 1)) & 1u)
+         {
+            const u32 v = float_bits(fabsf(rg[NFCB200_OFF_W + slot(k + a, 0)]));
+            best = v > best ? v : best;
+         }
+      best = W::max_u32(best);
+
+      u32 firstAt = 0xFFFFFFFFu;
+      for (u32 a = 1 + W::lane(); a <= m; a += W::width())
+         if (((segMask >> (a - 1)) & 1u) && float_bits(fabsf(rg[NFCB200_OFF_W + slot(k + a, 0)])) == best && a < firstAt)
+            firstAt = a;
+      firstAt = W::min_u32(firstAt);
+
+      if (W::lane() == 0)
+      {
+         union
+         {
+            float f;
+            u32 u;
+         } c;
+         c.u = best;
+         float peak = F.edgePeak;
+         if (!firstSeg || c.f > peak)
+         {
+            peak = c.f;
+            F.edgeTime = clk + firstAt;
+         }
+         F.edgePeak = resetAfter ? 0.0f : peak;
+      }
+      (void) mine;
+   }
+
+   // ring writes, running sum and clocks of m samples of a LOCKED NFC-A decoder (rate r): only its own sum moved
+   NFC_HD void commit_locked_A(u32 r, u32 m)
+   {
+      const RateParams &b = P.A[r];
+      const u32 ph0 = F.cA[r];
+      for (u32 a = 1 + W::lane(); a <= m; a += W::width())
+         rg[b.corr + wrap_add(ph0, a, b.p1)] = sh.lin[r][a];
+
+      W::sync();
+
+      if (W::lane() == 0)
+      {
+         F.fi[r] = sh.lin[r][m];
+         F.env = rg[NFCB200_OFF_M + slot(F.k + m, 0)];
+         advance(m);
+      }
+
+      W::sync();
+   }
+
+   // half-symbol running sum of a locked NFC-A decoder over cnt samples (one thread: the recurrence is sequential); the
+   // addends come from the x ring (poll frames) or from the w^2 * 10 integration ring (106 kbps listen frames)
+   NFC_HD void chain_locked_A(u32 r, u32 cnt, u32 ringOff)
+   {
+      if (W::lane() == 0)
+      {
+         const RateParams &b = P.A[r];
+         float s = F.fi[r];
+         u32 s0 = slot(F.k + 1, b.sdd), s1 = slot(F.k + 1, b.sdd + b.p2);
+         float *lin = sh.lin[r];
+         lin[0] = s;
+         for (u32 a = 1; a <= cnt; a++)
+         {
+            s += rg[ringOff + s0];
+            s -= rg[ringOff + s1];
+            lin[a] = s;
+            s0 = (s0 + 1) & (NFCB200_RING - 1);
+            s1 = (s1 + 1) & (NFCB200_RING - 1);
+         }
+      }
+   }
+
+   // w^2 * 10 of the span's samples into the integration ring (NfcA.cpp:963, 1118)
+   NFC_HD void integrate_w2(u32 sdd, u32 cnt)
+   {
+      for (u32 a = 1 + W::lane(); a <= cnt; a += W::width())
+      {
+         const u32 s = slot(F.k + a, sdd);
+         const float w = rg[NFCB200_OFF_W + s];
+         rg[NFCB200_OFF_I + s] = w * w * 10;
+      }
+   }
+
+   /*
+    * Locked NFC-A symbol decoders that share one shape -- decodePollFrameSymbolAsk (kind 0, NfcA.cpp:812-934) and
+    * decodeListenFrameSymbolAsk (kind 1, NfcA.cpp:1095-1214): integrate every sample; inside [searchStartTime,
+    * searchEndTime] keep the FIRST maximum of the correlation (above the threshold for poll frames), latch the values at
+    * searchSyncTime, classify at searchEndTime.  One call consumes the chunk's samples up to the end of the window; the
+    * window itself is evaluated by the 32 threads at once, the symbol and frame logic behind it by Machine's own code.
+    */
+   NFC_HD u32 ff_symbol_A(u32 j, u32 n, int kind)
+   {
+      const u32 r = F.lockRate;
+      const RateParams &b = P.A[r];
+      Mod &m = L.c.mA[r];
+      const u32 k = F.k, clk = F.clk;
+      const u32 end = m.searchEndTime, start = m.searchStartTime, syncT = m.searchSyncTime;
+
+      if (end <= clk)
+         return 0;
+
+      u32 cnt = n - j;
+      if (cnt > end - clk)
+         cnt = end - clk;
+
+      if (kind == 1)
+      {
+         integrate_w2(b.sdd, cnt);
+         W::sync();
+      }
+
+      chain_locked_A(r, cnt, kind == 0 ? NFCB200_OFF_X : NFCB200_OFF_I);
+      W::sync();
+
+      const float thr = m.searchValueThreshold, peak0 = m.correlatedPeakValue;
+      const SumChain c = sum_chain(P, r);
+      u32 best = 0, latchA = 0xFFFFFFFFu;
+      float mySd = 0, myS0 = 0, myS1 = 0;
+      bool myCand = false;
+
+      for (u32 a = 1 + W::lane(); a <= cnt; a += W::width())
+      {
+         const u32 ca = clk + a;
+         if (ca < start)
+            continue;
+         const float c1 = sh.lin[r][a];
+         const float c2 = corr_at(r, c, F.cA[r], a, c.p1 - c.p2);
+         const float c3 = corr_at(r, c, F.cA[r], a, 1);
+         const float s0 = c1 - c2, s1 = c2 - c3;
+         const float sd = kind == 0 ? fabsf(s0 - s1) / (float) b.p2 : fabsf(s0 - s1);
+         const bool cand = kind == 0 ? sd > thr : true;
+         if (cand)
+         {
+            const u32 v = float_bits(sd);
+            best = v > best ? v : best;
+         }
+         if (ca == syncT)
+         {
+            m.searchCorrDValue = sd;
+            m.searchCorr0Value = s0;
+            m.searchCorr1Value = s1;
+         }
+         // one sample per thread on the device; the host's single thread keeps its last in-window sample only for the
+         // second pass below, which recomputes instead
+         mySd = sd;
+         myS0 = s0;
+         myS1 = s1;
+         myCand = cand;
+      }
+
+      best = W::max_u32(best);
+      (void) latchA;
+      (void) myS0;
+      (void) myS1;
+      (void) mySd;
+      (void) myCand;
+
+      {
+         union
+         {
+            float f;
+            u32 u;
+         } cv;
+         cv.u = best;
+         if (best != 0 && cv.f > peak0)
+         {
+            // first sample that attains the maximum
+            u32 firstAt = 0xFFFFFFFFu;
+            for (u32 a = 1 + W::lane(); a <= cnt; a += W::width())
+            {
+               const u32 ca = clk + a;
+               if (ca < start)
+                  continue;
+               const float c1 = sh.lin[r][a];
+               const float c2 = corr_at(r, c, F.cA[r], a, c.p1 - c.p2);
+               const float c3 = corr_at(r, c, F.cA[r], a, 1);
+               const float s0 = c1 - c2, s1 = c2 - c3;
+               const float sd = kind == 0 ? fabsf(s0 - s1) / (float) b.p2 : fabsf(s0 - s1);
+               if (float_bits(sd) == best && (kind == 0 ? sd > thr : true) && a < firstAt)
+                  firstAt = a;
+            }
+            firstAt = W::min_u32(firstAt);
+            if (W::lane() == 0)
+            {
+               m.correlatedPeakValue = cv.f;
+               m.correlatedPeakTime = clk + firstAt;
+            }
+         }
+      }
+
+      W::sync();
+
+      edge_span(k, clk, cnt);
+      commit_locked_A(r, cnt);
+
+      if (clk + cnt == end)
+      {
+         if (W::lane() == 0)
+         {
+            if (kind == 0)
+            {
+               const int pattern = M.A_poll_symbol_tail();
+               if (pattern > (int) Mach::A_No)
+                  M.A_poll_after(pattern);
+            }
+            else
+            {
+               const int pattern = M.A_listen_symbol_ask_tail();
+               if (pattern > (int) Mach::A_No)
+                  M.A_listen_ask_after(pattern);
+            }
+            if (F.lock == LOCK_NONE)
+               M.refresh_busy();
+         }
+         W::sync();
+      }
+
+      return cnt;
+   }
+
+   /*
+    * decodeListenFrameStartAsk (NfcA.cpp:939-1090) while nothing happens: the integrator runs on every sample; before
+    * guardEnd nothing else does, after it the search acts only on a correlation beyond the threshold, a deep modulation,
+    * the time-out or a window end.  Consumes the samples before the first such sample.
+    */
+   NFC_HD u32 ff_listen_start_A(u32 j, u32 n)
+   {
+      const u32 r = F.lockRate;
+      const RateParams &b = P.A[r];
+      Mod &m = L.c.mA[r];
+      const FrameSt &fs = L.c.t[TECH_A].fs;
+      const u32 k = F.k, clk = F.clk;
+      const u32 cnt = n - j;
+
+      integrate_w2(b.sdd, cnt);
+      W::sync();
+      chain_locked_A(r, cnt, NFCB200_OFF_I);
+      W::sync();
+
+      const SumChain c = sum_chain(P, r);
+      const float thr = m.searchValueThreshold, peak = m.correlatedPeakValue;
+      const bool second = m.symbolStartTime != 0;
+      u32 first = cnt + 1;
+
+      for (u32 a = 1 + W::lane(); a <= cnt; a += W::width())
+      {
+         const u32 ca = clk + a;
+         if (ca < fs.guardEnd)
+            continue;
+         bool ev = ca == fs.guardEnd || ca > fs.waitingEnd || ca == m.searchEndTime;
+         {
+            const u32 s = slot(k + a, 0);
+            const float x = rg[NFCB200_OFF_X + s], env = rg[NFCB200_OFF_M + s];
+            const float clamped = x < 0.0f ? 0.0f : (env < x ? env : x);
+            ev |= (env - clamped) / env > P.thr[TECH_A].modMin;
+         }
+         const float s0 = sh.lin[r][a] - corr_at(r, c, F.cA[r], a, c.p1 - c.p2);
+         ev |= second ? (s0 < -thr && s0 < peak) : (s0 > thr && s0 > peak);
+         if (ev && a < first)
+            first = a;
+      }
+
+      first = W::min_u32(first);
+      const u32 mcount = first - 1;
+
+      if (mcount == 0)
+         return 0;
+
+      edge_span(k, clk, mcount);
+      commit_locked_A(r, mcount);
+      return mcount;
+   }
+
    // an idle stretch [pos, target), sums alone: no features exist there and nothing else can move (the correlation
    // rings are not maintained: the lane re-enters the features NFCB200_LEAD samples before the next active block and
    // refills them before its detectors open)
@@ -601,70 +959,87 @@ struct WLane
       const bool active = src.active(pos);
       sh.blockActive = active ? 1u : 0u;
 
+      if (active)
+         sh.nextB = 0;
+
       // outside the active blocks a settled lane retires, or skips ahead to NFCB200_LEAD samples before the next active block
-      if ((pos & 31) == 0 && !active && F.lock == LOCK_NONE && F.busy == 0 && M.dormant())
+      if ((pos & 31) == 0 && !active && F.lock == LOCK_NONE && F.busy == 0 && F.closed < 16 && M.dormant())
       {
-         u32 B = 0, ni = sh.si;
-         bool found = false;
+         // look ahead once per inactive run: the next active block B, the segment that holds it, the class of the stretch
+         if (sh.nextB == 0 || pos >= sh.nextB || sh.nextFrom > pos)
+         {
+            u32 B = 0, ni = sh.si;
+            bool found = false;
 
-         if (inFeat)
-         {
-            const u32 segEnd = src.seg(sh.si).end;
-            for (u32 p = (pos | (NFCB200_BLOCK - 1)) + 1; p < segEnd && !found; p += NFCB200_BLOCK)
-               if (src.active(p))
-               {
-                  B = p;
-                  found = true;
-               }
-         }
-         else
-         {
-            if (pos >= R.end)
+            if (inFeat)
             {
-               sh.act = WLANE_DONE;
-               return;
+               const u32 segEnd = src.seg(sh.si).end;
+               for (u32 p = (pos | (NFCB200_BLOCK - 1)) + 1; p < segEnd && !found; p += NFCB200_BLOCK)
+                  if (src.active(p))
+                  {
+                     B = p;
+                     found = true;
+                  }
             }
-
-            while (seg_of_lane(ni, R) && src.seg(ni).end <= pos)
-               ni++;
-
-            if (seg_of_lane(ni, R))
+            else
             {
-               const SegRec &N = src.seg(ni);
-               if (N.begin > pos)
+               if (pos >= R.end)
                {
-                  B = N.begin;
-                  found = true;
-               }
-               else if (pos >= N.first + NFCB200_HALO_SHORT)
-               {
-                  // inside that segment's feature range: its features are exact once the front pass has converged (the same
-                  // contraction a lane start relies on), and they continue the lane's own rings without a seam
-                  sh.mode = WMODE_FEAT;
-                  sh.si = ni;
-                  plain_chunk(pos, N.end);
+                  sh.act = WLANE_DONE;
                   return;
                }
+
+               while (seg_of_lane(ni, R) && src.seg(ni).end <= pos)
+                  ni++;
+
+               if (seg_of_lane(ni, R))
+               {
+                  const SegRec &N = src.seg(ni);
+                  if (N.begin > pos)
+                  {
+                     B = N.begin;
+                     found = true;
+                  }
+                  else if (pos >= N.first + NFCB200_HALO_SHORT)
+                  {
+                     // inside that segment's feature range: its features are exact once the front pass has converged (the
+                     // same contraction a lane start relies on), and they continue the lane's own rings without a seam
+                     sh.mode = WMODE_FEAT;
+                     sh.si = ni;
+                     plain_chunk(pos, N.end);
+                     return;
+                  }
+               }
             }
+
+            sh.nextB = found ? B : 0xFFFFFFFFu;
+            sh.nextSeg = ni;
+            sh.nextFrom = pos;
+            sh.nextCls = 0;
+            if (found && B >= NFCB200_LEAD + 512 && B - NFCB200_LEAD >= pos + 512)
+               sh.nextCls = (u32) gap_class(pos - 1, B - 512 - NFCB200_PREROLL);
+         }
+         else if (!inFeat && pos >= R.end)
+         {
+            sh.act = WLANE_DONE;
+            return;
          }
 
-         if (found && B >= NFCB200_LEAD + 512 && B - NFCB200_LEAD >= pos + 512)
+         const u32 B = sh.nextB;
+
+         if (B != 0xFFFFFFFFu && sh.nextCls != 0 && B - NFCB200_LEAD >= pos + 512)
          {
             const u32 T = B - NFCB200_LEAD, g = B - 512, gs = g - NFCB200_PREROLL;
-            const int cls = gap_class(pos - 1, gs);
-
-            if (cls != 0)
-            {
-               sh.act = cls == 3 ? WLANE_WALK : WLANE_JUMP;
-               sh.jumpCls = (u32) cls;
-               sh.jumpTa = pos - 1;
-               sh.jumpGs = gs;
-               sh.jumpT = T;
-               sh.jumpG = g;
-               sh.jumpB = B;
-               sh.jumpSeg = ni;
-               return;
-            }
+            sh.act = sh.nextCls == 3 ? WLANE_WALK : WLANE_JUMP;
+            sh.jumpCls = sh.nextCls;
+            sh.jumpTa = pos - 1;
+            sh.jumpGs = gs;
+            sh.jumpT = T;
+            sh.jumpG = g;
+            sh.jumpB = B;
+            sh.jumpSeg = sh.nextSeg;
+            sh.nextB = 0;
+            return;
          }
       }
 
@@ -693,14 +1068,17 @@ struct WLane
          sh.mode = WMODE_FEAT;
          sh.si = seg0;
          sh.stepped = 0;
+         sh.nextB = 0;
       }
       W::sync();
 
       for (;;)
       {
+         unsigned long long t0 = W::clock();
          if (W::lane() == 0)
             control(R, nsamples);
          W::sync();
+         tick(WPH_CONTROL, t0, 1);
 
          const u32 act = sh.act;
 
@@ -717,6 +1095,7 @@ struct WLane
                gap_delta(sh.jumpTa, sh.jumpGs);
 
             W::sync();
+            tick(act == WLANE_WALK ? WPH_WALK : WPH_JUMP, t0, T - from);
 
             if (W::lane() == 0)
             {
@@ -756,6 +1135,7 @@ struct WLane
          {
             fill_feat(pos, n, k0, src.seg(sh.si));
             W::sync();
+            tick(WPH_FILL, t0, n);
             chunk_feat(n);
          }
          else
@@ -766,6 +1146,7 @@ struct WLane
                for (u32 i = 0; i < n; i++)
                   M.step(src.x(pos + i));
             }
+            tick(WPH_SCALAR, t0, n);
          }
 
          if (W::lane() == 0)
@@ -777,23 +1158,77 @@ struct WLane
       }
    }
 
+   // a locked decoder with a fast path is about to run (the machine hands over after every sample it had to take)
+   NFC_HD bool fast_locked() const
+   {
+      if (F.lock != LOCK_A)
+         return false;
+      const FrameSt &fs = L.c.t[TECH_A].fs;
+      return fs.frameType == FT_Poll || (fs.frameType == FT_Listen && F.lockRate == 0);
+   }
+
+   // development counters: cycles since t0 go to phase ph, t0 restarts
+   NFC_HD void tick(u32 ph, unsigned long long &t0, u32 samples)
+   {
+      const unsigned long long t1 = W::clock();
+      if (W::lane() == 0)
+      {
+         sh.cyc[ph] += t1 - t0;
+         sh.cnt[ph] += samples;
+      }
+      t0 = t1;
+   }
+
    // the samples of one filled chunk
    NFC_HD void chunk_feat(u32 n)
    {
       u32 j = 0;
+      unsigned long long t0 = W::clock();
 
       while (j < n)
       {
          const bool idle = F.lock == LOCK_NONE && F.busy == 0 && !noff;
          const u32 carrierOn = L.c.carrierOn, carrierOff = L.c.carrierOff;
+         bool lockedA = false;
+         int aKind = 0;
+         if (!noff && F.lock == LOCK_A)
+         {
+            const FrameSt &fs = L.c.t[TECH_A].fs;
+            if (fs.frameType == FT_Poll)
+            {
+               lockedA = true;
+               aKind = 0;
+            }
+            else if (fs.frameType == FT_Listen && F.lockRate == 0)
+            {
+               lockedA = true;
+               aKind = fs.frameStart ? 1 : 2;
+            }
+         }
          W::sync();
 
          if (idle)
          {
             const u32 m = ff_search(j, n, carrierOn, carrierOff);
             j += m;
+            tick(WPH_SEARCH, t0, m);
             if (j >= n)
                break;
+         }
+         else if (lockedA)
+         {
+            // locked NFC-A decoders with a fast path; they return 0 on the samples that need the machine
+            u32 m = 0;
+            if (aKind == 2)
+               m = ff_listen_start_A(j, n);
+            else
+               m = ff_symbol_A(j, n, aKind);
+            j += m;
+            tick(WPH_LOCKED, t0, m);
+            if (j >= n)
+               break;
+            if (m)
+               continue;
          }
 
          // the machine, until it is idle again (or the chunk ends); after a fast-forward span at least one sample
@@ -806,11 +1241,13 @@ struct WLane
                M.featAvg = sh.cavg[i];
                M.step(0.0f);
                i++;
-            } while (i < n && (noff || !(F.lock == LOCK_NONE && F.busy == 0)));
+            } while (i < n && (noff || !((F.lock == LOCK_NONE && F.busy == 0) || fast_locked())));
             sh.j = i;
          }
          W::sync();
-         j = sh.j;
+         const u32 jn = sh.j;
+         tick(WPH_MACHINE, t0, jn - j);
+         j = jn;
          W::sync();
       }
    }

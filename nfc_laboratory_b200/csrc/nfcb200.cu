@@ -137,6 +137,7 @@ struct Counters
    u32 segTotal;
    u32 pad;
    unsigned long long featTotal;
+   unsigned long long phase[16];
 };
 
 // host-side milestones of a call, printed when NFCB200_TRACE is set (debug aid)
@@ -719,6 +720,8 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    lc.pool = h->feats.as<float4>();
    lc.frames = pool;
    lc.work = &dC->work;
+   lc.use_tma = sc.use_tma;
+   lc.phase = dC->phase;
 
    ChainConfig cc;
    cc.lanes = h->lanes.as<LaneRec>();
@@ -772,6 +775,16 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    CUDA_TRY(cudaStreamSynchronize(st));
 
    S.lane_samples = hc.work;
+   if (tr.on)
+   {
+      static const char *names[8] = {"control", "fill", "search", "machine", "walk", "jump", "scalar", "locked"};
+      unsigned long long tot = 0;
+      for (int i = 0; i < 8; i++)
+         tot += hc.phase[i];
+      for (int i = 0; i < 8; i++)
+         fprintf(stderr, "[nfcb200] lanes %-8s %5.1f %% of cycles, %12llu samples, %8.1f cycles / sample\n", names[i], 100.0 * hc.phase[i] / (double) (tot ? tot : 1),
+                 hc.phase[8 + i], hc.phase[8 + i] ? (double) hc.phase[i] / (double) hc.phase[8 + i] : 0.0);
+   }
    S.live_lanes = hc.live;
 
    if (hc.poolCount > poolCap || hc.extCount > extCap)
