@@ -77,7 +77,10 @@ typedef struct nfcb200_config
    uint32_t use_tma;              /* 1: stage screening tiles with cp.async.bulk (default); 0: plain loads (debug) */
    uint32_t max_rounds;           /* bound on speculation rounds (0 = default)                                    */
    uint32_t segments_per_lane;    /* 0 = choose from the batch size; >= 1 forces the lane grouping                */
-   uint32_t reserved[4];
+   uint32_t exact;                /* 1: one warp lane per stream carries the reference's float state across the whole
+                                     capture (running sums included): bit-exact on float input, slower.  0 (default): lanes
+                                     cold-start their running sums -- exact on 16-bit input, sums within 2e-6 on float input */
+   uint32_t reserved[3];
 } nfcb200_config;
 
 /* counters and device timings of the last nfcb200_decode_batch call */

@@ -39,7 +39,7 @@ class CConfig(C.Structure):
         ("device", C.c_int), ("enabled", C.c_uint32), ("power_level_threshold", C.c_float),
         ("correlation_threshold", C.c_float * 4), ("modulation_min", C.c_float * 4), ("modulation_max", C.c_float * 4),
         ("stream_time", C.c_uint32), ("use_tma", C.c_uint32), ("max_rounds", C.c_uint32), ("segments_per_lane", C.c_uint32),
-        ("reserved", C.c_uint32 * 4),
+        ("exact", C.c_uint32), ("reserved", C.c_uint32 * 3),
     ]
 
 
@@ -126,13 +126,14 @@ _SIG_DTYPE = {SIG_IQ_F32: (np.float32, 2), SIG_MAG_F32: (np.float32, 1), SIG_MAG
 class NfcDecoder:
     """GPU decoder handle.  Method names follow lab::NfcDecoder; batch decoding is the B200-native addition."""
 
-    def __init__(self, device=0, use_tma=True, segments_per_lane=0):
+    def __init__(self, device=0, use_tma=True, segments_per_lane=0, exact=False):
         self._lib = load_library()
         self._cfg = CConfig()
         self._lib.nfcb200_config_default(C.byref(self._cfg))
         self._cfg.device = device
         self._cfg.use_tma = 1 if use_tma else 0
         self._cfg.segments_per_lane = segments_per_lane
+        self._cfg.exact = 1 if exact else 0
         self._h = C.c_void_p()
         _check(self._lib, self._lib.nfcb200_create(C.byref(self._cfg), C.byref(self._h)))
         self._rate = 0

@@ -179,6 +179,19 @@ NFC_HD SumChain sum_chain(const Params &P, u32 d)
    return c;
 }
 
+// index of the highest set bit (v != 0)
+NFC_HD u32 high_bit(u32 v)
+{
+#if defined(__CUDA_ARCH__)
+   return 31u - (u32) __clz((int) v);
+#else
+   u32 h = 31;
+   while (!((v >> h) & 1u))
+      h--;
+   return h;
+#endif
+}
+
 // (ph + m) mod p for ph < p without a division (m is at most a few periods)
 NFC_HD u32 wrap_add(u32 ph, u32 m, u32 p)
 {
@@ -333,7 +346,8 @@ struct WLane
             if (!(P.enabled & c.tech))
                continue;
             const u32 ph0 = phase_of(d);
-            for (u32 a = 1 + W::lane(); a <= m; a += W::width())
+      #pragma unroll 1
+      for (u32 a = 1 + W::lane(); a <= m; a += W::width())
                rg[c.corr + wrap_add(ph0, a, c.p1)] = sh.lin[d][a];
          }
       }
@@ -384,6 +398,7 @@ struct WLane
       u32 cut = rem; // samples [0, cut) of the span are event-free and share regime0
       u32 below = 0; // bit a-1: |w| < low threshold (edge peak reset)
 
+#pragma unroll 1
       for (u32 a = 1 + W::lane(); a <= rem; a += W::width())
       {
          const u32 ka = k + a;
@@ -421,7 +436,8 @@ struct WLane
          // ---- trigger conditions, one sample per thread --------------------------------------------------------------
          u32 first = cut + 1; // first a whose sample must go to the machine
 
-         for (u32 a = 1 + W::lane(); a <= cut; a += W::width())
+   #pragma unroll 1
+      for (u32 a = 1 + W::lane(); a <= cut; a += W::width())
          {
             const u32 ka = k + a;
             const float env = rg[NFCB200_OFF_M + slot(ka, 0)];
@@ -517,8 +533,8 @@ struct WLane
    NFC_HD void edge_span(u32 k, u32 clk, u32 m)
    {
       u32 hi = 0, lo = 0;
-      float mine = 0;
 
+#pragma unroll 1
       for (u32 a = 1 + W::lane(); a <= m; a += W::width())
       {
          const float rect = fabsf(rg[NFCB200_OFF_W + slot(k + a, 0)]);
@@ -542,23 +558,15 @@ struct WLane
       }
 
       // the stretch that holds the last sample above the high threshold
-      u32 h = 31;
-      while (!((hi >> h) & 1u))
-         h--;
+      const u32 h = high_bit(hi);
       const u32 loBelow = lo & ((1u << h) - 1u);
-      u32 segStart = 0; // first bit of that stretch
-      if (loBelow)
-      {
-         segStart = 31;
-         while (!((loBelow >> segStart) & 1u))
-            segStart--;
-         segStart++;
-      }
+      const u32 segStart = loBelow ? high_bit(loBelow) + 1 : 0; // first bit of that stretch
       const u32 segMask = hi & ~((1u << segStart) - 1u);
       const bool firstSeg = loBelow == 0;
-      const bool resetAfter = (lo >> h) > 1u || ((lo >> h) & ~1u) != 0;
+      const bool resetAfter = (lo >> h) > 1u; // bit h of lo is clear (the sample is above the high threshold)
 
       u32 best = 0;
+#pragma unroll 1
       for (u32 a = 1 + W::lane(); a <= m; a += W::width())
          if ((segMask >> (a - 1)) & 1u)
          {
@@ -568,6 +576,7 @@ struct WLane
       best = W::max_u32(best);
 
       u32 firstAt = 0xFFFFFFFFu;
+#pragma unroll 1
       for (u32 a = 1 + W::lane(); a <= m; a += W::width())
          if (((segMask >> (a - 1)) & 1u) && float_bits(fabsf(rg[NFCB200_OFF_W + slot(k + a, 0)])) == best && a < firstAt)
             firstAt = a;
@@ -589,7 +598,6 @@ struct WLane
          }
          F.edgePeak = resetAfter ? 0.0f : peak;
       }
-      (void) mine;
    }
 
    // ring writes, running sum and clocks of m samples of a LOCKED NFC-A decoder (rate r): only its own sum moved
@@ -597,6 +605,7 @@ struct WLane
    {
       const RateParams &b = P.A[r];
       const u32 ph0 = F.cA[r];
+#pragma unroll 1
       for (u32 a = 1 + W::lane(); a <= m; a += W::width())
          rg[b.corr + wrap_add(ph0, a, b.p1)] = sh.lin[r][a];
 
@@ -637,6 +646,7 @@ struct WLane
    // w^2 * 10 of the span's samples into the integration ring (NfcA.cpp:963, 1118)
    NFC_HD void integrate_w2(u32 sdd, u32 cnt)
    {
+#pragma unroll 1
       for (u32 a = 1 + W::lane(); a <= cnt; a += W::width())
       {
          const u32 s = slot(F.k + a, sdd);
@@ -682,6 +692,7 @@ struct WLane
       float mySd = 0, myS0 = 0, myS1 = 0;
       bool myCand = false;
 
+#pragma unroll 1
       for (u32 a = 1 + W::lane(); a <= cnt; a += W::width())
       {
          const u32 ca = clk + a;
@@ -730,7 +741,8 @@ struct WLane
          {
             // first sample that attains the maximum
             u32 firstAt = 0xFFFFFFFFu;
-            for (u32 a = 1 + W::lane(); a <= cnt; a += W::width())
+      #pragma unroll 1
+      for (u32 a = 1 + W::lane(); a <= cnt; a += W::width())
             {
                const u32 ca = clk + a;
                if (ca < start)
@@ -806,6 +818,7 @@ struct WLane
       const bool second = m.symbolStartTime != 0;
       u32 first = cnt + 1;
 
+#pragma unroll 1
       for (u32 a = 1 + W::lane(); a <= cnt; a += W::width())
       {
          const u32 ca = clk + a;
@@ -838,7 +851,7 @@ struct WLane
    // an idle stretch [pos, target), sums alone: no features exist there and nothing else can move (the correlation
    // rings are not maintained: the lane re-enters the features NFCB200_LEAD samples before the next active block and
    // refills them before its detectors open)
-   NFC_HD void walk_generic(u32 pos, u32 target)
+   NFC_HDN void walk_generic(u32 pos, u32 target)
    {
       while (pos < target)
       {
@@ -873,7 +886,7 @@ struct WLane
    //    crosses into the next binade often enough) -> the stretch is walked with the sums alone; 0: cannot tell, keep stepping.
    // The level test uses the block means of the screening pass: an inactive block holds no level shift (nfc_decode.cuh
    // segment_flags_kernel), so its mean is the envelope to within the noise.
-   NFC_HD int gap_class(u32 ta, u32 gs) const
+   NFC_HDN int gap_class(u32 ta, u32 gs) const
    {
       const u32 lookback = P.V.sdd + P.V.p2 + 8;
       const u32 b0 = (ta > lookback ? ta - lookback : 0) / NFCB200_BLOCK, b1 = gs / NFCB200_BLOCK;
@@ -896,7 +909,7 @@ struct WLane
    }
 
    // change of the six window sums between ta and gs - 1 (exact: gap_class == 1)
-   NFC_HD void gap_delta(u32 ta, u32 gs)
+   NFC_HDN void gap_delta(u32 ta, u32 gs)
    {
       for (u32 d = 0; d < 6; d++)
       {
@@ -943,7 +956,7 @@ struct WLane
       sh.n = n;
    }
 
-   NFC_HD void control(const LaneRec &R, u32 nsamples)
+   NFC_HDN void control(const LaneRec &R, u32 nsamples)
    {
       const u32 pos = sh.pos;
 

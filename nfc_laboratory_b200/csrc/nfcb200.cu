@@ -171,11 +171,12 @@ struct nfcb200_handle
    cudaEvent_t ev[12] = {};
 
    int wlanesPerSm = 7; // resident warp lanes per SM (shared memory: sizeof(WLaneSmem) each)
+   int laneBlocks = 4;  // resident thread-lane blocks per SM (lanes_kernel __launch_bounds__)
    int shortHalo = 1;   // NFCB200_HALO_SHORT=0 forces the long warm-up for every segment (measurement knob)
 
    HostBuf hRecs, hExt, hMeta, hStreamOf; // gather staging
 
-   DevBuf samples, flags, bsum, counts, offsets, segCounts, segOffsets, segs, feats, lanes, queue, pool, ext, meta, streamOf, counters;
+   DevBuf samples, flags, bsum, counts, offsets, segCounts, segOffsets, segs, feats, lanes, queue, scratch, sbuf, pool, ext, meta, streamOf, counters;
    nfcb200_stats stats;
 
    // last batch geometry (for the flag tap)
@@ -408,7 +409,7 @@ void nfcb200_destroy(nfcb200_handle *h)
       return;
    cudaSetDevice(h->device);
    cudaStreamSynchronize(h->stream);
-   DevBuf *bufs[] = {&h->samples, &h->flags, &h->bsum, &h->counts, &h->offsets, &h->lanes, &h->queue, &h->segCounts, &h->segOffsets, &h->segs, &h->feats, &h->pool, &h->ext, &h->meta,
+   DevBuf *bufs[] = {&h->samples, &h->flags, &h->bsum, &h->counts, &h->offsets, &h->lanes, &h->queue, &h->segCounts, &h->segOffsets, &h->segs, &h->feats, &h->scratch, &h->sbuf, &h->pool, &h->ext, &h->meta,
                      &h->streamOf, &h->counters, &h->sState, &h->sScratch, &h->sSbuf, &h->sSamples, &h->sFlags, &h->sBsum, &h->sCounts};
    for (DevBuf *b: bufs)
       b->release();
@@ -591,25 +592,33 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       CUDA_TRY(cudaGetLastError());
    }
 
-   // Lanes.  On float input ONE lane decodes the whole stream: the detectors' running sums carry their rounding history
-   // (NfcA.cpp:246-250), which only a run over the whole capture reproduces bit for bit (nfc_wlane.h).  16-bit mono input
-   // adds exactly whatever the history, so a stream may be cut into several lanes (cold starts + carry chain): as many as
-   // fill the machine a few times over, no more (every lane boundary costs a speculation).
+   // Lanes.  Exact mode: ONE warp lane decodes the whole stream -- the detectors' running sums carry their rounding history
+   // (NfcA.cpp:246-250), which only a run over the whole capture reproduces bit for bit (nfc_wlane.h).  Throughput mode:
+   // thread lanes, one per group of segments, cold-started sums (exact on 16-bit input), as many lanes as fill the machine a
+   // few times over (every lane pays a warm-up halo; longer lanes keep more of the carry chain inside one sequential run).
+   const bool exact = h->cfg.exact != 0;
    u32 segTotal = 0;
    CUDA_TRY(cudaMemcpyAsync(&segTotal, &dC->segTotal, sizeof(u32), cudaMemcpyDeviceToHost, st));
    CUDA_TRY(cudaMemcpyAsync(h->segCounts.ptr, h->counts.ptr, (size_t) n_streams * sizeof(u32), cudaMemcpyDeviceToDevice, st));
    CUDA_TRY(cudaStreamSynchronize(st));
    {
-      const uint64_t resident = (uint64_t) h->smCount * (uint64_t) h->wlanesPerSm;
-      u32 group = 0xFFFFFFFFu; // one lane per stream
+      u32 group;
       if (h->cfg.segments_per_lane)
          group = h->cfg.segments_per_lane;
-      else if (sigtype == SIG_MAG_S16 && (uint64_t) n_streams < resident * 2)
-         group = (u32) std::max<uint64_t>(1, segTotal / (resident * 2));
+      else if (exact)
+         group = 0xFFFFFFFFu; // one lane per stream
+      else
+      {
+         const uint64_t residentLanes = (uint64_t) h->smCount * (uint64_t) h->laneBlocks * (LANE_THREADS / 32) * 32;
+         group = (u32) std::min<uint64_t>(64, std::max<uint64_t>(1, segTotal / std::max<uint64_t>(1, residentLanes * 2)));
+      }
       sg.group = group;
-      segment_group_kernel<<<sgrid, 64, 0, st>>>(sg);
-      launches++;
-      CUDA_TRY(cudaGetLastError());
+      if (group > 1)
+      {
+         segment_group_kernel<<<sgrid, 64, 0, st>>>(sg);
+         launches++;
+         CUDA_TRY(cudaGetLastError());
+      }
    }
    S.segments = segTotal;
    tr.mark("screen + segments");
@@ -660,13 +669,13 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    CUDA_TRY(cudaMemcpyAsync(&featTotal, &dC->featTotal, sizeof(featTotal), cudaMemcpyDeviceToHost, st));
    CUDA_TRY(cudaStreamSynchronize(st));
    {
-      int rc = h->feats.reserve((size_t) std::max<unsigned long long>(featTotal, 1) * sizeof(float4));
+      int rc = h->feats.reserve((size_t) std::max<unsigned long long>(exact ? featTotal : 0, 1) * sizeof(float4));
       if (rc)
          return rc;
    }
    S.feature_samples = featTotal;
    cudaEventRecord(h->ev[8], st);
-   if (nSegs)
+   if (nSegs && exact)
    {
       FrontConfig fc;
       fc.samples = dSamples;
@@ -740,11 +749,44 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       if (rounds >= maxRounds)
          return fail(NFCB200_ERR_CAPACITY, "carry chain did not converge in %u rounds", maxRounds);
 
-      const u32 blocks = std::min(maxWarps, queueCount);
-      lc.queue_count = queueCount;
-
       CUDA_TRY(cudaMemsetAsync(&dC->cursor, 0, sizeof(u32), st));
-      wlanes_kernel<<<blocks, 32, sizeof(WLaneSmem), st>>>(lc, h->P);
+
+      if (exact)
+      {
+         const u32 blocks = std::min(maxWarps, queueCount);
+         lc.queue_count = queueCount;
+         wlanes_kernel<<<blocks, 32, sizeof(WLaneSmem), st>>>(lc, h->P);
+      }
+      else
+      {
+         const u32 warpsPerBlock = LANE_THREADS / 32;
+         const u32 maxThreadWarps = (u32) h->smCount * (u32) h->laneBlocks * warpsPerBlock; // the kernel is persistent
+         u32 warps = std::min(maxThreadWarps, (queueCount + 31) / 32);
+         const u32 blocks = (warps + warpsPerBlock - 1) / warpsPerBlock;
+         warps = blocks * warpsPerBlock;
+
+         int rc = h->scratch.reserve((size_t) warps * NFCB200_SCRATCH_FLOATS * 32 * sizeof(float));
+         rc = rc ? rc : h->sbuf.reserve((size_t) warps * 32 * 512);
+         if (rc)
+            return rc;
+
+         LaneConfig tc;
+         memset(&tc, 0, sizeof(tc));
+         tc.samples = dSamples;
+         tc.n_samples = n_samples;
+         tc.sigtype = sigtype;
+         tc.flags = h->flags.as<uint8_t>();
+         tc.n_blocks = n_blocks;
+         tc.lanes = h->lanes.as<LaneRec>();
+         tc.queue = h->queue.as<u32>();
+         tc.queue_count = queueCount;
+         tc.cursor = &dC->cursor;
+         tc.scratch = h->scratch.as<float>();
+         tc.sbuf = h->sbuf.as<uint8_t>();
+         tc.pool = pool;
+         tc.work = &dC->work;
+         lanes_kernel<<<blocks, LANE_THREADS, 0, st>>>(tc, h->P);
+      }
       launches++;
       CUDA_TRY(cudaGetLastError());
 
@@ -775,7 +817,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    CUDA_TRY(cudaStreamSynchronize(st));
 
    S.lane_samples = hc.work;
-   if (tr.on)
+   if (tr.on && exact)
    {
       static const char *names[8] = {"control", "fill", "search", "machine", "walk", "jump", "scalar", "locked"};
       unsigned long long tot = 0;

@@ -8,7 +8,8 @@ import nfcutil as U
 import nfc_laboratory_b200 as N
 from test_golden_oracle import committed_ref
 
-d = N.NfcDecoder()
+exact = os.environ.get("PROBE_EXACT") == "1"
+d = N.NfcDecoder(exact=exact)
 names = U.fixture_names()
 if len(sys.argv) > 1:
     names = names[: int(sys.argv[1])]
