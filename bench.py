@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle spot check of the cpu_baseline leg")
+    ap.add_argument("--no-full-parity", action="store_true", help="skip the full-size differential against the reference (cpu_baseline leg, untimed)")
+    ap.add_argument("--parity-budget", type=float, default=120.0, help="seconds the full-size differential may take")
+    ap.add_argument("--exact", action="store_true", help="decode with one warp lane per stream (exact float state, slower)")
     ap.add_argument("--quick", action="store_true", help="small batch for smoke runs (64 streams x 2e6)")
     return ap.parse_args()
 
@@ -189,6 +192,62 @@ def cpu_reference_run(iq_host, threads):
     return S * n / sec / 1e6, int(frames.value)
 
 
+def full_parity(frames, iq, S, n, threads, budget_s=90.0, chunk_streams=32):
+    """full-size differential against the reference: EVERY stream of the batch is decoded by the reference's own CPU
+    decoder (oracle/_ref, `threads` host threads, IQ -> magnitude included) and compared frame for frame -- every field
+    RawFrame::operator== compares plus the payload, through one 64-bit hash per frame -- with the frames the GPU returned.
+    Part of the cpu_baseline leg (untimed).  Stops early when the time budget is spent and says how far it got."""
+    try:
+        import torch
+        import nfcutil as U
+        from nfc_laboratory_b200 import dist as ND
+        lib = U.ref_lib()
+        if lib is None:
+            return None
+        lib.nfcref_hash_batch.restype = C.c_double
+        lib.nfcref_hash_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]
+        hashes = ND.frame_hashes(frames)
+        streams = frames["stream"].astype(np.int64)
+        first = np.searchsorted(streams, np.arange(S + 1))   # frames are ordered by (stream, time)
+        cap = int(max(64, (first[1:] - first[:-1]).max() * 2))
+        try:
+            host = torch.empty((chunk_streams, n, 2), dtype=torch.float32, pin_memory=True)
+        except Exception:
+            host = torch.empty((chunk_streams, n, 2), dtype=torch.float32)
+        rh = np.zeros(chunk_streams * cap, dtype=np.uint64)
+        rc = np.zeros(chunk_streams, dtype=np.uint32)
+        t0 = time.perf_counter()
+        res = {"streams": 0, "frames": 0, "reference_frames": 0, "differing": 0, "streams_differing": 0, "first_diff": None, "reference_seconds": 0.0}
+        for c0 in range(0, S, chunk_streams):
+            c1 = min(S, c0 + chunk_streams)
+            host[:c1 - c0].copy_(iq[c0:c1])
+            if iq.is_cuda:
+                torch.cuda.synchronize()
+            res["reference_seconds"] += float(lib.nfcref_hash_batch(None, host.data_ptr(), n, c1 - c0, RATE, 65536, threads, rh.ctypes.data, cap, rc.ctypes.data))
+            for s_ in range(c0, c1):
+                mine = hashes[first[s_]:first[s_ + 1]]
+                k = int(rc[s_ - c0])
+                ref = rh[(s_ - c0) * cap:(s_ - c0) * cap + min(k, cap)]
+                m = min(mine.size, ref.size)
+                bad = int((mine[:m] != ref[:m]).sum()) + abs(int(mine.size) - k)
+                res["frames"] += int(mine.size)
+                res["reference_frames"] += k
+                if bad:
+                    res["differing"] += bad
+                    res["streams_differing"] += 1
+                    if res["first_diff"] is None:
+                        idx = int(np.argmax(mine[:m] != ref[:m])) if m and (mine[:m] != ref[:m]).any() else m
+                        res["first_diff"] = {"stream": int(s_), "frame_index": idx, "gpu_frames": int(mine.size), "reference_frames": k}
+            res["streams"] = c1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        res["complete"] = res["streams"] == S
+        res["seconds"] = time.perf_counter() - t0
+        return res
+    except Exception as e:  # a diagnostic must not cost the run its number
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def workload_name(workload, S, n, bytes_per_step):
     """config.workload: the same text for both arms (the reference arm times a bounded sample of it, named in config.sample)"""
     return "%s: %d synthetic 10 MS/s x %.1f s float2 IQ streams per GPU (BASELINE.json configs[1] shape), input %.1f GB per GPU, " \
@@ -310,19 +369,29 @@ def main():
     synth.synth_batch(args.workload, S, n, seed=args.seed + 1000 * rank, device=dev, out=iq)
     torch.cuda.synchronize()
 
-    dec = N.NfcDecoder(device=local)
+    dec = N.NfcDecoder(device=local, exact=args.exact)
     cap = max(1 << 16, S * (n // 12000 + 64))
 
     def step_device():
         buf, nf = dec.decode_batch_ptr(iq.data_ptr(), True, N.SIG_IQ_F32, S, n, RATE, cap=cap, raw=True)
         return buf, nf
 
+    gather_ms = {"gather_pack": [], "gather_nccl": [], "gather_d2h": []}
+
     def gather(buf, nf):
+        """frames of all ranks on rank 0.  GPUs: the packed device records of the decode go to rank 0 over NCCL point to point
+        (no host round trip on the senders); CPU flow test: the host wire format over gloo"""
         if world == 1:
             return nf
-        flat = ND.pack_frames(ND.frames_as_array(buf, nf), stream_offset=rank * S)
-        allf = ND.gather_frames(flat, dev)
-        return nf if allf is None else ND.count_frames(allf)
+        if flow_test or not hasattr(dec, "device_frames"):
+            flat = ND.pack_frames(ND.frames_as_array(buf, nf), stream_offset=rank * S)
+            allf = ND.gather_frames(flat, dev)
+            return nf if allf is None else ND.count_frames(allf)
+        tm = {}
+        g = ND.gather_device_frames(dec, dev, lambda r: r * S, RATE, timings=tm)
+        for k in gather_ms:
+            gather_ms[k].append(tm.get(k, 0.0))
+        return nf if g is None else nf + g.count
 
     parity = None  # set by the cpu_baseline leg (the only place this arm touches the oracle)
 
@@ -360,6 +429,14 @@ def main():
     dt = float(tmax.item())
 
     clocks = sampler.summary() if rank == 0 else None
+
+    # frame gather phases of the timed steps, max over ranks (the last gather_steps entries: warm-up and e2e gathers excluded)
+    gather_phases = {}
+    if world > 1 and gather_ms["gather_nccl"]:
+        vals = torch.tensor([statistics.mean(gather_ms[k][len(gather_ms[k]) - args.steps:]) for k in ("gather_pack", "gather_nccl", "gather_d2h")],
+                            dtype=torch.float64, device=dev)
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        gather_phases = {"gather_pack": float(vals[0]), "gather_nccl": float(vals[1]), "gather_d2h": float(vals[2])}
 
     value = world * S * n * args.steps / dt / 1e6
 
@@ -423,6 +500,7 @@ def main():
     # ---- CPU baseline: the reference decoder on this box's cores, bounded sample of the same batch -------------------------
     cpu = None
     fullcheck = None
+    fullparity = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = host_cores()
         Sc = min(S, max(cores, min(2 * cores, 32)))
@@ -446,6 +524,8 @@ def main():
                 raise SystemExit("parity check against the reference oracle FAILED: refusing to report a number")
         if v is not None and frames_last is not None:
             fullcheck = full_size_check(frames_last, S, n, args.workload, args.seed + 1000 * rank, iq)
+        if v is not None and frames_last is not None and not args.no_full_parity:
+            fullparity = full_parity(frames_last, iq, S, n, cores, budget_s=args.parity_budget)
         if v is not None:
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
                    "sample": "%d of the batch's streams x %d samples, one NfcDecoder per host thread on %d threads, IQ->magnitude included" % (Sc, nc, cores)}
@@ -457,7 +537,8 @@ def main():
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.workload, S, n, bytes_per_step),
-                       "streams_per_gpu": S, "samples_per_stream": n, "sample_rate": RATE, "sharding": "streams, block partition, NCCL frame gather" if world > 1 else "single GPU"},
+                       "streams_per_gpu": S, "samples_per_stream": n, "sample_rate": RATE, "sharding": "streams, block partition, NCCL frame gather (packed device records, point to point to rank 0)" if world > 1 else "single GPU",
+                       "lanes": "warp lanes, one per stream, exact float state" if args.exact else "thread lanes, cold-started running sums"},
             "e2e": e2e,
             "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -465,10 +546,12 @@ def main():
                          "algorithmic_bytes_per_launch": bytes_per_step, "ms_per_launch": ms_screen},
             "cpu_baseline": cpu,
             "clocks": clocks,
-            "phases_ms": {k: statistics.mean(s[k] for s in stats) for k in ("ms_screen", "ms_segment", "ms_lanes", "ms_gather", "ms_total", "ms_wall")},
+            "phases_ms": dict({k: statistics.mean(s[k] for s in stats) for k in ("ms_screen", "ms_segment", "ms_lanes", "ms_gather", "ms_total", "ms_wall")},
+                              **gather_phases),
             "decode": {"frames_per_step": frames_total // max(1, args.steps), "segments": st["segments"], "lanes": st["lanes"], "rounds": st["rounds"],
                        "lane_runs": st["lane_runs"], "lane_samples_frac": st["lane_samples"] / max(1, st["samples"])},
             "parity_spot_check": parity, "frames_digest": "%016x" % digest_resident, "full_size_check": fullcheck,
+            "full_parity": fullparity,
         }
         print(json.dumps(line))
 

@@ -151,6 +151,17 @@ int nfcb200_get_stats(nfcb200_handle *h, nfcb200_stats *stats);
 int nfcb200_get_block_flags(nfcb200_handle *h, uint8_t *out, uint64_t cap, uint64_t *n_blocks_per_stream);
 
 /*
+ * Multi-GPU frame gather (no counterpart in the reference, which has no second device): the frames of the
+ * last nfcb200_decode_batch call as they sit in DEVICE memory -- ordered by (stream, time), 128-byte records (stream,
+ * header fields, the first 80 payload bytes) plus 128-byte extension chunks for longer payloads -- so that a rank can hand
+ * them to NCCL without a host round trip; nfcb200_emit_records converts gathered records (host memory) into ABI frames
+ * on the receiving rank, adding stream_offset to the stream index.  The pointers stay valid until the next decode.
+ */
+int nfcb200_device_frames(nfcb200_handle *h, const void **records, uint64_t *n_records, const void **ext, uint64_t *n_ext_chunks);
+int nfcb200_emit_records(nfcb200_handle *h, const void *records, uint64_t n_records, const void *ext, uint64_t n_ext_chunks, uint32_t stream_offset,
+                         uint32_t sample_rate, nfcb200_frame *out, uint64_t cap, uint64_t *n_out);
+
+/*
  * Wire format of the multi-GPU frame gather (no reference counterpart: the reference is one decoder per process).
  * Writes [u64 count][count x 80-byte frame headers, stream index raised by stream_offset][payload bytes back to back]
  * to `out`; *n_bytes is the size needed (call with out == NULL to size the buffer).  Host-only, no CUDA call.

@@ -76,7 +76,7 @@ class Frame(tuple):
 EXPORTS = [
     "nfcb200_config_default", "nfcb200_create", "nfcb200_destroy", "nfcb200_configure", "nfcb200_decode_batch",
     "nfcb200_stream_push", "nfcb200_stream_reset", "nfcb200_get_stats", "nfcb200_get_block_flags", "nfcb200_pack_frames",
-    "nfcb200_last_error", "nfcb200_version",
+    "nfcb200_last_error", "nfcb200_version", "nfcb200_device_frames", "nfcb200_emit_records",
 ]
 
 
@@ -111,6 +111,9 @@ def load_library():
     lib.nfcb200_get_stats.argtypes = [C.c_void_p, C.POINTER(CStats)]
     lib.nfcb200_get_block_flags.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.nfcb200_pack_frames.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.nfcb200_device_frames.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.nfcb200_emit_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(CFrame),
+                                         C.c_uint64, C.POINTER(C.c_uint64)]
     _lib = lib
     return lib
 
@@ -237,6 +240,22 @@ class NfcDecoder:
                 continue
             _check(self._lib, rc)
             return (buf, n.value) if raw else self._convert(buf, n.value)
+
+    def device_frames(self):
+        """(records_ptr, n_records, ext_ptr, n_ext_chunks): the frames of the last decode_batch as they sit in device memory,
+        ordered by (stream, time) -- 128-byte records + 128-byte payload extension chunks (include/nfcb200.h)"""
+        rp, ep = C.c_void_p(), C.c_void_p()
+        n, ne = C.c_uint64(0), C.c_uint64(0)
+        _check(self._lib, self._lib.nfcb200_device_frames(self._h, C.byref(rp), C.byref(n), C.byref(ep), C.byref(ne)))
+        return rp.value or 0, int(n.value), ep.value or 0, int(ne.value)
+
+    def emit_records(self, records_ptr, n_records, ext_ptr, n_ext_chunks, stream_offset, sample_rate, raw=False):
+        """gathered device-format records (HOST memory) -> frames, stream index raised by stream_offset"""
+        buf = (CFrame * max(1, n_records))()
+        n = C.c_uint64(0)
+        _check(self._lib, self._lib.nfcb200_emit_records(self._h, C.c_void_p(records_ptr), n_records, C.c_void_p(ext_ptr), n_ext_chunks,
+                                                         int(stream_offset), int(sample_rate), buf, max(1, n_records), C.byref(n)))
+        return (buf, int(n.value)) if raw else self._convert(buf, int(n.value))
 
     def decode_batch(self, samples, sigtype, sample_rate, cap=1 << 16):
         """samples: numpy array [n_streams, n_samples(, 2)] or torch CUDA tensor of the same shape"""

@@ -48,6 +48,7 @@ struct LaneRec
    u32 lcWritten, lcLive, fZeroed, fThrWritten, fThrRead;
    u32 fInc0[2];
    float fThrSync[2];
+   u32 edgeWritten, edgeLive;
    u32 seg0;       // index of the lane's first segment in the segment table (nfc_wlane.h)
    Carry in;       // carry the last run started from
    Carry out;      // canonical carry the last run retired with
@@ -201,12 +202,14 @@ NFC_HD bool lane_iterate(MACH &M, Lane &L, const Params &P, u32 &pos, u32 end, u
       if (begin > pos + NFCB200_HALO)
       {
          Carry carry = L.c;
+         carry.edgeTime = L.fe.edgeTime;
          carry_canon(carry);
          // what the run has recorded so far about its use of the INCOMING carry (chain_walk reads it) survives the restart:
          // the run goes on from its own exact carry, it does not start a new dependency history
          const u32 locked = L.lockedMask, lcWritten = L.lcWritten, lcLive = L.lcLive, fZeroed = L.fZeroed, fThrWritten = L.fThrWritten,
                    fThrRead = L.fThrRead, fInc00 = L.fInc0[0], fInc01 = L.fInc0[1];
          const float fThrSync0 = L.fThrSync[0], fThrSync1 = L.fThrSync[1];
+         const u32 edgeWritten = L.edgeWritten, edgeLive = L.edgeLive;
          u32 target = begin - NFCB200_HALO;
          zero();
          lane_begin(L, P, carry, target, NFCB200_HALO);
@@ -220,6 +223,8 @@ NFC_HD bool lane_iterate(MACH &M, Lane &L, const Params &P, u32 &pos, u32 end, u
          L.fInc0[1] = fInc01;
          L.fThrSync[0] = fThrSync0;
          L.fThrSync[1] = fThrSync1;
+         L.edgeWritten = edgeWritten;
+         L.edgeLive = edgeLive;
          L.fe.kbase = kw;
          M.reload_front();
          pos = target;
@@ -238,6 +243,7 @@ NFC_HD void lane_record(LaneRec &R, const Lane &L, u32 stop, u32 gen, u32 nframe
    R.stop = stop;
    R.lockedMask = L.lockedMask;
    R.out = L.c;
+   R.out.edgeTime = L.fe.edgeTime;
    carry_canon(R.out);
    R.gen = gen;
    R.dirty = 0;
@@ -251,6 +257,8 @@ NFC_HD void lane_record(LaneRec &R, const Lane &L, u32 stop, u32 gen, u32 nframe
    R.fInc0[1] = L.fInc0[1];
    R.fThrSync[0] = L.fThrSync[0];
    R.fThrSync[1] = L.fThrSync[1];
+   R.edgeWritten = L.edgeWritten;
+   R.edgeLive = L.edgeLive;
 }
 
 // word offsets inside Mod / TechSt used by the relaxed dependency rules
@@ -273,6 +281,7 @@ NFC_HD float u32_as_float(u32 v)
 // are shared by the scalar walk and by the warp-parallel device walk)
 struct LaneObs
 {
+   u32 edgeWritten, edgeLive;
    u32 lcWritten, lcLive, fZeroed, fThrWritten, fThrRead;
    u32 fInc0[2];
    float fThrSync[2];
@@ -281,6 +290,8 @@ struct LaneObs
 NFC_HD LaneObs lane_obs(const LaneRec &L)
 {
    LaneObs o;
+   o.edgeWritten = L.edgeWritten;
+   o.edgeLive = L.edgeLive;
    o.lcWritten = L.lcWritten;
    o.lcLive = L.lcLive;
    o.fZeroed = L.fZeroed;
@@ -309,6 +320,9 @@ NFC_HD bool word_observed_equal(const LaneObs &L, int g, u32 w, u32 a, u32 t)
 
    if (g >= 4 && g < 8 && w == 0)
       return !((L.lcLive >> (g - 4)) & 1);
+
+   if (g == 8 && w == 2) // carrier edge time: read only when a carrier frame is stamped, before the run's own first assignment
+      return !L.edgeLive;
 
    if (g == 2)
    {
@@ -358,6 +372,9 @@ NFC_HD u32 compose_word(const LaneObs &L, int g, u32 w, u32 n, u32 o, u32 i)
 {
    if (g >= 4 && g < 8 && w == 0)
       return ((L.lcWritten >> (g - 4)) & 1) ? o : n;
+
+   if (g == 8 && w == 2)
+      return L.edgeWritten ? o : n;
 
    if (g == 2)
    {

@@ -111,6 +111,8 @@ struct Carry
    TechSt t[4];
    u32 carrierOn;  // carrierOnTime  (0 = unset)
    u32 carrierOff; // carrierOffTime (0 = unset)
+   u32 edgeTime;   // carrierEdgeTime (NfcTech.cpp:77-92): the time of the last strong edge, however old, stamps the next carrier
+                   // frame (NfcDecoder.cpp:477, 502).  The working copy is Front::edgeTime; this is its value at lane boundaries
 };
 
 // front end (NfcDecoderStatus scalars, NfcTech.h:317-393) plus the rest of the state a lane touches on EVERY sample.
@@ -138,6 +140,8 @@ struct Front
    u32 lockRate;  // rate index of the locked modulation
    u32 gate;      // local steps during which the detectors are off (reference: signalClock < BUFFER_SIZE)
    u32 warm;      // local steps during which carrier detection is suppressed (cold-started lanes)
+   u32 edgeHold;  // local steps during which the carrier-edge tracker is off: the DC-removal filter of a cold-started front end
+                  // rings for a few samples (w starts at x), which is not an edge of the signal
    u32 gateSum;   // local steps before which not even the detectors' running sums advance (<= gate).  Between gateSum and
                   // gate only the sums and their correlation rings run (sums_only()): a lane that skipped an idle stretch with
                   // its sums carried exactly (nfc_wlane.h) refills the rings this way before its detectors open
@@ -159,6 +163,8 @@ struct Lane
    u32 fZeroed;    // bit r: NFC-F rate r searchPulseWidth was reset during this run (restart / reset / listen clear)
    u32 fThrWritten;// bit r: NFC-F rate r searchValueThreshold was assigned during this run
    u32 fThrRead;   // bit r: ... and was compared before any assignment, against fThrSync[r]
+   u32 edgeWritten;// the carrier edge time was assigned during this run (an edge, or the reset after a carrier frame)
+   u32 edgeLive;   // ... and a carrier frame read it before any assignment (the run depends on the carried value)
    u32 fInc0[2];   // `searchPulseWidth++ < 94` tests executed before the first reset (NfcF.cpp:307)
    float fThrSync[2];
 };
@@ -545,12 +551,16 @@ struct Machine
       Front &f = F;
       float rect = fabsf(w);
 
+      if (f.k <= f.edgeHold)
+         return;
+
       if (rect > P.highThr)
       {
          if (rect > f.edgePeak)
          {
             f.edgePeak = rect;
             f.edgeTime = f.clk;
+            L.edgeWritten = 1;
          }
       }
       else if (rect < P.lowThr)
@@ -624,6 +634,9 @@ struct Machine
       {
          if (!L.c.carrierOn)
          {
+            if (!L.edgeWritten)
+               L.edgeLive = 1;
+            L.edgeWritten = 1;
             L.c.carrierOn = f.edgeTime ? f.edgeTime : f.clk;
             emit(TT_Any, FT_CarrierOn, 0, PH_Carrier, 0, L.c.carrierOn, L.c.carrierOn, sb, 0);
             L.c.carrierOff = 0;
@@ -634,6 +647,9 @@ struct Machine
       {
          if (!L.c.carrierOff)
          {
+            if (!L.edgeWritten)
+               L.edgeLive = 1;
+            L.edgeWritten = 1;
             L.c.carrierOff = f.edgeTime ? f.edgeTime : f.clk;
             emit(TT_Any, FT_CarrierOff, 0, PH_Carrier, 0, L.c.carrierOff, L.c.carrierOff, sb, 0);
             L.c.carrierOn = 0;
@@ -3896,7 +3912,7 @@ NFC_HD void carry_group(Carry &c, int g, u32 *&ptr, u32 &words)
          break;
       case 8:
          ptr = &c.carrierOn;
-         words = 2;
+         words = 3;
          break;
       default:
          ptr = (u32 *) &c.t[g - 4];
@@ -3948,6 +3964,7 @@ NFC_HD void lane_begin(Lane &L, const Params &P, const Carry &carry, u32 first, 
 
    L.fe.clk = first - 1; // signalClock starts at -1 (NfcTech.h:338)
    L.fe.k = 0;
+   L.fe.edgeTime = carry.edgeTime;
 
    for (int r = 0; r < 3; r++)
       L.fe.cA[r] = P.A[r].c1 ? P.A[r].c1 - 1 : P.A[r].p1 - 1; // incremented before use
@@ -3962,6 +3979,7 @@ NFC_HD void lane_begin(Lane &L, const Params &P, const Carry &carry, u32 first, 
    // (longest period 378), while the front end alone converges over the rest of the halo
    L.fe.gate = (first && warm > NFCB200_RING + 512) ? warm - 512 : NFCB200_RING;
    L.fe.gateSum = L.fe.gate;
+   L.fe.edgeHold = first ? 64 : 0;
 }
 
 }

@@ -7,7 +7,7 @@
  *                      over one segment.  The 32 lanes of a warp step in lock step and address their history rings with
  *                      the same relative slot, so ring traffic is fully coalesced (scratch words interleaved by lane).
  *   chain_kernel     : one thread per stream; chain_walk() -> list of lanes whose speculated carry was wrong
- *   lane_meta_kernel : compact (generation, dead) per lane for the host-side frame gather
+ *   frame_*_kernel   : frames of the final generation of the live lanes, ordered and packed on the device
  *   stream_kernel    : single-lane sequential decode for the streaming entry point (nfcb200_stream_push)
  *
  * No kernel here has a counterpart in the reference: the reference runs this logic on one CPU thread per stream.
@@ -864,7 +864,7 @@ __device__ __forceinline__ void carry_word_group(u32 w, int &g, u32 &wi)
 
 __global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_warp_kernel(ChainConfig c, const __grid_constant__ Params dP)
 {
-   static_assert(sizeof(Carry) == (8 * sizeof(Mod) + 4 * sizeof(TechSt) + 8), "carry groups must tile the Carry");
+   static_assert(sizeof(Carry) == (8 * sizeof(Mod) + 4 * sizeof(TechSt) + 12), "carry groups must tile the Carry");
 
    __shared__ u32 carry[CHAIN_WARPS][2][CARRY_WORDS];
 
@@ -990,16 +990,124 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_warp_kernel(ChainConfi
    }
 }
 
-// (generation << 1 | dead) per lane, plus the stream of the lane: what the host needs to gather frames
-__global__ void lane_meta_kernel(const LaneRec *lanes, uint32_t n, uint32_t *meta, uint32_t *streamOf, unsigned long long *liveCount)
+// length of every lane's own region + halo (the host orders the first-round queue by it: lanes of similar length share a
+// warp, long lanes start first)
+__global__ void lane_length_kernel(const LaneRec *lanes, uint32_t n, uint32_t *length)
 {
    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= n)
-      return;
-   meta[i] = (lanes[i].gen << 1) | (lanes[i].dead ? 1u : 0u);
-   streamOf[i] = lanes[i].stream;
-   if (!lanes[i].dead)
-      atomicAdd(liveCount, 1ull);
+   if (i < n)
+      length[i] = lanes[i].end - lanes[i].first;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// frame gather on the device: the frames of the final generation of the live lanes, ordered (stream, time), packed
+// ---------------------------------------------------------------------------------------------------------------------
+// Lanes are globally ordered by (stream, time) and a run numbers its frames 0 .. nframes-1, so the position of a frame is
+// a counting sort: offset[lane] + seq, offset = exclusive scan of the frame counts of the live lanes.
+
+// one block: exclusive scan of the lanes' frame counts (dead lanes count 0) -> laneOff[0 .. n], live lane count
+__global__ void __launch_bounds__(1024) frame_offsets_kernel(const LaneRec *lanes, uint32_t n, uint32_t *laneOff, unsigned long long *liveCount)
+{
+   __shared__ uint32_t warpSum[32];
+   __shared__ uint32_t carry;
+   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   uint32_t live = 0;
+
+   if (tid == 0)
+      carry = 0;
+   __syncthreads();
+
+   for (uint32_t base = 0; base < n; base += 1024)
+   {
+      const uint32_t i = base + tid;
+      uint32_t v = 0;
+      if (i < n && !lanes[i].dead)
+      {
+         v = lanes[i].nframes;
+         live++;
+      }
+      uint32_t incl = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
+      {
+         const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+         if ((int) lane >= d)
+            incl += o;
+      }
+      if (lane == 31)
+         warpSum[warp] = incl;
+      __syncthreads();
+      if (warp == 0)
+      {
+         uint32_t w = warpSum[lane];
+#pragma unroll
+         for (int d = 1; d < 32; d <<= 1)
+         {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, w, d);
+            if ((int) lane >= d)
+               w += o;
+         }
+         warpSum[lane] = w; // inclusive over warps
+      }
+      __syncthreads();
+      const uint32_t before = carry + (warp ? warpSum[warp - 1] : 0) + (incl - v);
+      if (i < n)
+         laneOff[i] = before;
+      __syncthreads();
+      if (tid == 1023)
+         carry = before + v;
+      __syncthreads();
+   }
+
+   if (tid == 0)
+      laneOff[n] = carry;
+
+   live = __reduce_add_sync(0xffffffffu, live);
+   if (lane == 0 && live)
+      atomicAdd(liveCount, (unsigned long long) live);
+}
+
+// scatter the kept records to their final position; `.lane` of a packed record holds the STREAM of the frame (offset by
+// streamBase), extension chunks are re-packed behind extBase
+__global__ void frame_compact_kernel(const FrameRec *pool, uint32_t nRecs, const LaneRec *lanes, uint32_t nLanes, const uint32_t *laneOff,
+                                     const u8 *ext, uint32_t extChunks, uint32_t streamBase, FrameRec *out, u8 *extOut, uint32_t extCap, uint32_t *extCount)
+{
+   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nRecs; i += gridDim.x * blockDim.x)
+   {
+      const FrameRec r = pool[i];
+      if (r.lane >= nLanes)
+         continue;
+      const LaneRec &L = lanes[r.lane];
+      if (L.dead || L.gen != r.gen || r.seq >= L.nframes)
+         continue;
+
+      FrameRec o = r;
+      o.lane = streamBase + L.stream;
+      o.ext = 0xFFFFFFFFu;
+
+      if (r.len > 80)
+      {
+         const uint32_t rest = r.len - 80, chunks = (rest + 127) / 128;
+         if (r.ext != 0xFFFFFFFFu && r.ext + chunks <= extChunks)
+         {
+            const uint32_t e = atomicAdd(extCount, chunks);
+            if (e + chunks <= extCap)
+            {
+               const uint4 *src = reinterpret_cast<const uint4 *>(ext + (size_t) r.ext * 128);
+               uint4 *dst = reinterpret_cast<uint4 *>(extOut + (size_t) e * 128);
+               for (uint32_t k = 0; k < chunks * 8; k++)
+                  dst[k] = src[k];
+               o.ext = e;
+            }
+            else
+               o.len = 80;
+         }
+         else
+            o.len = 80; // extension chunk missing (pool exhausted, reported by the caller): truncated payload
+      }
+
+      out[laneOff[r.lane] + r.seq] = o;
+   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1111,6 +1219,7 @@ __global__ void stream_kernel(StreamConfig c, const __grid_constant__ Params dP)
          if (pos >= noParkBefore && !active(pos) && M.dormant())
          {
             S.carry = L.c;
+            S.carry.edgeTime = L.fe.edgeTime;
             carry_canon(S.carry);
             running = 0;
             contig = 1;

@@ -408,12 +408,12 @@ struct WLane
          const float avg = sh.cavg[j + a - 1];
          const u32 regime = (ka - 1 < gateSum || env < P.power) ? 0 : (ka - 1 < gate ? 1 : 2);
          bool ev = regime != regime0;
-         ev |= rect > P.highThr;
+         ev |= rect > P.highThr && ka > F.edgeHold;
          if (ka > warm)
             ev |= (avg > P.highThr && !carrierOn) || (!(avg > P.highThr) && avg < P.lowThr && !carrierOff);
          if (ev && a - 1 < cut)
             cut = a - 1;
-         if (rect < P.lowThr)
+         if (rect < P.lowThr && ka > F.edgeHold)
             below |= 1u << (a - 1);
       }
 
@@ -538,6 +538,8 @@ struct WLane
       for (u32 a = 1 + W::lane(); a <= m; a += W::width())
       {
          const float rect = fabsf(rg[NFCB200_OFF_W + slot(k + a, 0)]);
+         if (k + a <= F.edgeHold)
+            continue;
          if (rect > P.highThr)
             hi |= 1u << (a - 1);
          else if (rect < P.lowThr)
@@ -1131,6 +1133,7 @@ struct WLane
                }
                F.gate = F.k + (sh.jumpG - T);
                F.warm = F.k + (sh.jumpB - T);
+               F.edgeHold = F.k + 64; // the features it enters may start with the front pass's cold-start transient
                F.closed = 64;
                sh.si = sh.jumpSeg;
                sh.mode = WMODE_FEAT;

@@ -74,6 +74,28 @@ struct DevBuf
       return 0;
    }
 
+   // grow, preserving the first `keep` bytes (the packed frames of the earlier chunks of one call)
+   int reserve_keep(size_t bytes, size_t keep, cudaStream_t st)
+   {
+      if (bytes <= cap)
+         return 0;
+      size_t want = bytes + bytes / 2 + 256;
+      void *np = nullptr;
+      cudaError_t e = cudaMalloc(&np, want);
+      if (e != cudaSuccess)
+         return fail(NFCB200_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+      if (ptr && keep)
+      {
+         cudaMemcpyAsync(np, ptr, keep, cudaMemcpyDeviceToDevice, st);
+         cudaStreamSynchronize(st);
+      }
+      if (ptr)
+         cudaFree(ptr);
+      ptr = np;
+      cap = want;
+      return 0;
+   }
+
    void release()
    {
       if (ptr)
@@ -174,9 +196,13 @@ struct nfcb200_handle
    int laneBlocks = 4;  // resident thread-lane blocks per SM (lanes_kernel __launch_bounds__)
    int shortHalo = 1;   // NFCB200_HALO_SHORT=0 forces the long warm-up for every segment (measurement knob)
 
-   HostBuf hRecs, hExt, hMeta, hStreamOf; // gather staging
+   HostBuf hRecs, hExt; // gather staging
+   DevBuf packed, packedExt, packCtr; // frames of the current call, ordered and packed on the device (all chunks)
+   uint64_t packedCount = 0;           // records in `packed`
+   u32 packedExtCount = 0;             // 128-byte chunks in `packedExt`
+   u32 packedRate = 0;
 
-   DevBuf samples, flags, bsum, counts, offsets, segCounts, segOffsets, segs, feats, lanes, queue, scratch, sbuf, pool, ext, meta, streamOf, counters;
+   DevBuf samples, flags, bsum, counts, offsets, segCounts, segOffsets, segs, feats, lanes, queue, scratch, sbuf, pool, ext, meta, counters;
    nfcb200_stats stats;
 
    // last batch geometry (for the flag tap)
@@ -367,6 +393,8 @@ int nfcb200_create(const nfcb200_config *cfg, nfcb200_handle **out)
    h->cfg = c;
    h->device = c.device;
    memset(&h->stats, 0, sizeof(h->stats));
+   h->packedCount = 0;
+   h->packedExtCount = 0;
 
    cudaDeviceProp prop;
    if (cudaGetDeviceProperties(&prop, c.device) == cudaSuccess)
@@ -409,11 +437,11 @@ void nfcb200_destroy(nfcb200_handle *h)
       return;
    cudaSetDevice(h->device);
    cudaStreamSynchronize(h->stream);
-   DevBuf *bufs[] = {&h->samples, &h->flags, &h->bsum, &h->counts, &h->offsets, &h->lanes, &h->queue, &h->segCounts, &h->segOffsets, &h->segs, &h->feats, &h->scratch, &h->sbuf, &h->pool, &h->ext, &h->meta,
-                     &h->streamOf, &h->counters, &h->sState, &h->sScratch, &h->sSbuf, &h->sSamples, &h->sFlags, &h->sBsum, &h->sCounts};
+   DevBuf *bufs[] = {&h->samples, &h->flags, &h->bsum, &h->counts, &h->offsets, &h->lanes, &h->queue, &h->segCounts, &h->segOffsets, &h->segs, &h->feats, &h->scratch, &h->sbuf, &h->pool, &h->ext, &h->meta, &h->packed, &h->packedExt, &h->packCtr,
+                     &h->counters, &h->sState, &h->sScratch, &h->sSbuf, &h->sSamples, &h->sFlags, &h->sBsum, &h->sCounts};
    for (DevBuf *b: bufs)
       b->release();
-   HostBuf *hbufs[] = {&h->hRecs, &h->hExt, &h->hMeta, &h->hStreamOf};
+   HostBuf *hbufs[] = {&h->hRecs, &h->hExt};
    for (HostBuf *b: hbufs)
       b->release();
    for (auto &ev: h->ev)
@@ -646,8 +674,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       int rc = h->lanes.reserve((size_t) nLanes * sizeof(LaneRec));
       rc = rc ? rc : h->segs.reserve((size_t) std::max<u32>(nSegs, 1) * sizeof(SegRec));
       rc = rc ? rc : h->queue.reserve((size_t) nLanes * sizeof(u32));
-      rc = rc ? rc : h->meta.reserve((size_t) nLanes * sizeof(u32));
-      rc = rc ? rc : h->streamOf.reserve((size_t) nLanes * sizeof(u32));
+      rc = rc ? rc : h->meta.reserve((size_t) (nLanes + 1) * sizeof(u32));
       if (rc)
          return rc;
    }
@@ -663,6 +690,27 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    segment_fill_kernel<<<n_streams, 32, 0, st>>>(sg, h->P);
    launches++;
    CUDA_TRY(cudaGetLastError());
+
+   // first-round queue ordered by decreasing lane length (counting sort on the host: the lengths are 4 bytes per lane)
+   if (!exact && nLanes > 64)
+   {
+      lane_length_kernel<<<(nLanes + 255) / 256, 256, 0, st>>>(h->lanes.as<LaneRec>(), nLanes, h->meta.as<u32>());
+      launches++;
+      std::vector<u32> len(nLanes), order(nLanes);
+      CUDA_TRY(cudaMemcpyAsync(len.data(), h->meta.ptr, (size_t) nLanes * sizeof(u32), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      const u32 shift = 8, buckets = 1u << 16;
+      std::vector<u32> hist(buckets + 1, 0);
+      auto key = [&](u32 v) { u32 k = v >> shift; return k >= buckets ? 0u : buckets - 1 - k; }; // descending
+      for (u32 i = 0; i < nLanes; i++)
+         hist[key(len[i]) + 1]++;
+      for (u32 b = 0; b < buckets; b++)
+         hist[b + 1] += hist[b];
+      for (u32 i = 0; i < nLanes; i++)
+         order[hist[key(len[i])]++] = i;
+      CUDA_TRY(cudaMemcpyAsync(h->queue.ptr, order.data(), (size_t) nLanes * sizeof(u32), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+   }
 
    // ---- front pass: the sequential float recurrences of nextSample, one thread per segment -> feature pool ----------
    unsigned long long featTotal = 0;
@@ -807,13 +855,16 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
 
    cudaEventRecord(h->ev[4], st);
 
-   // ---- gather --------------------------------------------------------------------------------------------------------
-   lane_meta_kernel<<<(nLanes + 255) / 256, 256, 0, st>>>(h->lanes.as<LaneRec>(), nLanes, h->meta.as<u32>(), h->streamOf.as<u32>(), &dC->live);
+   // ---- gather: ordered and packed on the device, one copy to the host ---------------------------------------------------
+   u32 *dLaneOff = h->meta.as<u32>(); // [nLanes + 1]
+   frame_offsets_kernel<<<1, 1024, 0, st>>>(h->lanes.as<LaneRec>(), nLanes, dLaneOff, &dC->live);
    launches++;
    CUDA_TRY(cudaGetLastError());
 
    Counters hc;
+   u32 nf32 = 0;
    CUDA_TRY(cudaMemcpyAsync(&hc, dC, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaMemcpyAsync(&nf32, dLaneOff + nLanes, sizeof(u32), cudaMemcpyDeviceToHost, st));
    CUDA_TRY(cudaStreamSynchronize(st));
 
    S.lane_samples = hc.work;
@@ -832,94 +883,80 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    if (hc.poolCount > poolCap || hc.extCount > extCap)
       return fail(NFCB200_ERR_CAPACITY, "frame pool exhausted (%u frames, %u extension chunks)", hc.poolCount, hc.extCount);
 
+   const uint64_t nf = nf32;
+   const u32 extBefore = h->packedExtCount;
    {
-      int rc = h->hRecs.reserve((size_t) hc.poolCount * sizeof(FrameRec));
-      rc = rc ? rc : h->hExt.reserve((size_t) hc.extCount * 128);
-      rc = rc ? rc : h->hMeta.reserve((size_t) nLanes * sizeof(u32));
-      rc = rc ? rc : h->hStreamOf.reserve((size_t) nLanes * sizeof(u32));
+      int rc = h->packed.reserve_keep((size_t) (h->packedCount + nf) * sizeof(FrameRec), (size_t) h->packedCount * sizeof(FrameRec), st);
+      rc = rc ? rc : h->packedExt.reserve_keep((size_t) (extBefore + hc.extCount + 1) * 128, (size_t) extBefore * 128, st);
+      rc = rc ? rc : h->packCtr.reserve(sizeof(u32));
+      if (rc)
+         return rc;
+   }
+   const u32 packedExtCap = (u32) std::min<size_t>(h->packedExt.cap / 128, 0xFFFFFFFFu);
+   CUDA_TRY(cudaMemcpyAsync(h->packCtr.ptr, &extBefore, sizeof(u32), cudaMemcpyHostToDevice, st));
+
+   FrameRec *dPacked = h->packed.as<FrameRec>() + h->packedCount;
+   if (hc.poolCount)
+   {
+      const u32 grid = std::min<u32>((hc.poolCount + 255) / 256, (u32) h->smCount * 8);
+      frame_compact_kernel<<<grid, 256, 0, st>>>(h->pool.as<FrameRec>(), hc.poolCount, h->lanes.as<LaneRec>(), nLanes, dLaneOff, h->ext.as<u8>(), hc.extCount,
+                                                  streamBase, dPacked, h->packedExt.as<u8>(), packedExtCap, h->packCtr.as<u32>());
+      launches++;
+      CUDA_TRY(cudaGetLastError());
+   }
+
+   u32 extAfter = extBefore;
+   CUDA_TRY(cudaMemcpyAsync(&extAfter, h->packCtr.ptr, sizeof(u32), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaStreamSynchronize(st));
+   if (extAfter > packedExtCap)
+      extAfter = packedExtCap;
+
+   {
+      int rc = h->hRecs.reserve((size_t) std::max<uint64_t>(nf, 1) * sizeof(FrameRec));
+      rc = rc ? rc : h->hExt.reserve((size_t) std::max<u32>(extAfter - extBefore, 1) * 128);
       if (rc)
          return rc;
    }
 
-   const FrameRec *recs = h->hRecs.as<FrameRec>();
-   const unsigned char *ext = h->hExt.as<unsigned char>();
-   const u32 *meta = h->hMeta.as<u32>();
-   const u32 *streamOf = h->hStreamOf.as<u32>();
-   const u32 nRecs = hc.poolCount;
-
-   if (hc.poolCount)
-      CUDA_TRY(cudaMemcpyAsync(h->hRecs.ptr, h->pool.ptr, (size_t) hc.poolCount * sizeof(FrameRec), cudaMemcpyDeviceToHost, st));
-   if (hc.extCount)
-      CUDA_TRY(cudaMemcpyAsync(h->hExt.ptr, h->ext.ptr, (size_t) hc.extCount * 128, cudaMemcpyDeviceToHost, st));
-   CUDA_TRY(cudaMemcpyAsync(h->hMeta.ptr, h->meta.ptr, (size_t) nLanes * sizeof(u32), cudaMemcpyDeviceToHost, st));
-   CUDA_TRY(cudaMemcpyAsync(h->hStreamOf.ptr, h->streamOf.ptr, (size_t) nLanes * sizeof(u32), cudaMemcpyDeviceToHost, st));
+   if (nf)
+      CUDA_TRY(cudaMemcpyAsync(h->hRecs.ptr, dPacked, (size_t) nf * sizeof(FrameRec), cudaMemcpyDeviceToHost, st));
+   if (extAfter > extBefore)
+      CUDA_TRY(cudaMemcpyAsync(h->hExt.ptr, h->packedExt.as<u8>() + (size_t) extBefore * 128, (size_t) (extAfter - extBefore) * 128, cudaMemcpyDeviceToHost, st));
 
    cudaEventRecord(h->ev[5], st);
    CUDA_TRY(cudaStreamSynchronize(st));
-   tr.mark("pool d2h");
+   tr.mark("frames d2h");
 
-   // keep only the frames of the final generation of live lanes.  Lanes are globally ordered by (stream, time) and a
-   // run numbers its frames 0 .. nframes-1, so the output position of a frame is a counting sort: offset[lane] + seq.
-   // Both passes over the records and the conversion to ABI frames run on a few host threads (4e5 frames per batch).
-   const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(16, nRecs / 4096));
-   auto parallel = [&](uint64_t count, const std::function<void(uint64_t, uint64_t)> &fn) {
-      if (workers <= 1 || count < 8192)
-      {
-         fn(0, count);
-         return;
-      }
-      std::vector<std::thread> pool;
-      const uint64_t step = (count + workers - 1) / workers;
-      for (unsigned w = 0; w < workers; w++)
-         pool.emplace_back(fn, std::min(count, w * step), std::min(count, (w + 1) * step));
-      for (auto &t: pool)
-         t.join();
-   };
+   h->packedCount += nf;
+   h->packedExtCount = extAfter;
+   h->packedRate = sample_rate;
 
-   auto kept = [&](const FrameRec &r) {
-      if (r.lane >= nLanes)
-         return false;
-      const u32 m = meta[r.lane];
-      return !(m & 1) && (m >> 1) == r.gen;
-   };
-
-   std::vector<std::atomic<u32>> laneCount(nLanes + 1);
-   parallel(nLanes + 1, [&](uint64_t lo, uint64_t hi) {
-      for (uint64_t i = lo; i < hi; i++)
-         laneCount[i].store(0, std::memory_order_relaxed);
-   });
-   parallel(nRecs, [&](uint64_t lo, uint64_t hi) {
-      for (uint64_t i = lo; i < hi; i++)
-         if (kept(recs[i]))
-            laneCount[recs[i].lane + 1].fetch_add(1, std::memory_order_relaxed);
-   });
-
-   std::vector<u32> laneOff(nLanes + 1);
-   laneOff[0] = 0;
-   for (u32 i = 0; i < nLanes; i++)
-      laneOff[i + 1] = laneOff[i] + laneCount[i + 1].load(std::memory_order_relaxed);
-
-   const uint64_t nf = laneOff[nLanes];
-   std::vector<u32> order(nf);
-   parallel(nRecs, [&](uint64_t lo, uint64_t hi) {
-      for (uint64_t i = lo; i < hi; i++)
-      {
-         const FrameRec &r = recs[i];
-         if (!kept(r))
-            continue;
-         const uint64_t pos = (uint64_t) laneOff[r.lane] + r.seq;
-         if (pos < (uint64_t) laneOff[r.lane + 1])
-            order[pos] = (u32) i;
-      }
-   });
-
-   tr.mark("counting sort");
+   // conversion to ABI frames on a few host threads (4e5 frames per batch)
    {
+      const FrameRec *recs = h->hRecs.as<FrameRec>();
+      const unsigned char *ext = h->hExt.as<unsigned char>();
       const uint64_t count = outOffset >= cap ? 0 : std::min<uint64_t>(nf, cap - outOffset);
-      parallel(count, [&](uint64_t lo, uint64_t hi) {
+      const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(16, count / 4096));
+      auto work = [&](uint64_t lo, uint64_t hi) {
          for (uint64_t i = lo; i < hi; i++)
-            emit_frame(h, recs[order[i]], ext, (size_t) hc.extCount * 128, streamBase + streamOf[recs[order[i]].lane], sample_rate, out[outOffset + i]);
-      });
+         {
+            FrameRec r = recs[i];
+            if (r.ext != 0xFFFFFFFFu)
+               r.ext -= extBefore; // chunk index inside this call's host copy
+            emit_frame(h, r, ext, (size_t) (extAfter - extBefore) * 128, r.lane, sample_rate, out[outOffset + i]);
+         }
+      };
+      if (workers <= 1 || count < 8192)
+         work(0, count);
+      else
+      {
+         std::vector<std::thread> pool;
+         const uint64_t step = (count + workers - 1) / workers;
+         for (unsigned w = 0; w < workers; w++)
+            pool.emplace_back(work, std::min(count, w * step), std::min(count, (w + 1) * step));
+         for (auto &t: pool)
+            t.join();
+      }
    }
 
    tr.mark("emit");
@@ -1082,7 +1119,57 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// wire format of the multi-GPU frame gather: [u64 count][count x 80-byte headers][payloads back to back]
+// multi-GPU frame gather without a host round trip: the frames of the last decode, ordered and packed, as they sit in
+// device memory (128-byte records + 128-byte payload extension chunks), and the conversion of such records to ABI frames
+// ---------------------------------------------------------------------------------------------------------------------
+int nfcb200_device_frames(nfcb200_handle *h, const void **records, uint64_t *n_records, const void **ext, uint64_t *n_ext_chunks)
+{
+   if (!h)
+      return fail(NFCB200_ERR_INVALID, "null handle");
+   if (records)
+      *records = h->packed.ptr;
+   if (n_records)
+      *n_records = h->packedCount;
+   if (ext)
+      *ext = h->packedExt.ptr;
+   if (n_ext_chunks)
+      *n_ext_chunks = h->packedExtCount;
+   return 0;
+}
+
+int nfcb200_emit_records(nfcb200_handle *h, const void *records, uint64_t n_records, const void *ext, uint64_t n_ext_chunks, uint32_t stream_offset,
+                         uint32_t sample_rate, nfcb200_frame *out, uint64_t cap, uint64_t *n_out)
+{
+   if (!h)
+      return fail(NFCB200_ERR_INVALID, "null handle");
+   if (n_out)
+      *n_out = n_records;
+   if (n_records > cap)
+      return fail(NFCB200_ERR_CAPACITY, "%llu records but room for %llu frames", (unsigned long long) n_records, (unsigned long long) cap);
+   if (n_records && (!records || !out))
+      return fail(NFCB200_ERR_INVALID, "null buffer");
+   const FrameRec *recs = (const FrameRec *) records;
+   const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(16, n_records / 4096));
+   auto work = [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; i++)
+         emit_frame(h, recs[i], (const unsigned char *) ext, (size_t) n_ext_chunks * 128, recs[i].lane + stream_offset, sample_rate, out[i]);
+   };
+   if (workers <= 1 || n_records < 8192)
+      work(0, n_records);
+   else
+   {
+      std::vector<std::thread> pool;
+      const uint64_t step = (n_records + workers - 1) / workers;
+      for (unsigned w = 0; w < workers; w++)
+         pool.emplace_back(work, std::min(n_records, w * step), std::min(n_records, (w + 1) * step));
+      for (auto &t: pool)
+         t.join();
+   }
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// wire format of the host-side frame gather (gloo / CPU tests): [u64 count][count x 80-byte headers][payloads back to back]
 // ---------------------------------------------------------------------------------------------------------------------
 int nfcb200_pack_frames(const nfcb200_frame *frames, uint64_t n, uint32_t stream_offset, uint8_t *out, uint64_t cap, uint64_t *n_bytes)
 {

@@ -50,6 +50,27 @@ def frames_digest(arr):
     return total & 0xFFFFFFFFFFFFFFFF
 
 
+def frame_hashes(arr):
+    """one 64-bit hash per frame over every field RawFrame::operator== compares plus the payload (NOT the stream index):
+    the value oracle/ref_wrap.cpp nfcref_hash_batch computes for the reference's frames (full-size differential)"""
+    a = np.asarray(arr)
+    n = int(a.size)
+    if n == 0:
+        return np.zeros(0, dtype=np.uint64)
+    mask = np.uint64(0xFFFFFFFFFFFFFFFF)
+    h = np.zeros(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for k, name in enumerate(("tech_type", "frame_type", "frame_flags", "frame_phase", "frame_rate", "length", "sample_start", "sample_end")):
+            h = (h * np.uint64(0x100000001B3) + a[name].astype(np.uint64) + np.uint64(k + 1)) & mask
+        L = int(a["length"].max())
+        if L:
+            d = a["data"][:, :L].astype(np.uint64)
+            live = np.arange(L, dtype=np.uint64)[None, :] < a["length"].astype(np.uint64)[:, None]
+            w = (np.arange(L, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(1)) & mask
+            h = (h + ((d + np.uint64(1)) * w[None, :] * live).sum(axis=1, dtype=np.uint64)) & mask
+    return h
+
+
 def pack_frames(arr, stream_offset=0):
     """frame records (numpy FRAME_DTYPE array, e.g. a view of the decoder's output buffer) -> one flat uint8 buffer
     [u64 count][count x 80-byte headers][payload bytes back to back], packed by nfcb200_pack_frames (host threads)"""
@@ -155,6 +176,104 @@ def gather_frames(flat, device, group=None):
         pos += s
     torch.cuda.synchronize()
     return stage[:total].numpy()  # a view of the cached staging buffer: valid until the next gather_frames call
+
+
+class _DevView:
+    """zero-copy torch view of raw device memory (torch.as_tensor reads __cuda_array_interface__)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def gather_device_frames(dec, device, stream_offset, sample_rate, group=None, timings=None):
+    """frame gather of the batch decode WITHOUT a host round trip on the sending side: every rank hands the device-resident,
+    already ordered and packed records of its last decode (NfcDecoder.device_frames) to NCCL; one all_gather of the counts,
+    then point-to-point transfers to rank 0 only.  Rank 0 copies what it received to page-locked host memory
+    (GatheredRecords; .frames(dec) converts to ABI frames).  Returns None on the other ranks.  stream_offset(r) gives the
+    first global stream index of rank r.  timings (dict) receives gather_pack / gather_nccl / gather_d2h in milliseconds."""
+    import time
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    t0 = time.perf_counter()
+    rp, n, ep, ne = dec.device_frames()
+    counts = torch.tensor([n, ne], dtype=torch.int64, device=device)
+    allc = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(allc, counts, group=group)
+    allc = [(int(c[0].item()), int(c[1].item())) for c in allc]
+    t1 = time.perf_counter()
+
+    if rank != 0:
+        ops = []
+        if n:
+            ops.append(dist.P2POp(dist.isend, torch.as_tensor(_DevView(rp, n * 128), device=device), 0, group))
+        if ne:
+            ops.append(dist.P2POp(dist.isend, torch.as_tensor(_DevView(ep, ne * 128), device=device), 0, group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        torch.cuda.synchronize()
+        if timings is not None:
+            timings.update(gather_pack=(t1 - t0) * 1e3, gather_nccl=(time.perf_counter() - t1) * 1e3, gather_d2h=0.0)
+        return None
+
+    bufs = []
+    ops = []
+    for r in range(1, world):
+        nr, er = allc[r]
+        rb = torch.empty(max(nr, 1) * 128, dtype=torch.uint8, device=device)
+        eb = torch.empty(max(er, 1) * 128, dtype=torch.uint8, device=device)
+        bufs.append((rb, eb))
+        if nr:
+            ops.append(dist.P2POp(dist.irecv, rb[:nr * 128], r, group))
+        if er:
+            ops.append(dist.P2POp(dist.irecv, eb[:er * 128], r, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+
+    # device -> page-locked host, one staging buffer for all ranks' records and one for their extension chunks
+    tot_r = sum(c[0] for c in allc[1:])
+    tot_e = sum(c[1] for c in allc[1:])
+    hr = _pinned_bytes("recv_r", max(tot_r, 1) * 128)
+    he = _pinned_bytes("recv_e", max(tot_e, 1) * 128)
+    pr = pe = 0
+    spans = []
+    for (rb, eb), (nr, er) in zip(bufs, allc[1:]):
+        if nr:
+            hr[pr:pr + nr * 128].copy_(rb[:nr * 128], non_blocking=True)
+        if er:
+            he[pe:pe + er * 128].copy_(eb[:er * 128], non_blocking=True)
+        spans.append((pr, nr, pe, er))
+        pr += nr * 128
+        pe += er * 128
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+
+    if timings is not None:
+        timings.update(gather_pack=(t1 - t0) * 1e3, gather_nccl=(t2 - t1) * 1e3, gather_d2h=(t3 - t2) * 1e3)
+    return GatheredRecords(hr, he, spans, stream_offset, sample_rate)
+
+
+class GatheredRecords:
+    """what rank 0 holds after gather_device_frames: the other ranks' frames as packed 128-byte records (+ extension
+    chunks) in page-locked host memory, one span per rank in rank order.  frames(dec) converts them to ABI frames."""
+
+    def __init__(self, records, ext, spans, stream_offset, sample_rate):
+        self.records, self.ext, self.spans = records, ext, spans
+        self.stream_offset, self.sample_rate = stream_offset, sample_rate
+        self.count = sum(s[1] for s in spans)
+
+    def frames(self, dec):
+        out = []
+        for i, (pr, nr, pe, er) in enumerate(self.spans):
+            if nr:
+                out += dec.emit_records(self.records.data_ptr() + pr, nr, self.ext.data_ptr() + pe, er, self.stream_offset(i + 1), self.sample_rate)
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------

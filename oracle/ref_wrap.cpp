@@ -225,4 +225,85 @@ double nfcref_time_batch(const float *mag, const float *iq, uint64_t n, uint32_t
    return std::chrono::duration<double>(stop - start).count();
 }
 
+
+/*
+ * Full-size differential (bench.py cpu_baseline leg, tests): one 64-bit hash per reference frame over every field
+ * RawFrame::operator== compares (lab-data RawFrame.cpp:82-98) plus the payload, hashes[s * cap + i] for frame i of stream s,
+ * counts[s] = frames of stream s (may exceed cap: the excess is not stored).  nfc_laboratory_b200/dist.py frame_hashes()
+ * computes the same value from the GPU's frames.  Returns the seconds spent (IQ -> magnitude included when iq != NULL).
+ */
+static uint64_t hash_frame(const lab::RawFrame &f)
+{
+   const uint64_t fields[8] = {f.techType(), f.frameType(), f.frameFlags(), f.framePhase(), f.frameRate(), f.limit() > 512 ? 512u : f.limit(),
+                               f.sampleStart(), f.sampleEnd()};
+   uint64_t h = 0;
+   for (int k = 0; k < 8; k++)
+      h = h * 0x100000001B3ull + fields[k] + (uint64_t) (k + 1);
+   unsigned int n = f.limit() > 512 ? 512 : f.limit();
+   for (unsigned int j = 0; j < n; j++)
+      h += ((uint64_t) (unsigned char) f[j] + 1ull) * ((uint64_t) j * 0x9E3779B97F4A7C15ull + 1ull);
+   return h;
+}
+
+double nfcref_hash_batch(const float *mag, const float *iq, uint64_t n, uint32_t n_streams, uint32_t sample_rate, uint32_t chunk, int threads,
+                         uint64_t *hashes, uint32_t cap, uint32_t *counts)
+{
+   if (threads < 1)
+      threads = 1;
+   if (chunk == 0)
+      chunk = 65536;
+
+   std::atomic<uint32_t> next {0};
+   auto start = std::chrono::steady_clock::now();
+   std::vector<std::thread> pool;
+
+   for (int t = 0; t < threads; t++)
+   {
+      pool.emplace_back([&]() {
+         std::vector<float> scratch;
+
+         for (;;)
+         {
+            uint32_t s = next.fetch_add(1);
+            if (s >= n_streams)
+               break;
+
+            const float *src = mag ? mag + (uint64_t) s * n : nullptr;
+            if (iq)
+            {
+               scratch.resize(n);
+               nfcref_iq_magnitude(iq + 2 * (uint64_t) s * n, n, scratch.data());
+               src = scratch.data();
+            }
+
+            lab::NfcDecoder decoder;
+            decoder.setEnableNfcA(true);
+            decoder.setEnableNfcB(true);
+            decoder.setEnableNfcF(true);
+            decoder.setEnableNfcV(true);
+
+            uint32_t produced = 0;
+            for (uint64_t pos = 0; pos < n; pos += chunk)
+            {
+               uint32_t len = (uint32_t) std::min<uint64_t>(chunk, n - pos);
+               hw::SignalBuffer samples(len, 1, 1, sample_rate, 0, 0, hw::SignalType::SIGNAL_TYPE_RADIO_SAMPLES, 0);
+               samples.put(src + pos, len).flip();
+               for (const lab::RawFrame &frame: decoder.nextFrames(samples))
+               {
+                  if (produced < cap)
+                     hashes[(uint64_t) s * cap + produced] = hash_frame(frame);
+                  produced++;
+               }
+            }
+            counts[s] = produced;
+         }
+      });
+   }
+
+   for (auto &th: pool)
+      th.join();
+
+   return std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+}
+
 }

@@ -76,6 +76,14 @@ void nfcref_iq_magnitude(const float *iq, uint64_t n, float *mag);
 double nfcref_time_batch(const float *mag, const float *iq, uint64_t n, uint32_t n_streams, uint32_t sample_rate,
                          uint32_t chunk, int threads, long *frames_out);
 
+/*
+ * One 64-bit hash per reference frame (every field RawFrame::operator== compares plus the payload): hashes[s * cap + i]
+ * for frame i of stream s, counts[s] = its frame count.  The full-size differential of bench.py compares these with the
+ * hashes of the GPU's frames (nfc_laboratory_b200/dist.py frame_hashes).  Returns elapsed seconds.
+ */
+double nfcref_hash_batch(const float *mag, const float *iq, uint64_t n, uint32_t n_streams, uint32_t sample_rate, uint32_t chunk, int threads,
+                         uint64_t *hashes, uint32_t cap, uint32_t *counts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -158,6 +158,7 @@ long hostsim_run(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t ena
    if (carry_out)
    {
       Carry c = L.c;
+      c.edgeTime = L.fe.edgeTime;
       carry_canon(c);
       std::memcpy(carry_out, &c, sizeof(Carry));
    }

@@ -58,21 +58,26 @@ def test_single_lane_equals_reference(name):
     assert frames == U.ref_decode(x, FS)
 
 
-# Known gap (DESIGN.md "other deviations"): the reference stamps a carrier frame with the time of the last strong edge of
-# the DC-removed signal, however old (NfcTech.cpp:77-92, NfcDecoder.cpp:477-521).  That time is front-end state a
-# cold-started lane does not inherit -- it holds the lane's own start-up transient instead -- so a carrier event that
-# arrives without a fresh edge (a slow fade) inside a cold-started lane gets the wrong time stamp.  Abrupt carrier
-# changes, i.e. every capture of the regression set, bring their own edge and are exact.
-STALE_EDGE_TIME = {"ramps_around_the_power_threshold"}
-
-
-@pytest.mark.parametrize("name", [pytest.param(n, marks=pytest.mark.xfail(strict=True, reason="carrier frame stamped with a stale edge time, see above"))
-                                  if n in STALE_EDGE_TIME else n for n in sorted(CASES)])
+# The reference stamps a carrier frame with the time of the last strong edge of the DC-removed signal, however old
+# (NfcTech.cpp:77-92, NfcDecoder.cpp:477-521): lanes carry that time across their boundaries (Carry::edgeTime) and ignore the
+# start-up transient of a cold-started DC filter (Front::edgeHold), so a slow fade inside a later lane is stamped like there.
+@pytest.mark.parametrize("name", sorted(CASES))
 def test_lane_pipeline_equals_reference(name):
     x = CASES[name]
     if x.size < 2:
         pytest.skip("the block model needs two samples")
     out, _ = U.sim_pipeline(x, S.block_flags_device_model(x, S.ScreenParams(FS)), FS)
+    assert out == U.ref_decode(x, FS)
+
+
+@pytest.mark.parametrize("group", [0, 1])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_warp_lane_pipeline_equals_reference(name, group):
+    """round-2 pipeline (front pass, feature pool, warp lanes): one lane per stream (group 0) and one lane per segment"""
+    x = CASES[name]
+    if x.size < 2:
+        pytest.skip("the block model needs two samples")
+    out, _ = U.sim_pipeline2(x, S.block_flags_device_model(x, S.ScreenParams(FS)), FS, group=group)
     assert out == U.ref_decode(x, FS)
 
 
