@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle spot check of the cpu_baseline leg")
+    ap.add_argument("--no-wav-set", action="store_true", help="skip the regression-set leg (tests/golden, cpu_baseline leg, untimed)")
     ap.add_argument("--no-full-parity", action="store_true", help="skip the full-size differential against the reference (cpu_baseline leg, untimed)")
     ap.add_argument("--parity-budget", type=float, default=120.0, help="seconds the full-size differential may take")
     ap.add_argument("--exact", action="store_true", help="decode with one warp lane per stream (exact float state, slower)")
@@ -248,6 +249,92 @@ def full_parity(frames, iq, S, n, threads, budget_s=90.0, chunk_streams=32):
         return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
+def lanes_traffic(exact):
+    """DRAM bytes per launch of the lane kernel from the committed ncu capture of the same workload (profiles/), or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "lanes_kernel_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["exact" if exact else "thread"]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+def wav_set(dec_factory, threads):
+    """the reference's own regression set (19 captures, 13 954 142 samples of 16-bit mono at 10 MS/s,
+    tests/golden/) -- decoded capture by capture through nfcb200_decode_batch as int16 and as float, through the streaming
+    entry point (nfcb200_stream_push, 65 536-sample chunks like test-sdr), and by the reference on ONE host thread
+    (oracle/_ref, how test-sdr runs it) and on all granted threads.  Every GPU frame list is compared with the golden files."""
+    try:
+        import nfcutil as U
+        import nfc_laboratory_b200 as N
+        names = U.fixture_names()
+        caps = [(nm,) + tuple(U.fixture_wav(nm)[:2]) for nm in names]
+        total = sum(c[1].size for c in caps)
+        res = {"captures": len(caps), "samples": int(total)}
+
+        def golden_ok(frames, nm):
+            return [k for k in frames if k[1] in (0x102, 0x103)] == U.fixture_golden(nm)
+
+        for label, exact in (("batch_thread_lanes", False), ("batch_warp_lanes_exact", True)):
+            d = dec_factory(exact)
+            ok = True
+            for fmt in ("s16", "f32"):
+                best = None
+                for rep in range(3):
+                    t0 = time.perf_counter()
+                    for nm, mag, rate in caps:
+                        if fmt == "s16":
+                            x = np.round(mag * 32768.0).astype(np.int16)
+                            fr = d.decode_batch(x[None], N.SIG_MAG_S16, rate)
+                        else:
+                            fr = d.decode_batch(mag[None], N.SIG_MAG_F32, rate)
+                        if rep == 0:
+                            ok = ok and golden_ok([f.key() for f in fr], nm)
+                    dt = time.perf_counter() - t0
+                    best = dt if best is None else min(best, dt)
+                res["%s_%s_msps" % (label, fmt)] = total / best / 1e6
+            res["%s_equals_golden" % label] = bool(ok)
+            d.close()
+
+        # streaming entry point, chunk by chunk
+        d = dec_factory(False)
+        ok = True
+        t0 = time.perf_counter()
+        slowest = None
+        for nm, mag, rate in caps:
+            d.initialize()
+            t1 = time.perf_counter()
+            out = []
+            for pos in range(0, mag.size, 65536):
+                out += d.nextFrames(mag[pos:pos + 65536], rate)
+            out += d.nextFrames(None, rate)
+            dt1 = time.perf_counter() - t1
+            rate1 = mag.size / dt1 / 1e6
+            slowest = rate1 if slowest is None else min(slowest, rate1)
+            ok = ok and golden_ok([f.key() for f in out], nm)
+        res["stream_push_msps"] = total / (time.perf_counter() - t0) / 1e6
+        res["stream_push_slowest_capture_msps"] = slowest
+        res["stream_push_equals_golden"] = bool(ok)
+        d.close()
+
+        lib = U.ref_lib()
+        if lib is not None:
+            def ref_seconds(c):
+                fr = C.c_long(0)
+                return float(lib.nfcref_time_batch(c[1].ctypes.data, None, c[1].size, 1, c[2], 65536, 1, C.byref(fr)))
+
+            lib.nfcref_time_batch.restype = C.c_double
+            res["reference_1_thread_msps"] = total / sum(ref_seconds(c) for c in caps) / 1e6
+            import concurrent.futures as cf
+            t0 = time.perf_counter()
+            with cf.ThreadPoolExecutor(threads) as ex:
+                list(ex.map(ref_seconds, caps))
+            res["reference_%d_threads_msps" % threads] = total / (time.perf_counter() - t0) / 1e6
+        return res
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def workload_name(workload, S, n, bytes_per_step):
     """config.workload: the same text for both arms (the reference arm times a bounded sample of it, named in config.sample)"""
     return "%s: %d synthetic 10 MS/s x %.1f s float2 IQ streams per GPU (BASELINE.json configs[1] shape), input %.1f GB per GPU, " \
@@ -440,8 +527,13 @@ def main():
 
     value = world * S * n * args.steps / dt / 1e6
 
-    # ---- roofline of the dominant dense kernel (K1 screen): algorithmic bytes = one read of the IQ input ------------------
+    # ---- rooflines (HBM-bound path, algorithmic bytes = one read of the IQ input) ------------------------------
+    # `roofline` is the DOMINANT kernel's: the lane kernel (K2), which only has to touch the active share of the samples
+    # (lane_samples / samples of the input bytes); K1 (the dense screen that reads every byte) and the whole step follow.
     ms_screen = statistics.mean(s["ms_screen"] for s in stats)
+    ms_lanes = statistics.mean(s["ms_lanes"] for s in stats)
+    ms_step = statistics.mean(s["ms_total"] for s in stats)
+    lane_frac = statistics.mean(s["lane_samples"] / max(1, s["samples"]) for s in stats)
     peak, peak_src = measured_peaks()
     achieved = bytes_per_step / (ms_screen * 1e-3) / 1e9
     traffic = None
@@ -454,6 +546,19 @@ def main():
             traffic = float(t["dram_bytes_per_sample"]) * S * n
         except Exception:
             traffic = None
+    lanes_bytes = bytes_per_step * lane_frac
+    lanes_achieved = lanes_bytes / (ms_lanes * 1e-3) / 1e9 if ms_lanes > 0 else 0.0
+    step_achieved = bytes_per_step / (ms_step * 1e-3) / 1e9 if ms_step > 0 else 0.0
+    lane_kernel = "wlanes_kernel (K2, warp lanes: one warp per stream, rings in shared memory)" if args.exact else \
+        "lanes_kernel (K2, thread lanes: one thread per segment group, exact per-sample decoder)"
+    roofline = {"bound": "hbm", "achieved": lanes_achieved, "peak": peak, "unit": "GB/s", "frac": lanes_achieved / peak, "traffic": lanes_traffic(args.exact),
+                "kernel": lane_kernel, "peak_source": peak_src, "algorithmic_bytes_per_launch": lanes_bytes, "ms_per_launch": ms_lanes,
+                "note": "algorithmic bytes = the active share of the input the lanes must read (%.3f of %d bytes); all lane + chain launches of a step" % (lane_frac, bytes_per_step)}
+    roofline_k1 = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                   "kernel": "screen_kernel (K1: IQ->magnitude, prefix-sum moving sums, A/F/V correlators, B edge IIR)", "peak_source": peak_src,
+                   "algorithmic_bytes_per_launch": bytes_per_step, "ms_per_launch": ms_screen}
+    roofline_step = {"bound": "hbm", "achieved": step_achieved, "peak": peak, "unit": "GB/s", "frac": step_achieved / peak,
+                     "algorithmic_bytes_per_launch": bytes_per_step, "ms_per_launch": ms_step, "kernel": "whole step (K1 + segments + lanes + chain + gather)"}
 
     # ---- e2e: the same decode through the C ABI with HOST buffers (H2D inside the timed region) ---------------------------
     e2e = None
@@ -474,7 +579,7 @@ def main():
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         d2h = 0
-        esteps = max(1, min(args.steps, 2))
+        esteps = max(1, min(args.steps, 5)) if not args.quick else 2
         for _ in range(esteps):
             buf, nf = dec.decode_batch_ptr(host.data_ptr(), False, N.SIG_IQ_F32, Se, n, RATE, cap=cap, raw=True)
             d2h = nf * 128 + 8
@@ -501,6 +606,7 @@ def main():
     cpu = None
     fullcheck = None
     fullparity = None
+    wavset = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = host_cores()
         Sc = min(S, max(cores, min(2 * cores, 32)))
@@ -526,6 +632,8 @@ def main():
             fullcheck = full_size_check(frames_last, S, n, args.workload, args.seed + 1000 * rank, iq)
         if v is not None and frames_last is not None and not args.no_full_parity:
             fullparity = full_parity(frames_last, iq, S, n, cores, budget_s=args.parity_budget)
+        if v is not None and not args.no_wav_set:
+            wavset = wav_set(lambda exact: N.NfcDecoder(device=local, exact=exact), cores)
         if v is not None:
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
                    "sample": "%d of the batch's streams x %d samples, one NfcDecoder per host thread on %d threads, IQ->magnitude included" % (Sc, nc, cores)}
@@ -541,9 +649,7 @@ def main():
                        "lanes": "warp lanes, one per stream, exact float state" if args.exact else "thread lanes, cold-started running sums"},
             "e2e": e2e,
             "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "screen_kernel (K1: IQ->magnitude, prefix-sum moving sums, A/F/V correlators, B edge IIR)", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_per_step, "ms_per_launch": ms_screen},
+            "roofline": roofline, "roofline_k1": roofline_k1, "roofline_step": roofline_step,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "phases_ms": dict({k: statistics.mean(s[k] for s in stats) for k in ("ms_screen", "ms_segment", "ms_lanes", "ms_gather", "ms_total", "ms_wall")},
@@ -552,6 +658,7 @@ def main():
                        "lane_runs": st["lane_runs"], "lane_samples_frac": st["lane_samples"] / max(1, st["samples"])},
             "parity_spot_check": parity, "frames_digest": "%016x" % digest_resident, "full_size_check": fullcheck,
             "full_parity": fullparity,
+            "wav_set": wavset,
         }
         print(json.dumps(line))
 

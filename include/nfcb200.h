@@ -142,6 +142,13 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
 int nfcb200_stream_push(nfcb200_handle *h, const void *samples, int sigtype, uint64_t n, uint32_t sample_rate, nfcb200_frame *out, uint64_t cap,
                         uint64_t *n_out);
 
+/*
+ * Frames of the stream that did not fit the buffer of an earlier nfcb200_stream_push (which then returned
+ * NFCB200_ERR_CAPACITY after delivering `cap` frames): delivers up to cap of them, *n_left = how many remain.  Nothing is
+ * lost on overflow; the stream state has advanced regardless.
+ */
+int nfcb200_stream_pending(nfcb200_handle *h, nfcb200_frame *out, uint64_t cap, uint64_t *n_out, uint64_t *n_left);
+
 /* forget the streaming state (NfcDecoder::initialize on a sample-rate change, NfcDecoder.cpp:383-388) */
 int nfcb200_stream_reset(nfcb200_handle *h);
 

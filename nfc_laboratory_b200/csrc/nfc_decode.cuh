@@ -183,6 +183,7 @@ struct SegmentConfig
    const uint32_t *segOffsets; // [n_streams] exclusive prefix of segCounts
    SegRec *segs;               // segment table, ordered by (stream, time)
    unsigned long long *featTotal; // feature samples allocated so far (every segment takes end - first)
+   uint32_t *activeTotal;         // active blocks (statistics), may be null
 };
 
 // ---- block-granular part of the screen, parallel over all blocks ---------------------------------------------------------
@@ -243,6 +244,13 @@ __global__ void segment_activate_kernel(SegmentConfig c)
 
    if (act)
       c.flags[i] |= SCR_ACTIVE; // other threads only read the trigger bit of this byte
+
+   if (c.activeTotal)
+   {
+      const unsigned m = __ballot_sync(__activemask(), act);
+      if (act && (threadIdx.x & 31) == (unsigned) (__ffs(m) - 1))
+         atomicAdd(c.activeTotal, (uint32_t) __popc(m));
+   }
 }
 
 // a segment starts at an active block with no active block among the previous GAP - 1 blocks (blocks_segments())

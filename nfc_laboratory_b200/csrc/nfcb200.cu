@@ -157,7 +157,7 @@ struct Counters
    unsigned long long work;
    unsigned long long live;
    u32 segTotal;
-   u32 pad;
+   u32 activeBlocks;
    unsigned long long featTotal;
    unsigned long long phase[16];
 };
@@ -217,6 +217,7 @@ struct nfcb200_handle
    int sSig = 0;
    bool sInit = false;
    u32 sEmitted = 0;     // frames already returned
+   std::vector<nfcb200_frame> sPending; // decoded but not yet delivered (the caller's buffer was too small)
 };
 
 static int setup_params(nfcb200_handle *h, u32 sampleRate)
@@ -606,6 +607,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    Counters *dC = h->counters.as<Counters>();
    CUDA_TRY(cudaMemsetAsync(dC, 0, sizeof(Counters), st));
    sg.segTotal = &dC->segTotal;
+   sg.activeTotal = &dC->activeBlocks;
    sg.group = 1;
 
    const u32 sgrid = (n_streams + 63) / 64;
@@ -879,6 +881,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
                  hc.phase[8 + i], hc.phase[8 + i] ? (double) hc.phase[i] / (double) hc.phase[8 + i] : 0.0);
    }
    S.live_lanes = hc.live;
+   S.active_blocks = prev.active_blocks + hc.activeBlocks;
 
    if (hc.poolCount > poolCap || hc.extCount > extCap)
       return fail(NFCB200_ERR_CAPACITY, "frame pool exhausted (%u frames, %u extension chunks)", hc.poolCount, hc.extCount);
@@ -1093,7 +1096,10 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
          uint64_t got = 0;
          rc = decode_resident(h, (unsigned char *) h->samples.ptr + (c & 1) * chunkBytes, sigtype, sc, n_samples, sample_rate, s0, out, cap, nf, &got);
          if (rc)
+         {
+            cudaStreamSynchronize(h->copyStream); // the next chunk's copy still reads the caller's buffer
             return rc;
+         }
          nf += got;
 
          float w = 0;
@@ -1233,6 +1239,23 @@ int nfcb200_stream_reset(nfcb200_handle *h)
    h->sBase = 0;
    h->sCount = 0;
    h->sEmitted = 0;
+   h->sHostTail.clear();
+   h->sPending.clear();
+   return 0;
+}
+
+int nfcb200_stream_pending(nfcb200_handle *h, nfcb200_frame *out, uint64_t cap, uint64_t *n_out, uint64_t *n_left)
+{
+   if (!h)
+      return fail(NFCB200_ERR_INVALID, "null handle");
+   const uint64_t deliver = std::min<uint64_t>(h->sPending.size(), out ? cap : 0);
+   for (uint64_t i = 0; i < deliver; i++)
+      out[i] = h->sPending[i];
+   h->sPending.erase(h->sPending.begin(), h->sPending.begin() + (size_t) deliver);
+   if (n_out)
+      *n_out = deliver;
+   if (n_left)
+      *n_left = h->sPending.size();
    return 0;
 }
 
@@ -1307,6 +1330,12 @@ int nfcb200_stream_push(nfcb200_handle *h, const void *samples, int sigtype, uin
    }
 
    const u32 bs = sig_bytes(h->sSig);
+
+   // The streaming lane keeps absolute sample positions in 32 bits like the reference's signalClock (NfcTech.h:338).  The
+   // reference wraps silently after 2^32 samples (7 minutes at 10 MS/s); here the position space must not wrap (retention and
+   // the flag window are indexed by it), so the stream refuses further samples with an explicit error instead of stalling.
+   if ((uint64_t) h->sBase + h->sCount + n >= 0xFFFF0000ull)
+      return fail(NFCB200_ERR_UNSUPPORTED, "stream position would pass 2^32 samples: call nfcb200_stream_reset (the reference's 32-bit sample clock wraps here)");
 
    // retained host-side tail + new samples -> device buffer covering absolute samples [sBase, sBase + sCount + n)
    const u32 newCount = h->sCount + (u32) n;
@@ -1433,12 +1462,11 @@ int nfcb200_stream_push(nfcb200_handle *h, const void *samples, int sigtype, uin
 
    std::sort(recs.begin(), recs.end(), [](const FrameRec &a, const FrameRec &b) { return a.seq < b.seq; });
 
-   uint64_t nf = 0;
+   // frames go through a pending list: what does not fit the caller's buffer is delivered by the next call, not lost
    for (const FrameRec &r: recs)
    {
-      if (nf < cap)
-         emit_frame(h, r, ext.data(), ext.size(), 0, h->sRate, out[nf]);
-      nf++;
+      h->sPending.emplace_back();
+      emit_frame(h, r, ext.data(), ext.size(), 0, h->sRate, h->sPending.back());
    }
 
    if (flush)
@@ -1446,20 +1474,23 @@ int nfcb200_stream_push(nfcb200_handle *h, const void *samples, int sigtype, uin
       // nextFrames({}): one carrier frame at the current clock (NfcDecoder.cpp:449-463)
       u32 clock = hs.pos - 1;
       bool on = hs.running ? hs.L.c.carrierOn != 0 : hs.carry.carrierOn != 0;
-      if (nf < cap)
-      {
-         nfcb200_frame &o = out[nf];
-         memset(&o, 0, sizeof(o));
-         o.tech_type = TT_Any;
-         o.frame_type = on ? FT_CarrierOn : FT_CarrierOff;
-         o.frame_phase = PH_Carrier;
-         o.sample_start = o.sample_end = clock;
-         o.sample_rate = h->sRate;
-         o.time_start = o.time_end = (double) clock / (double) h->sRate;
-         o.date_time = (double) h->P.streamTime + o.time_start;
-      }
-      nf++;
+      h->sPending.emplace_back();
+      nfcb200_frame &o = h->sPending.back();
+      memset(&o, 0, sizeof(o));
+      o.tech_type = TT_Any;
+      o.frame_type = on ? FT_CarrierOn : FT_CarrierOff;
+      o.frame_phase = PH_Carrier;
+      o.sample_start = o.sample_end = clock;
+      o.sample_rate = h->sRate;
+      o.time_start = o.time_end = (double) clock / (double) h->sRate;
+      o.date_time = (double) h->P.streamTime + o.time_start;
    }
+
+   const uint64_t nf = h->sPending.size();
+   const uint64_t deliver = std::min<uint64_t>(nf, cap);
+   for (uint64_t i = 0; i < deliver; i++)
+      out[i] = h->sPending[i];
+   h->sPending.erase(h->sPending.begin(), h->sPending.begin() + (size_t) deliver);
 
    // retention: keep what the parked / running lane can still need.  A running lane only reads forward (its history is in
    // its rings); a parked lane may cold start HALO samples before a later active block or be resumed at pos.
@@ -1480,10 +1511,11 @@ int nfcb200_stream_push(nfcb200_handle *h, const void *samples, int sigtype, uin
    }
 
    if (n_out)
-      *n_out = nf;
+      *n_out = deliver;
 
    if (nf > cap)
-      return fail(NFCB200_ERR_CAPACITY, "%llu frames decoded but room for %llu only", (unsigned long long) nf, (unsigned long long) cap);
+      return fail(NFCB200_ERR_CAPACITY, "%llu frames decoded but room for %llu only: the rest waits in nfcb200_stream_pending", (unsigned long long) nf,
+                  (unsigned long long) cap);
 
    return 0;
 }

@@ -34,8 +34,10 @@ struct NfcDecoder::Impl
    nfcb200_handle *handle = nullptr;
    bool debugEnabled = false;
    long sampleRate = 0;
-   bool dirty = true; // configuration changed since the last initialize
+   bool dirty = true; // configuration changed since the last initialize; applied by the next nextFrames / initialize
    std::vector<nfcb200_frame> frames;
+   int lastStatus = 0;       // status of the last library call (0 = ok): lab::NfcDecoder has no error channel and its callers
+   std::string lastMessage;  // (RadioDecoderTask.cpp:377-401) no try / catch -- failures are reported here, never thrown
 
    Impl()
    {
@@ -49,20 +51,32 @@ struct NfcDecoder::Impl
          nfcb200_destroy(handle);
    }
 
-   void ensure()
+   bool note(int rc)
+   {
+      lastStatus = rc;
+      lastMessage = rc ? nfcb200_last_error() : "";
+      return rc == 0;
+   }
+
+   bool ensure()
    {
       if (!handle)
       {
-         if (nfcb200_create(&cfg, &handle) != 0)
-            throw std::runtime_error(std::string("nfcb200: ") + nfcb200_last_error());
+         if (!note(nfcb200_create(&cfg, &handle)))
+         {
+            handle = nullptr;
+            return false;
+         }
          dirty = false;
       }
+      return true;
    }
 
    void initialize()
    {
-      ensure();
-      nfcb200_configure(handle, &cfg);
+      if (!ensure())
+         return;
+      note(nfcb200_configure(handle, &cfg));
       nfcb200_stream_reset(handle);
       dirty = false;
    }
@@ -87,7 +101,15 @@ struct NfcDecoder::Impl
    {
       std::list<RawFrame> result;
 
-      ensure();
+      if (!ensure())
+         return result; // no device: an empty list, the reason is in status()
+
+      if (dirty)
+      {
+         // a setter ran since the last initialize: the thresholds reach the device before the next samples
+         note(nfcb200_configure(handle, &cfg));
+         dirty = false;
+      }
 
       uint64_t count = 0;
       int rc;
@@ -118,24 +140,29 @@ struct NfcDecoder::Impl
 
          const float *data = samples.data() + samples.position();
 
-         for (;;)
-         {
-            rc = nfcb200_stream_push(handle, data, sigtype, n, (uint32_t) sampleRate, frames.data(), frames.size(), &count);
-            if (rc == NFCB200_ERR_CAPACITY && count > frames.size())
-               throw std::runtime_error("nfcb200: frame buffer overflow in streaming decode");
-            break;
-         }
+         rc = nfcb200_stream_push(handle, data, sigtype, n, (uint32_t) sampleRate, frames.data(), frames.size(), &count);
       }
       else
       {
          rc = nfcb200_stream_push(handle, nullptr, NFCB200_SIG_MAG_F32, 0, (uint32_t) sampleRate, frames.data(), frames.size(), &count);
       }
 
-      if (rc != 0)
-         throw std::runtime_error(std::string("nfcb200: ") + nfcb200_last_error());
-
       for (uint64_t i = 0; i < count; i++)
          result.push_back(convert(frames[i]));
+
+      // more frames than the buffer holds: drain the rest (nothing is dropped, nothing is thrown)
+      while (rc == NFCB200_ERR_CAPACITY)
+      {
+         uint64_t left = 0;
+         if (nfcb200_stream_pending(handle, frames.data(), frames.size(), &count, &left) != 0)
+            break;
+         for (uint64_t i = 0; i < count; i++)
+            result.push_back(convert(frames[i]));
+         if (left == 0)
+            rc = 0;
+      }
+
+      note(rc);
 
       return result;
    }
