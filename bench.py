@@ -597,7 +597,40 @@ def main():
             same = ND.frames_digest(ND.frames_as_array(buf, nf)) == digest_resident
             if not same:
                 raise SystemExit("the host-input decode and the device-resident decode of the same batch differ: refusing to report a number")
-        e2e = {"value": world * Se * n * esteps / de / 1e6, "unit": UNIT, "h2d_bytes_per_step": Se * n * 8, "d2h_bytes_per_step": int(d2h),
+        # the same batch as 16-bit IQ (the WAV ingest format, SIG_IQ_S16: 4 bytes per sample): half the PCIe bytes
+        e2e_s16 = None
+        try:
+            del host
+            host16 = torch.empty((Se, n, 2), dtype=torch.int16, pin_memory=not flow_test)
+            for c0 in range(0, Se, 16):
+                host16[c0:c0 + 16].copy_((iq[c0:c0 + 16] * 32768.0).round().clamp_(-32768, 32767).to(torch.int16))
+            torch.cuda.synchronize()
+            if not flow_test:
+                dec.decode_batch_ptr(host16.data_ptr(), False, N.SIG_IQ_S16, Se, n, RATE, cap=cap, raw=True)  # warm
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                t2 = time.perf_counter()
+                nf16 = 0
+                for _ in range(esteps):
+                    buf16, nf16 = dec.decode_batch_ptr(host16.data_ptr(), False, N.SIG_IQ_S16, Se, n, RATE, cap=cap, raw=True)
+                    gather(buf16, nf16)
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                d16 = time.perf_counter() - t2
+                tm16 = torch.tensor([d16], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(tm16, op=dist.ReduceOp.MAX)
+                d16 = float(tm16.item())
+                e2e_s16 = {"value": world * Se * n * esteps / d16 / 1e6, "unit": UNIT, "h2d_bytes_per_step": Se * n * 4, "streams": Se,
+                           "frames_per_step": int(nf16), "note": "host-pinned int16 IQ (SIG_IQ_S16) -> nfcb200_decode_batch -> frames in host memory"}
+            del host16
+            host = None
+        except Exception as e:
+            e2e_s16 = {"error": "%s: %s" % (type(e).__name__, e)}
+            host = None
+        e2e = {"value": world * Se * n * esteps / de / 1e6, "unit": UNIT, "h2d_bytes_per_step": Se * n * 8, "d2h_bytes_per_step": int(d2h), "steps": esteps, "s16": e2e_s16,
                "streams": Se, "same_frames_as_resident": same, "note": "host-pinned float2 IQ -> nfcb200_decode_batch -> frames in host memory"
                                       + ("" if Se == S else " (sub-batch of %d streams: host memory bound)" % Se)}
         del host

@@ -149,6 +149,16 @@ int nfcb200_stream_push(nfcb200_handle *h, const void *samples, int sigtype, uin
  */
 int nfcb200_stream_pending(nfcb200_handle *h, nfcb200_frame *out, uint64_t cap, uint64_t *n_out, uint64_t *n_left);
 
+/*
+ * Per-sample value tap on the device (debug / test): ONE lane of the decoder over a host capture, one row of 8 floats per
+ * sample from `first` on -- [x, w, deviation, average, channel 4, channel 5, lock state, 0], the channels of the
+ * reference's signal debugger (NfcTech.h:32-37, NfcDecoder::setEnableDebug), NaN where a channel was not written.
+ * first = 0: the exact stream start; otherwise a cold start with `warm` warm-up samples.  rows must hold (n - first) * 8
+ * floats.  Slow by design (one GPU thread); the product kernels compile the taps away.
+ */
+int nfcb200_debug_trace(const nfcb200_config *cfg, const void *samples, int sigtype, uint64_t n, uint32_t sample_rate, uint32_t first,
+                        uint32_t warm, float *rows);
+
 /* forget the streaming state (NfcDecoder::initialize on a sample-rate change, NfcDecoder.cpp:383-388) */
 int nfcb200_stream_reset(nfcb200_handle *h);
 
