@@ -147,6 +147,8 @@ struct WShared
    float cavg[32];   // carrier average of the chunk's samples
    u32 act;          // control: what the warp does next (WLANE_*)
    u32 pos, n, mode, si, j, stepped, blockActive;
+   float scalEnv, scalAvg, scalDev, scalF1; // front-end state of a lane past its feature range (fill_front)
+   u32 scalPulse;
    u32 nextB, nextSeg, nextCls, nextFrom; // cached look-ahead of the current inactive run: next active block, its segment, gap class
    u32 jumpCls, jumpTa, jumpGs, jumpT, jumpG, jumpB, jumpSeg;
    float delta[6];
@@ -272,6 +274,61 @@ struct WLane
             F.closed = 64;
          else
             F.closed = F.closed >= 32 ? F.closed - 32 : 0;
+      }
+   }
+
+   // the same for a chunk WITHOUT features: the recurrences of nextSample (NfcTech.cpp:39-68) from the lane's own state
+   NFC_HD void fill_front(u32 pos, u32 n, u32 k0)
+   {
+      fill_x(pos, n, k0);
+      W::sync();
+
+      if (W::lane() == 0)
+      {
+         float env = sh.scalEnv, avg = sh.scalAvg, dev = sh.scalDev, f1 = sh.scalF1;
+         u32 pulse = sh.scalPulse, closed = F.closed;
+         const u32 hold = (u32) (P.etu * 10);
+
+         for (u32 i = 0; i < n; i++)
+         {
+            const u32 s = slot(k0 + 1 + i, 0);
+            const float x = rg[NFCB200_OFF_X + s];
+
+            ++pulse;
+
+            const float adiff = fabsf(x - env);
+            const bool open = gate_open(adiff, env);
+
+            if (open)
+               closed = closed ? closed - 1 : 0;
+            else if (closed < 4096)
+               closed++;
+
+            if (open || pulse > hold)
+            {
+               pulse = 0;
+               env = env * P.envW0 + x * P.envW1;
+            }
+
+            float n0 = x + f1 * P.iirA;
+            float w = n0 - f1;
+            f1 = n0;
+
+            dev = dev * P.mdevW0 + fabsf(w) * P.mdevW1;
+            avg = avg * P.meanW0 + x * P.meanW1;
+
+            rg[NFCB200_OFF_W + s] = w;
+            rg[NFCB200_OFF_D + s] = dev;
+            rg[NFCB200_OFF_M + s] = env;
+            sh.cavg[i] = avg;
+         }
+
+         sh.scalEnv = env;
+         sh.scalAvg = avg;
+         sh.scalDev = dev;
+         sh.scalF1 = f1;
+         sh.scalPulse = pulse;
+         F.closed = closed;
       }
    }
 
@@ -942,11 +999,11 @@ struct WLane
    {
       // the lane ran past its feature range without settling: it continues with the per-sample front end from the state
       // the front pass left at the end of the range
-      F.env = S.tEnv;
-      F.avg = S.tAvg;
-      F.dev = S.tDev;
-      F.f1 = S.tF1;
-      F.pulseFilter = S.tPulse;
+      sh.scalEnv = S.tEnv;
+      sh.scalAvg = S.tAvg;
+      sh.scalDev = S.tDev;
+      sh.scalF1 = S.tF1;
+      sh.scalPulse = S.tPulse;
       sh.mode = WMODE_SCAL;
    }
 
@@ -1156,13 +1213,12 @@ struct WLane
          }
          else
          {
-            if (W::lane() == 0)
-            {
-               M.featMode = false;
-               for (u32 i = 0; i < n; i++)
-                  M.step(src.x(pos + i));
-            }
+            // past the feature range: the front-end recurrences of the chunk run here, on one thread, from the lane's own
+            // state; everything behind them is the same chunk path
+            fill_front(pos, n, k0);
+            W::sync();
             tick(WPH_SCALAR, t0, n);
+            chunk_feat(n);
          }
 
          if (W::lane() == 0)

@@ -635,6 +635,13 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       u32 group;
       if (h->cfg.segments_per_lane)
          group = h->cfg.segments_per_lane;
+      else if (exact && sigtype == SIG_MAG_S16 && (uint64_t) n_streams < (uint64_t) h->smCount * (uint64_t) h->wlanesPerSm)
+      {
+         // 16-bit mono input adds exactly whatever the history of a running sum: a stream may be cut into several warp lanes
+         // (cold starts + carry chain) without losing a bit -- small batches fill the machine that way
+         const uint64_t resident = (uint64_t) h->smCount * (uint64_t) h->wlanesPerSm;
+         group = (u32) std::max<uint64_t>(1, segTotal / (resident * 2));
+      }
       else if (exact)
          group = 0xFFFFFFFFu; // one lane per stream
       else
