@@ -463,7 +463,7 @@ def main():
         buf, nf = dec.decode_batch_ptr(iq.data_ptr(), True, N.SIG_IQ_F32, S, n, RATE, cap=cap, raw=True)
         return buf, nf
 
-    gather_ms = {"gather_pack": [], "gather_nccl": [], "gather_d2h": []}
+    gather_ms = {"gather_pack": [], "gather_nccl": [], "gather_d2h": [], "gather_d2h_alloc": [], "gather_d2h_issue": [], "gather_d2h_wait": []}
 
     def gather(buf, nf):
         """frames of all ranks on rank 0.  GPUs: the packed device records of the decode go to rank 0 over NCCL point to point
@@ -520,10 +520,10 @@ def main():
     # frame gather phases of the timed steps, max over ranks (the last gather_steps entries: warm-up and e2e gathers excluded)
     gather_phases = {}
     if world > 1 and gather_ms["gather_nccl"]:
-        vals = torch.tensor([statistics.mean(gather_ms[k][len(gather_ms[k]) - args.steps:]) for k in ("gather_pack", "gather_nccl", "gather_d2h")],
-                            dtype=torch.float64, device=dev)
+        keys = list(gather_ms)
+        vals = torch.tensor([statistics.mean(gather_ms[k][len(gather_ms[k]) - args.steps:]) for k in keys], dtype=torch.float64, device=dev)
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-        gather_phases = {"gather_pack": float(vals[0]), "gather_nccl": float(vals[1]), "gather_d2h": float(vals[2])}
+        gather_phases = {k: float(v) for k, v in zip(keys, vals)}
 
     value = world * S * n * args.steps / dt / 1e6
 

@@ -214,7 +214,7 @@ def gather_device_frames(dec, device, stream_offset, sample_rate, group=None, ti
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
         if timings is not None:
             timings.update(gather_pack=(t1 - t0) * 1e3, gather_nccl=(time.perf_counter() - t1) * 1e3, gather_d2h=0.0)
         return None
@@ -233,7 +233,7 @@ def gather_device_frames(dec, device, stream_offset, sample_rate, group=None, ti
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-    torch.cuda.synchronize()
+    torch.cuda.current_stream().synchronize()
     t2 = time.perf_counter()
 
     # device -> page-locked host, one staging buffer for all ranks' records and one for their extension chunks
@@ -241,6 +241,7 @@ def gather_device_frames(dec, device, stream_offset, sample_rate, group=None, ti
     tot_e = sum(c[1] for c in allc[1:])
     hr = _pinned_bytes("recv_r", max(tot_r, 1) * 128)
     he = _pinned_bytes("recv_e", max(tot_e, 1) * 128)
+    t2a = time.perf_counter()
     pr = pe = 0
     spans = []
     for (rb, eb), (nr, er) in zip(bufs, allc[1:]):
@@ -251,11 +252,13 @@ def gather_device_frames(dec, device, stream_offset, sample_rate, group=None, ti
         spans.append((pr, nr, pe, er))
         pr += nr * 128
         pe += er * 128
-    torch.cuda.synchronize()
+    t2b = time.perf_counter()
+    torch.cuda.current_stream().synchronize()
     t3 = time.perf_counter()
 
     if timings is not None:
-        timings.update(gather_pack=(t1 - t0) * 1e3, gather_nccl=(t2 - t1) * 1e3, gather_d2h=(t3 - t2) * 1e3)
+        timings.update(gather_pack=(t1 - t0) * 1e3, gather_nccl=(t2 - t1) * 1e3, gather_d2h=(t3 - t2) * 1e3,
+                       gather_d2h_alloc=(t2a - t2) * 1e3, gather_d2h_issue=(t2b - t2a) * 1e3, gather_d2h_wait=(t3 - t2b) * 1e3)
     return GatheredRecords(hr, he, spans, stream_offset, sample_rate)
 
 
