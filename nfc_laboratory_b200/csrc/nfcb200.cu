@@ -390,6 +390,13 @@ int nfcb200_create(const nfcb200_config *cfg, nfcb200_handle **out)
 
    CUDA_TRY(cudaSetDevice(c.device));
 
+   // Host threads SLEEP while they wait for the device (the default is to spin).  A decode waits ~0.2 s per batch on a
+   // stream; with one process per GPU and a CPU quota shared by all of them (16 cores for 8 ranks on this pool) spinning
+   // waiters exhaust the quota and the whole cgroup is throttled for tens of milliseconds at arbitrary points -- measured
+   // as 50-125 ms stalls inside trivial host code at 2 GPUs, and as the 0.59 weak-scaling efficiency of round 1 at 4 / 8.
+   cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);
+   cudaGetLastError(); // older runtimes refuse to change the flags of an initialised context: not fatal
+
    nfcb200_handle *h = new nfcb200_handle();
    h->cfg = c;
    h->device = c.device;

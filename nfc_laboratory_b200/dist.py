@@ -219,6 +219,14 @@ def gather_device_frames(dec, device, stream_offset, sample_rate, group=None, ti
             timings.update(gather_pack=(t1 - t0) * 1e3, gather_nccl=(time.perf_counter() - t1) * 1e3, gather_d2h=0.0)
         return None
 
+    # page-locked staging for what the other ranks send (cached: allocated on the first call, grown when needed)
+    t1a = time.perf_counter()
+    tot_r = sum(c[0] for c in allc[1:])
+    tot_e = sum(c[1] for c in allc[1:])
+    hr = _pinned_bytes("recv_r", max(tot_r, 1) * 128)
+    he = _pinned_bytes("recv_e", max(tot_e, 1) * 128)
+    t1b = time.perf_counter()
+
     bufs = []
     ops = []
     for r in range(1, world):
@@ -237,10 +245,6 @@ def gather_device_frames(dec, device, stream_offset, sample_rate, group=None, ti
     t2 = time.perf_counter()
 
     # device -> page-locked host, one staging buffer for all ranks' records and one for their extension chunks
-    tot_r = sum(c[0] for c in allc[1:])
-    tot_e = sum(c[1] for c in allc[1:])
-    hr = _pinned_bytes("recv_r", max(tot_r, 1) * 128)
-    he = _pinned_bytes("recv_e", max(tot_e, 1) * 128)
     t2a = time.perf_counter()
     pr = pe = 0
     spans = []
@@ -257,8 +261,8 @@ def gather_device_frames(dec, device, stream_offset, sample_rate, group=None, ti
     t3 = time.perf_counter()
 
     if timings is not None:
-        timings.update(gather_pack=(t1 - t0) * 1e3, gather_nccl=(t2 - t1) * 1e3, gather_d2h=(t3 - t2) * 1e3,
-                       gather_d2h_alloc=(t2a - t2) * 1e3, gather_d2h_issue=(t2b - t2a) * 1e3, gather_d2h_wait=(t3 - t2b) * 1e3)
+        timings.update(gather_pack=(t1 - t0) * 1e3, gather_nccl=(t2 - t1b) * 1e3, gather_d2h=(t3 - t2) * 1e3,
+                       gather_d2h_alloc=(t1b - t1a) * 1e3, gather_d2h_issue=(t2b - t2a) * 1e3, gather_d2h_wait=(t3 - t2b) * 1e3)
     return GatheredRecords(hr, he, spans, stream_offset, sample_rate)
 
 
