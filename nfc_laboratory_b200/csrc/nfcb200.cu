@@ -1038,6 +1038,8 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
    const uint64_t total = (uint64_t) n_streams * n_samples;
 
    memset(&h->stats, 0, sizeof(h->stats));
+   h->packedCount = 0;      // the packed frames of a call: every chunk of this call appends
+   h->packedExtCount = 0;
    nfcb200_stats &S = h->stats;
    Trace wall;
 

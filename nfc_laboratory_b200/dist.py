@@ -124,13 +124,23 @@ _pinned = {}
 def _pinned_bytes(key, n):
     """a cached page-locked uint8 host tensor of at least n bytes (None when pinning is not possible, e.g. no CUDA)"""
     import torch
+    import os
+    import sys
+    import time
     try:
+        t0 = time.perf_counter()
         t = _pinned.get(key)
-        if t is None or t.numel() < n:
+        fresh = t is None or t.numel() < n
+        if fresh:
             t = torch.empty(max(n, 1) + max(n, 1) // 4, dtype=torch.uint8, pin_memory=True)
             _pinned[key] = t
+        if os.environ.get("NFCB200_GATHER_DEBUG"):
+            print("[dist] pinned %s: need %d, have %d, %s, %.2f ms" % (key, n, t.numel(), "allocated" if fresh else "cached", (time.perf_counter() - t0) * 1e3),
+                  file=sys.stderr, flush=True)
         return t
-    except Exception:
+    except Exception as e:
+        if os.environ.get("NFCB200_GATHER_DEBUG"):
+            print("[dist] pinned %s failed: %s" % (key, e), file=sys.stderr, flush=True)
         return None
 
 
@@ -223,9 +233,13 @@ def gather_device_frames(dec, device, stream_offset, sample_rate, group=None, ti
     t1a = time.perf_counter()
     tot_r = sum(c[0] for c in allc[1:])
     tot_e = sum(c[1] for c in allc[1:])
+    t1x = time.perf_counter()
     hr = _pinned_bytes("recv_r", max(tot_r, 1) * 128)
     he = _pinned_bytes("recv_e", max(tot_e, 1) * 128)
     t1b = time.perf_counter()
+    if __import__("os").environ.get("NFCB200_GATHER_DEBUG"):
+        print("[dist] gather rank0: counts %.3f ms, sums %.3f ms, staging %.3f ms" % ((t1 - t0) * 1e3, (t1x - t1a) * 1e3, (t1b - t1x) * 1e3),
+              file=__import__("sys").stderr, flush=True)
 
     bufs = []
     ops = []
