@@ -497,10 +497,15 @@ def main():
     t0 = time.perf_counter()
     stats = []
     frames_total = 0
+    t_decode, t_gather = [], []
     for _ in range(args.steps):
+        ta = time.perf_counter()
         buf, nf = step_device()
+        tb = time.perf_counter()
         stats.append(dec.stats())
         frames_total += gather(buf, nf)
+        t_decode.append((tb - ta) * 1e3)
+        t_gather.append((time.perf_counter() - tb) * 1e3)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -516,6 +521,16 @@ def main():
     dt = float(tmax.item())
 
     clocks = sampler.summary() if rank == 0 else None
+
+    # host wall time of the decode call and of the gather per step: slowest and fastest rank (the weak-scaling loss is the spread)
+    rank_spread = None
+    if world > 1:
+        v = torch.tensor([statistics.mean(t_decode), statistics.mean(t_gather)], dtype=torch.float64, device=dev)
+        vmax, vmin = v.clone(), v.clone()
+        dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(vmin, op=dist.ReduceOp.MIN)
+        rank_spread = {"decode_call_ms_max": float(vmax[0]), "decode_call_ms_min": float(vmin[0]), "gather_call_ms_max": float(vmax[1]),
+                       "gather_call_ms_min": float(vmin[1])}
 
     # frame gather phases of the timed steps, max over ranks (the last gather_steps entries: warm-up and e2e gathers excluded)
     gather_phases = {}
@@ -692,6 +707,7 @@ def main():
             "parity_spot_check": parity, "frames_digest": "%016x" % digest_resident, "full_size_check": fullcheck,
             "full_parity": fullparity,
             "wav_set": wavset,
+            "rank_spread": rank_spread,
         }
         print(json.dumps(line))
 

@@ -168,6 +168,20 @@ int nfcb200_get_stats(nfcb200_handle *h, nfcb200_stats *stats);
 int nfcb200_get_block_flags(nfcb200_handle *h, uint8_t *out, uint64_t cap, uint64_t *n_blocks_per_stream);
 
 /*
+ * Time shards of ONE long capture (BASELINE.json configs[4]): a shard that does not start at the capture's first sample
+ * continues its predecessor's decoder.  After a single-stream nfcb200_decode_batch, nfcb200_carry_before returns the carry
+ * of the decoder in front of the first lane that begins at or after `sample` (*lane_begin: that lane's begin, an idle point
+ * of the capture; ~0 when there is none).  nfcb200_set_carry hands such a carry to the NEXT single-stream decode of a handle
+ * (one shot; clock_shift is subtracted from the absolute sample times it holds: the next window counts from its own first
+ * sample).  The blob is opaque, nfcb200_carry_size() bytes: protocol state (FSD / FWT / SFGT from RATS / ATS / ATTRIB, the
+ * Encrypted flag, lastCommand -- NfcA.cpp:1592-1790, NfcB.cpp:1153-1258), carrier flags, the carrier edge time.
+ */
+int nfcb200_carry_size(void);
+int nfcb200_default_carry(nfcb200_handle *h, void *blob, uint64_t cap); /* what a cold-started lane assumes: power-on state, carrier on */
+int nfcb200_set_carry(nfcb200_handle *h, const void *blob, uint64_t size, uint32_t clock_shift);
+int nfcb200_carry_before(nfcb200_handle *h, uint64_t sample, void *blob, uint64_t cap, uint64_t *size, uint64_t *lane_begin);
+
+/*
  * Multi-GPU frame gather (no counterpart in the reference, which has no second device): the frames of the
  * last nfcb200_decode_batch call as they sit in DEVICE memory -- ordered by (stream, time), 128-byte records (stream,
  * header fields, the first 80 payload bytes) plus 128-byte extension chunks for longer payloads -- so that a rank can hand

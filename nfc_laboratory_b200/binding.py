@@ -76,7 +76,8 @@ class Frame(tuple):
 EXPORTS = [
     "nfcb200_config_default", "nfcb200_create", "nfcb200_destroy", "nfcb200_configure", "nfcb200_decode_batch",
     "nfcb200_stream_push", "nfcb200_stream_reset", "nfcb200_get_stats", "nfcb200_get_block_flags", "nfcb200_pack_frames",
-    "nfcb200_last_error", "nfcb200_version", "nfcb200_device_frames", "nfcb200_emit_records", "nfcb200_stream_pending", "nfcb200_debug_trace",
+    "nfcb200_last_error", "nfcb200_version", "nfcb200_device_frames", "nfcb200_emit_records", "nfcb200_stream_pending", "nfcb200_debug_trace", "nfcb200_carry_size", "nfcb200_set_carry",
+    "nfcb200_carry_before", "nfcb200_default_carry",
 ]
 
 
@@ -111,6 +112,10 @@ def load_library():
     lib.nfcb200_get_stats.argtypes = [C.c_void_p, C.POINTER(CStats)]
     lib.nfcb200_get_block_flags.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.nfcb200_pack_frames.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.nfcb200_carry_size.restype = C.c_int
+    lib.nfcb200_default_carry.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.nfcb200_set_carry.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint32]
+    lib.nfcb200_carry_before.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.nfcb200_device_frames.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.nfcb200_emit_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(CFrame),
                                          C.c_uint64, C.POINTER(C.c_uint64)]
@@ -240,6 +245,33 @@ class NfcDecoder:
                 continue
             _check(self._lib, rc)
             return (buf, n.value) if raw else self._convert(buf, n.value)
+
+    def set_carry(self, blob, clock_shift=0):
+        """carry in front of the next single-stream decode (a time shard continuing a capture); None clears"""
+        if blob is None:
+            _check(self._lib, self._lib.nfcb200_set_carry(self._h, None, 0, 0))
+        else:
+            b = bytes(blob)
+            _check(self._lib, self._lib.nfcb200_set_carry(self._h, b, len(b), int(clock_shift)))
+
+    def carry_size(self):
+        return int(self._lib.nfcb200_carry_size())
+
+    def default_carry(self):
+        """the carry a cold-started lane assumes in front of it (power-on protocol state, carrier on)"""
+        n = self.carry_size()
+        buf = C.create_string_buffer(n)
+        _check(self._lib, self._lib.nfcb200_default_carry(self._h, buf, n))
+        return buf.raw
+
+    def carry_before(self, sample):
+        """(carry blob, lane_begin) of the last single-stream decode: the decoder's carry in front of the first lane that
+        begins at or after `sample`; lane_begin is None when no lane begins there"""
+        n = self._lib.nfcb200_carry_size()
+        buf = C.create_string_buffer(n)
+        size, begin = C.c_uint64(0), C.c_uint64(0)
+        _check(self._lib, self._lib.nfcb200_carry_before(self._h, int(sample), buf, n, C.byref(size), C.byref(begin)))
+        return buf.raw, (None if begin.value == 0xFFFFFFFFFFFFFFFF else int(begin.value))
 
     def device_frames(self):
         """(records_ptr, n_records, ext_ptr, n_ext_chunks): the frames of the last decode_batch as they sit in device memory,

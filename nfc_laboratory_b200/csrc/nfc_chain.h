@@ -237,6 +237,10 @@ NFC_HD bool lane_iterate(MACH &M, Lane &L, const Params &P, u32 &pos, u32 end, u
    return true;
 }
 
+// carry composed in front of the first live lane that begins at or after `sample` (valid once the chain has converged);
+// laneBegin receives that lane's begin (or 0xFFFFFFFF when the stream has no such lane: the carry is then the final one)
+NFC_HD void carry_before(LaneRec *lanes, u32 n, const Params &P, const Carry *init, u32 sample, Carry &out, u32 &laneBegin);
+
 // copy the outcome of a finished run into its record
 NFC_HD void lane_record(LaneRec &R, const Lane &L, u32 stop, u32 gen, u32 nframes)
 {
@@ -428,11 +432,16 @@ NFC_HD void carry_speculate(Carry &c, const Params &P)
  *   - the carry after a lane is PREDICTED for lanes that must re-run: groups the last run left unchanged are assumed
  *     to pass the corrected value through (pure heuristic -- validity is only ever established by the equality test)
  */
-NFC_HD u32 chain_walk(LaneRec *lanes, u32 n, const Params &P)
+NFC_HD u32 chain_walk(LaneRec *lanes, u32 n, const Params &P, const Carry *init = nullptr)
 {
    Carry cur;
-   carry_init(cur, P);
-   carry_canon(cur);
+   if (init)
+      cur = *init; // the stream does not start at power-on: a time shard of a longer capture continues its predecessor's carry
+   else
+   {
+      carry_init(cur, P);
+      carry_canon(cur);
+   }
 
    u32 ndirty = 0;
    int prev = -1;
@@ -516,6 +525,41 @@ NFC_HD u32 chain_walk(LaneRec *lanes, u32 n, const Params &P)
    }
 
    return ndirty;
+}
+
+
+NFC_HD void carry_before(LaneRec *lanes, u32 n, const Params &P, const Carry *init, u32 sample, Carry &out, u32 &laneBegin)
+{
+   Carry cur;
+   if (init)
+      cur = *init;
+   else
+   {
+      carry_init(cur, P);
+      carry_canon(cur);
+   }
+
+   laneBegin = 0xFFFFFFFFu;
+
+   for (u32 j = 0; j < n; j++)
+   {
+      LaneRec &L = lanes[j];
+      if (L.dead)
+         continue;
+      if (L.begin >= sample)
+      {
+         laneBegin = L.begin;
+         break;
+      }
+      if (L.gen > 0)
+      {
+         Carry next = cur;
+         carry_compose(L, cur, next, 0x10F | ((L.lockedMask & 0xF) << 4));
+         cur = next;
+      }
+   }
+
+   out = cur;
 }
 
 }

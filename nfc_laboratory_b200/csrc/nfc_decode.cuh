@@ -184,6 +184,7 @@ struct SegmentConfig
    SegRec *segs;               // segment table, ordered by (stream, time)
    unsigned long long *featTotal; // feature samples allocated so far (every segment takes end - first)
    uint32_t *activeTotal;         // active blocks (statistics), may be null
+   const Carry *carryIn;          // carry in front of the first lane of stream 0 (a time shard continuing a capture), or null
 };
 
 // ---- block-granular part of the screen, parallel over all blocks ---------------------------------------------------------
@@ -393,6 +394,13 @@ __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Par
       carry_speculate(spec, dP);
       carry_init(pon, dP);
       carry_canon(pon);
+      if (c.carryIn && s == 0)
+      {
+         // the stream continues a capture: its first lane starts from the injected carry, the later ones speculate that
+         // the session state it carries is still in force
+         pon = *c.carryIn;
+         spec = *c.carryIn;
+      }
 
       for (uint32_t j = 0; j < nLanes; j++)
       {
@@ -841,6 +849,7 @@ __global__ void __launch_bounds__(32) wlanes_kernel(WLaneConfig c, const __grid_
 // ---------------------------------------------------------------------------------------------------------------------
 struct ChainConfig
 {
+   const Carry *carryIn; // carry in front of the first lane of stream 0, or null (power-on)
    LaneRec *lanes;
    const uint32_t *offsets;
    const uint32_t *counts;
@@ -893,7 +902,7 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_warp_kernel(ChainConfi
       Carry pon;
       carry_init(pon, dP);
       carry_canon(pon);
-      const u32 *raw = (const u32 *) &pon;
+      const u32 *raw = (c.carryIn && s == 0) ? (const u32 *) c.carryIn : (const u32 *) &pon;
       for (u32 w = lane; w < CARRY_WORDS; w += 32)
          cur[w] = raw[w];
    }
@@ -1005,6 +1014,18 @@ __global__ void lane_length_kernel(const LaneRec *lanes, uint32_t n, uint32_t *l
    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i < n)
       length[i] = lanes[i].end - lanes[i].first;
+}
+
+// carry in front of the first lane of stream 0 that begins at or after `sample` (nfc_chain.h carry_before)
+__global__ void carry_before_kernel(LaneRec *lanes, uint32_t n, const Carry *carryIn, uint32_t sample, Carry *out, uint32_t *laneBegin, const __grid_constant__ Params dP)
+{
+   if (threadIdx.x != 0 || blockIdx.x != 0)
+      return;
+   Carry c;
+   u32 b;
+   carry_before(lanes, n, dP, carryIn, sample, c, b);
+   *out = c;
+   *laneBegin = b;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

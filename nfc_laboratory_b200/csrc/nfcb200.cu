@@ -8,6 +8,7 @@
  * There is no CPU fallback in this library: every entry point that decodes requires a CUDA device.
  */
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <chrono>
@@ -162,6 +163,33 @@ struct Counters
    unsigned long long phase[16];
 };
 
+// Host threads this process may use for the conversion of frame records: the CPUs it is allowed to run on (affinity, clipped
+// by a cgroup CPU quota) divided by the processes that share them (one per GPU under torchrun: LOCAL_WORLD_SIZE).  With 8
+// ranks on a 16-CPU quota, 8 x 16 conversion threads exhausted the quota and the kernel throttled the whole job.
+static unsigned host_workers()
+{
+   static unsigned cached = 0;
+   if (cached)
+      return cached;
+   unsigned n = std::max(1u, std::thread::hardware_concurrency());
+   cpu_set_t set;
+   if (sched_getaffinity(0, sizeof(set), &set) == 0)
+      n = std::max(1, CPU_COUNT(&set));
+   if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r"))
+   {
+      char q[64] = "";
+      double per = 0;
+      if (fscanf(f, "%63s %lf", q, &per) == 2 && strcmp(q, "max") != 0 && per > 0)
+         n = std::max(1u, std::min(n, (unsigned) (atof(q) / per + 0.5)));
+      fclose(f);
+   }
+   unsigned share = 1;
+   if (const char *e = getenv("LOCAL_WORLD_SIZE"))
+      share = (unsigned) std::max(1, atoi(e));
+   cached = std::max(1u, std::min(16u, n / share));
+   return cached;
+}
+
 // host-side milestones of a call, printed when NFCB200_TRACE is set (debug aid)
 struct Trace
 {
@@ -197,6 +225,11 @@ struct nfcb200_handle
    int shortHalo = 1;   // NFCB200_HALO_SHORT=0 forces the long warm-up for every segment (measurement knob)
 
    HostBuf hRecs, hExt; // gather staging
+   DevBuf carryDev;                    // injected carry (nfcb200_set_carry) / carry query result
+   Carry carryIn;                      // host copy of the injected carry
+   bool haveCarryIn = false;
+   bool lastCarryInUsed = false;       // the last decode started from the injected carry
+   u32 lastLanes = 0;                  // lanes of the last single-stream decode (nfcb200_carry_before)
    DevBuf packed, packedExt, packCtr; // frames of the current call, ordered and packed on the device (all chunks)
    uint64_t packedCount = 0;           // records in `packed`
    u32 packedExtCount = 0;             // 128-byte chunks in `packedExt`
@@ -445,7 +478,7 @@ void nfcb200_destroy(nfcb200_handle *h)
       return;
    cudaSetDevice(h->device);
    cudaStreamSynchronize(h->stream);
-   DevBuf *bufs[] = {&h->samples, &h->flags, &h->bsum, &h->counts, &h->offsets, &h->lanes, &h->queue, &h->segCounts, &h->segOffsets, &h->segs, &h->feats, &h->scratch, &h->sbuf, &h->pool, &h->ext, &h->meta, &h->packed, &h->packedExt, &h->packCtr,
+   DevBuf *bufs[] = {&h->samples, &h->flags, &h->bsum, &h->counts, &h->offsets, &h->lanes, &h->queue, &h->segCounts, &h->segOffsets, &h->segs, &h->feats, &h->scratch, &h->sbuf, &h->pool, &h->ext, &h->meta, &h->carryDev, &h->packed, &h->packedExt, &h->packCtr,
                      &h->counters, &h->sState, &h->sScratch, &h->sSbuf, &h->sSamples, &h->sFlags, &h->sBsum, &h->sCounts};
    for (DevBuf *b: bufs)
       b->release();
@@ -568,6 +601,19 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       rc = rc ? rc : h->counters.reserve(sizeof(Counters));
       if (rc)
          return rc;
+   }
+
+   // a single-stream decode may continue a capture: the carry in front of its first lane (nfcb200_set_carry, one shot)
+   const Carry *dCarryIn = nullptr;
+   {
+      int rc = h->carryDev.reserve(2 * sizeof(Carry) + 16);
+      if (rc)
+         return rc;
+      if (h->haveCarryIn && n_streams == 1 && streamBase == 0)
+      {
+         CUDA_TRY(cudaMemcpyAsync(h->carryDev.ptr, &h->carryIn, sizeof(Carry), cudaMemcpyHostToDevice, st));
+         dCarryIn = h->carryDev.as<Carry>();
+      }
    }
 
    ScreenConfig sc;
@@ -703,6 +749,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    sg.segOffsets = h->segOffsets.as<u32>();
    sg.segs = h->segs.as<SegRec>();
    sg.featTotal = &dC->featTotal;
+   sg.carryIn = dCarryIn;
    segment_fill_kernel<<<n_streams, 32, 0, st>>>(sg, h->P);
    launches++;
    CUDA_TRY(cudaGetLastError());
@@ -797,6 +844,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    lc.phase = dC->phase;
 
    ChainConfig cc;
+   cc.carryIn = dCarryIn;
    cc.lanes = h->lanes.as<LaneRec>();
    cc.offsets = h->offsets.as<u32>();
    cc.counts = h->counts.as<u32>();
@@ -953,7 +1001,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       const FrameRec *recs = h->hRecs.as<FrameRec>();
       const unsigned char *ext = h->hExt.as<unsigned char>();
       const uint64_t count = outOffset >= cap ? 0 : std::min<uint64_t>(nf, cap - outOffset);
-      const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(16, count / 4096));
+      const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(host_workers(), count / 4096));
       auto work = [&](uint64_t lo, uint64_t hi) {
          for (uint64_t i = lo; i < hi; i++)
          {
@@ -981,6 +1029,10 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
 
    h->lastStreams = n_streams;
    h->lastBlocks = n_blocks;
+   h->lastLanes = n_streams == 1 ? nLanes : 0;
+   h->lastCarryInUsed = dCarryIn != nullptr;
+   if (dCarryIn)
+      h->haveCarryIn = false; // one shot
 
    // accumulate the statistics over the chunks of one call
    float msScreen = 0, msSeg = 0, msLanes = 0, msGather = 0, msFront = 0;
@@ -1144,6 +1196,77 @@ int nfcb200_decode_batch(nfcb200_handle *h, const void *samples, int samples_on_
 // multi-GPU frame gather without a host round trip: the frames of the last decode, ordered and packed, as they sit in
 // device memory (128-byte records + 128-byte payload extension chunks), and the conversion of such records to ABI frames
 // ---------------------------------------------------------------------------------------------------------------------
+/*
+ * Time shards of ONE long capture (BASELINE.json configs[4], dist.decode_long_capture): a shard that does not start at the
+ * capture's first sample continues its predecessor's decoder.  nfcb200_carry_before returns, after a single-stream decode,
+ * the carry in front of the first lane that begins at or after `sample` (and that lane's begin: an idle point of the
+ * capture); nfcb200_set_carry hands it to the next single-stream decode of this handle (one shot), with clock_shift
+ * subtracted from the absolute sample times inside (the next window counts from its own first sample).  The blob is
+ * opaque (a `Carry`, nfc_core.h): protocol state (FSD / FWT / SFGT, the Encrypted flag, lastCommand), carrier flags, the
+ * carrier edge time.  Running sums and front-end state are not part of it: they re-converge over the window's overlap.
+ */
+int nfcb200_carry_size(void)
+{
+   return (int) sizeof(Carry);
+}
+
+int nfcb200_default_carry(nfcb200_handle *h, void *blob, uint64_t cap)
+{
+   if (!h || !blob || cap < sizeof(Carry))
+      return fail(NFCB200_ERR_INVALID, "carry blob needs %zu bytes", sizeof(Carry));
+   if (!h->paramsRate)
+      return fail(NFCB200_ERR_INVALID, "no decode yet: the protocol defaults depend on the sample rate");
+   Carry c;
+   carry_speculate(c, h->P);
+   memcpy(blob, &c, sizeof(Carry));
+   return 0;
+}
+
+int nfcb200_set_carry(nfcb200_handle *h, const void *blob, uint64_t size, uint32_t clock_shift)
+{
+   if (!h)
+      return fail(NFCB200_ERR_INVALID, "null handle");
+   if (!blob || size == 0)
+   {
+      h->haveCarryIn = false;
+      return 0;
+   }
+   if (size != sizeof(Carry))
+      return fail(NFCB200_ERR_INVALID, "carry blob of %llu bytes, expected %zu", (unsigned long long) size, sizeof(Carry));
+   memcpy(&h->carryIn, blob, sizeof(Carry));
+   carry_canon(h->carryIn);
+   if (h->carryIn.edgeTime)
+      h->carryIn.edgeTime = h->carryIn.edgeTime > clock_shift ? h->carryIn.edgeTime - clock_shift : 1;
+   h->haveCarryIn = true;
+   return 0;
+}
+
+int nfcb200_carry_before(nfcb200_handle *h, uint64_t sample, void *blob, uint64_t cap, uint64_t *size, uint64_t *lane_begin)
+{
+   if (!h)
+      return fail(NFCB200_ERR_INVALID, "null handle");
+   if (size)
+      *size = sizeof(Carry);
+   if (!blob || cap < sizeof(Carry))
+      return fail(NFCB200_ERR_CAPACITY, "carry blob needs %zu bytes", sizeof(Carry));
+   if (h->lastStreams != 1)
+      return fail(NFCB200_ERR_INVALID, "the carry query needs a single-stream decode before it");
+   CUDA_TRY(cudaSetDevice(h->device));
+   cudaStream_t st = h->stream;
+   Carry *dOut = h->carryDev.as<Carry>() + 1;
+   u32 *dBegin = (u32 *) (h->carryDev.as<Carry>() + 2);
+   carry_before_kernel<<<1, 32, 0, st>>>(h->lanes.as<LaneRec>(), h->lastLanes, h->lastCarryInUsed ? h->carryDev.as<Carry>() : nullptr,
+                                          (u32) std::min<uint64_t>(sample, 0xFFFFFFFFull), dOut, dBegin, h->P);
+   CUDA_TRY(cudaGetLastError());
+   u32 b = 0;
+   CUDA_TRY(cudaMemcpyAsync(blob, dOut, sizeof(Carry), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaMemcpyAsync(&b, dBegin, sizeof(u32), cudaMemcpyDeviceToHost, st));
+   CUDA_TRY(cudaStreamSynchronize(st));
+   if (lane_begin)
+      *lane_begin = b == 0xFFFFFFFFu ? ~0ull : b;
+   return 0;
+}
+
 int nfcb200_device_frames(nfcb200_handle *h, const void **records, uint64_t *n_records, const void **ext, uint64_t *n_ext_chunks)
 {
    if (!h)
@@ -1171,7 +1294,7 @@ int nfcb200_emit_records(nfcb200_handle *h, const void *records, uint64_t n_reco
    if (n_records && (!records || !out))
       return fail(NFCB200_ERR_INVALID, "null buffer");
    const FrameRec *recs = (const FrameRec *) records;
-   const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(16, n_records / 4096));
+   const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(host_workers(), n_records / 4096));
    auto work = [&](uint64_t lo, uint64_t hi) {
       for (uint64_t i = lo; i < hi; i++)
          emit_frame(h, recs[i], (const unsigned char *) ext, (size_t) n_ext_chunks * 128, recs[i].lane + stream_offset, sample_rate, out[i]);
@@ -1229,7 +1352,7 @@ int nfcb200_pack_frames(const nfcb200_frame *frames, uint64_t n, uint32_t stream
          memcpy(pay + offs[i], frames[i].data, offs[i + 1] - offs[i]);
       }
    };
-   const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(16, n / 8192));
+   const unsigned workers = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(host_workers(), n / 8192));
    if (workers <= 1)
       work(0, n);
    else

@@ -345,3 +345,127 @@ def decode_long_capture(decode, samples, n_shards, overlap=1 << 20, rank=None):
             continue
         out += stitch_shard(decode(samples[wb:we]), b, e, wb, r == 0)
     return out
+
+
+def _same_protocol_state(a, b):
+    """two carry blobs agree on everything but the carrier edge time (the last word of the blob)"""
+    return a[:-4] == b[:-4]
+
+
+def decode_long_capture_carry(dec, window, n_samples, n_shards, sigtype, sample_rate, overlap=1 << 18, left=8192, lead=4096, rank=None, group=None,
+                              device=None, stats=None):
+    """Time-sharded decode of ONE capture WITH the inter-shard carry exchange (SURVEY.md 8e "exchange step").
+
+    The predecessor of a shard hands over the decoder's CARRY -- protocol state (FSD / FWT / SFGT from RATS / ATS / ATTRIB,
+    the Encrypted flag, lastCommand), carrier flags, carrier edge time: NfcDecoder.carry_before -- in front of the first
+    lane L that begins at or after the successor's window start (`left` samples before its own range): an idle point of
+    the capture.  Frames that start before L
+    belong to the predecessor, from L on to the successor.  A successor whose cold start would assume another protocol
+    state decodes from `lead` samples before L with the carry injected (NfcDecoder.set_carry) instead of from its
+    overlap window.  Exact for protocol state however old; the overlap stitch alone (decode_long_capture) loses state set
+    further back than the overlap.
+
+    dec: nfc_laboratory_b200.NfcDecoder; window(b, e) -> samples [b, e) of the capture in `sigtype` layout (numpy array or
+    CUDA tensor).  rank=None: all shards in this process in time order (every shard is decoded once).  rank=r: shard r of
+    a torch.distributed group -- all ranks first decode their overlap windows in parallel (cold), then the carries travel
+    rank to rank as byte tensors and only the shards whose assumption was wrong decode again.  Returns this process's
+    frames (absolute sample indices; all frames when rank is None).  stats["redecoded"]: shards decoded from an injected
+    carry."""
+    import numpy as np
+
+    # a window reaches `overlap` samples past the shard (the frames it owns may end there: longest exchange + waiting time)
+    # but only `left` samples before it: what a cold start cannot re-derive over those arrives with the carry
+    shards = [(b, e, max(0, b - left) // BLOCK * BLOCK, we) for (b, e, wb, we) in time_shards(n_samples, n_shards, overlap)]
+    live = [r for r in range(n_shards) if shards[r][1] > shards[r][0]]
+    NONE = 0xFFFFFFFFFFFFFFFF
+    redecoded = 0
+
+    def decode_window(b, e, carry=None, shift=0):
+        dec.set_carry(carry, shift)
+        fr = dec.decode_batch(window(b, e), sigtype, sample_rate, cap=1 << 18)
+        return [(f.tech_type, f.frame_type, f.frame_flags, f.frame_phase, f.frame_rate, f.sample_start, f.sample_end, f.data) for f in fr]
+
+    def own(frames, base, lo, hi, first):
+        return [f[:5] + (f[5] + base, f[6] + base) + tuple(f[7:]) for f in frames if (first or f[5] + base >= lo) and f[5] + base < hi]
+
+    def plan(r, blob, L):
+        """(window begin, carry or None, first owned sample) of shard r given its predecessor's answer"""
+        b, e, wb, we = shards[r]
+        if L == NONE or L >= e:
+            return wb, None, b            # no idle point inside the shard: the overlap stitch stands
+        if _same_protocol_state(blob, dec.default_carry()):
+            return wb, None, L            # a cold start assumes exactly this state
+        return max(0, (L - lead) // BLOCK * BLOCK), blob, L
+
+    if rank is None:
+        out = []
+        pending = None  # (frames, base, lo, first) of the previous live shard
+        prev_base = 0
+        for i, r in enumerate(live):
+            b, e, wb, we = shards[r]
+            if i == 0:
+                base, carry, lo = wb, None, 0
+            else:
+                blob, lane = dec.carry_before(max(0, wb - prev_base))  # the decoder still holds the predecessor's decode
+                base, carry, lo = plan(r, blob, NONE if lane is None else prev_base + lane)
+            if pending is not None:
+                out += own(pending[0], pending[1], pending[2], lo, pending[3])
+            if carry is not None:
+                redecoded += 1
+            frames = decode_window(base, we, carry, base - prev_base)
+            pending = (frames, base, lo, i == 0)
+            prev_base = base
+        if pending is not None:
+            out += own(pending[0], pending[1], pending[2], n_samples, pending[3])
+        if stats is not None:
+            stats["redecoded"] = redecoded
+        return out
+
+    import torch
+    import torch.distributed as dist
+
+    csize = dec.carry_size()
+    b, e, wb, we = shards[rank]
+    mine = rank in live
+    base = wb
+    frames = decode_window(wb, we) if mine else []      # pass 1: every rank, in parallel, cold
+    lower = {r: shards[r][0] for r in live}
+    if live:
+        lower[live[0]] = 0
+
+    for i in range(1, len(live)):
+        src, dst = live[i - 1], live[i]
+        payload = None
+        if rank == src:
+            blob, lane = dec.carry_before(max(0, shards[dst][2] - base))
+            L = NONE if lane is None else base + lane
+            payload = blob + np.array([L, base], dtype="<u8").tobytes()
+            t = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(device)
+            dist.send(t, dst, group=group)
+        elif rank == dst:
+            t = torch.empty(csize + 16, dtype=torch.uint8, device=device)
+            dist.recv(t, src, group=group)
+            payload = t.cpu().numpy().tobytes()
+        if payload is not None:
+            blob, tail = payload[:csize], np.frombuffer(payload[csize:csize + 16], dtype="<u8")
+            L, pred_base = int(tail[0]), int(tail[1])
+            nb, carry, lo = plan(dst, blob, L)
+            lower[dst] = lo
+            if rank == dst and carry is not None:
+                frames = decode_window(nb, shards[dst][3], carry, nb - pred_base)
+                base = nb
+                redecoded += 1
+
+    if stats is not None:
+        stats["redecoded"] = redecoded
+    if not mine:
+        return []
+    # the bound towards the successor is known to both sides of that boundary only: fetch it from the successor
+    idx = live.index(rank)
+    hi = n_samples
+    bounds = torch.tensor([lower.get(rank, 0)], dtype=torch.int64, device=device)
+    allb = [torch.zeros_like(bounds) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(allb, bounds, group=group)
+    if idx + 1 < len(live):
+        hi = int(allb[live[idx + 1]].item())
+    return own(frames, base, lower[rank], hi, idx == 0)

@@ -124,3 +124,22 @@ def test_time_sharded_capture_on_the_device(decoder, name):
 
     for shards in (2, 4):
         assert ND.decode_long_capture(decode, mag, shards, OVERLAP) == full, (name, shards)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_carry_exchange_makes_a_short_overlap_exact(name):
+    """time shards with only 8 192 samples of left overlap: the plain overlap stitch loses frames on most captures (a cut
+    between a poll frame and its answer, protocol state set before the overlap); with the decoder's carry handed from shard
+    to shard at an idle point (dist.decode_long_capture_carry, NfcDecoder.carry_before / set_carry) the stitched decode
+    equals the uncut one"""
+    import nfc_laboratory_b200 as N
+    from nfc_laboratory_b200 import dist as ND
+    mag, rate, _ = U.fixture_wav(name)
+    d = N.NfcDecoder()
+    full = [f.key() for f in d.decode_batch(mag[None], N.SIG_MAG_F32, rate)]
+    for shards in (2, 3, 4):
+        st = {}
+        got = ND.decode_long_capture_carry(d, lambda b, e: mag[None, b:e], mag.size, shards, N.SIG_MAG_F32, rate, overlap=1 << 18, left=8192, stats=st)
+        assert got == full, (name, shards, st)
+    d.close()
