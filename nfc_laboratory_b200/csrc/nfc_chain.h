@@ -81,16 +81,18 @@ NFC_HD u32 lane_first_sample(const u8 *flags, u32 nb, u32 bb, bool allowShort = 
    return begin - NFCB200_HALO_SHORT;
 }
 
-// dilate the raw trigger flags into active blocks, in place: bit SCR_ACTIVE
-NFC_HD void blocks_activate(u8 *flags, u32 nb)
+// dilate the raw trigger flags into active blocks, in place: bit SCR_ACTIVE.  streamStart: the buffer begins at the stream's
+// first sample.  false for a window that continues a capture from an injected carry: its first START_BLOCKS blocks are
+// warm-up (the screen's own start-up transient triggers there; what they hold belongs to the predecessor's window)
+NFC_HD void blocks_activate(u8 *flags, u32 nb, bool streamStart = true)
 {
    // forward reach (POST) and backward reach (PRE) of every trigger
    int reach = 0;
    for (u32 b = 0; b < nb; b++)
    {
-      if (flags[b] & SCR_TRIGGER)
+      if ((flags[b] & SCR_TRIGGER) && (streamStart || b >= NFCB200_START_BLOCKS))
          reach = NFCB200_POST_BLOCKS + 1;
-      if (reach > 0 || b < NFCB200_START_BLOCKS)
+      if (reach > 0 || (streamStart && b < NFCB200_START_BLOCKS))
          flags[b] |= SCR_ACTIVE;
       if (reach > 0)
          reach--;
@@ -98,7 +100,7 @@ NFC_HD void blocks_activate(u8 *flags, u32 nb)
    reach = 0;
    for (u32 b = nb; b-- > 0;)
    {
-      if (flags[b] & SCR_TRIGGER)
+      if ((flags[b] & SCR_TRIGGER) && (streamStart || b >= NFCB200_START_BLOCKS))
          reach = NFCB200_PRE_BLOCKS + 1;
       if (reach > 0)
          flags[b] |= SCR_ACTIVE;

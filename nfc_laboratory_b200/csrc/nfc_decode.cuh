@@ -237,8 +237,14 @@ __global__ void segment_activate_kernel(SegmentConfig c)
    const uint32_t b = (uint32_t) (i % c.n_blocks);
    const uint8_t *flags = c.flags + (i - b);
 
-   bool act = b < NFCB200_START_BLOCKS;
-   const uint32_t lo = b > NFCB200_POST_BLOCKS ? b - NFCB200_POST_BLOCKS : 0;
+   // the stream start is always a segment -- unless stream 0 continues a capture from an injected carry
+   // the stream start is always a segment -- unless stream 0 continues a capture from an injected carry: then its first
+   // blocks are warm-up and their triggers (the screen's start-up transient) do not count (blocks_activate, nfc_chain.h)
+   const bool cont = c.carryIn && i < c.n_blocks;
+   bool act = b < NFCB200_START_BLOCKS && !cont;
+   uint32_t lo = b > NFCB200_POST_BLOCKS ? b - NFCB200_POST_BLOCKS : 0;
+   if (cont && lo < NFCB200_START_BLOCKS)
+      lo = NFCB200_START_BLOCKS;
    const uint32_t hi = b + NFCB200_PRE_BLOCKS < c.n_blocks ? b + NFCB200_PRE_BLOCKS : c.n_blocks - 1;
    for (uint32_t k = lo; k <= hi && !act; k++)
       act = (flags[k] & SCR_TRIGGER) != 0;
@@ -342,7 +348,9 @@ __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Par
                close_seg(segIdx - 1, e);
             }
 
-            const uint32_t segFirst = lane_first_sample(flags, c.n_blocks, base + p, c.shortHalo != 0);
+            uint32_t segFirst = lane_first_sample(flags, c.n_blocks, base + p, c.shortHalo != 0);
+            if (segFirst == 0 && c.carryIn && s == 0)
+               segFirst = 1; // a continued capture has no stream start: also its first lane is a cold-started one
             {
                SegRec &S = c.segs[segOff + segIdx];
                S.stream = s;

@@ -662,6 +662,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    sg.segTotal = &dC->segTotal;
    sg.activeTotal = &dC->activeBlocks;
    sg.group = 1;
+   sg.carryIn = dCarryIn;
 
    const u32 sgrid = (n_streams + 63) / 64;
    {

@@ -347,125 +347,250 @@ def decode_long_capture(decode, samples, n_shards, overlap=1 << 20, rank=None):
     return out
 
 
-def _same_protocol_state(a, b):
-    """two carry blobs agree on everything but the carrier edge time (the last word of the blob)"""
-    return a[:-4] == b[:-4]
+NO_LANE = 0xFFFFFFFFFFFFFFFF
+GAP = 32 * BLOCK  # an idle point (a lane's begin) has this many samples without activity in front of it (NFCB200_GAP_BLOCKS)
 
 
-def decode_long_capture_carry(dec, window, n_samples, n_shards, sigtype, sample_rate, overlap=1 << 18, left=8192, lead=4096, rank=None, group=None,
-                              device=None, stats=None):
+def _same_carry(a, base_a, b, base_b):
+    """two carry blobs, each with the window base its clock counts from, describe the same decoder state"""
+    if a[:-4] != b[:-4]:
+        return False
+    ea, eb = int.from_bytes(a[-4:], "little"), int.from_bytes(b[-4:], "little")  # carrier edge time, 0 = unset
+    return (ea == 0 and eb == 0) or (ea != 0 and eb != 0 and ea + base_a == eb + base_b)
+
+
+class _CarryShard:
+    """One time shard of a capture on one decoder: cold decode, the carry received from the predecessor, the re-run of
+    the decoder from the received carry up to the point where it agrees with the cold decode again, the answer for the
+    successor.  A message is (blob, clock_base, L, covered): the carry in front of the idle point L (absolute sample, None
+    when the sender has no idle point at or after the receiver's window start) with the base its clock counts from;
+    covered: the sender's decode reaches the end of the capture, so without an idle point it owns the rest."""
+
+    def __init__(self, dec, window, n_samples, shards, r, sigtype, sample_rate, lead, step, overlap):
+        self.dec, self.window, self.n, self.shards, self.r, self.overlap = dec, window, n_samples, shards, r, overlap
+        self.sigtype, self.rate, self.lead, self.step = sigtype, sample_rate, lead, step
+        self.b, self.e, self.wb, self.we = shards[r]
+        nxt = [q for q in range(r + 1, len(shards)) if shards[q][1] > shards[q][0]]
+        self.next_wb = shards[nxt[0]][2] if nxt else None
+        self.lo = 0
+        self.kept = []         # [(frames with absolute times, from, to)]: what this shard keeps of each decode
+        self.live_base = None  # window base of the decode the decoder handle holds
+        self.live_end = 0
+        self.next_answer = None
+        self.relay = None
+        self.decodes = 0       # decodes after the cold one
+        self.samples = 0       # samples decoded after the cold one
+
+    def _decode(self, b, e, carry=None, clock_base=0):
+        self.dec.set_carry(carry, max(0, b - clock_base))
+        fr = self.dec.decode_batch(self.window(b, e), self.sigtype, self.rate, cap=1 << 18)
+        self.live_base, self.live_end = b, e
+        return [(f.tech_type, f.frame_type, f.frame_flags, f.frame_phase, f.frame_rate, f.sample_start + b, f.sample_end + b, f.data) for f in fr]
+
+    def _query(self, sample):
+        """(blob, clock base, idle point or None) of the decode in the handle: first lane that begins at or after `sample`"""
+        blob, lane = self.dec.carry_before(max(0, sample - self.live_base))
+        return blob, self.live_base, (None if lane is None else self.live_base + lane)
+
+    def cold(self):
+        self.cold_frames = self._decode(self.wb, self.we)
+        self.kept = [(self.cold_frames, 0 if self.r == 0 else self.b, self.n)]
+
+    def receive(self, msg):
+        blob, cbase, L, covered = msg
+        if L is None:
+            if covered:
+                self.lo, self.kept, self.relay = self.n, [], msg  # the predecessor's decode owns the rest of the capture
+            else:
+                # no idle point within the predecessor's reach: the plain overlap stitch, with its full overlap to the left
+                self.lo = self.b
+                nb = max(0, self.b - self.overlap) // BLOCK * BLOCK
+                if nb < self.wb:
+                    self.cold_frames = self._decode(nb, self.we)
+                    self.decodes += 1
+                    self.samples += self.we - nb
+                self.kept = [(self.cold_frames, self.b, self.n)]
+            return
+        self.lo = L
+        self.kept = [(self.cold_frames, L, self.n)]
+        mine = self._query(L)
+        # the successor's idle point must not lie before this shard's own: what precedes L is the predecessor's
+        ask = max(self.next_wb, L) if self.next_wb is not None else None
+        nq = self._query(ask) if ask is not None else None
+        if mine[2] == L and _same_carry(mine[0], mine[1], blob, cbase):
+            return  # the cold start assumed the right state
+        # idle points of the cold decode further on: where the re-run may meet it again
+        cands, s = [], self.step
+        while L + s < self.we - GAP:
+            c = self._query(L + s)
+            if c[2] is None:
+                break
+            if c[2] > L and (not cands or c[2] > cands[-1][2]):
+                cands.append(c)
+            s = max(s * 4, c[2] - L + BLOCK)
+        if nq is not None and nq[2] is not None and nq[2] > L and all(c[2] != nq[2] for c in cands):
+            cands = sorted(cands + [nq], key=lambda c: c[2])
+        pending_next = nq is not None
+        start, carry = L, (blob, cbase)
+        self.kept = []
+        for c in cands + [None]:
+            end = self.we if c is None else min(self.we, c[2] + GAP)
+            nb = max(carry[1], (start - self.lead) // BLOCK * BLOCK, 0)
+            frames = self._decode(nb, end, carry[0], carry[1])
+            self.decodes += 1
+            self.samples += end - nb
+            if c is None:
+                self.kept.append((frames, start, self.n))
+                if pending_next:
+                    self.next_answer = None  # answered from the handle: it holds the decode up to the window's end
+                return
+            here = self._query(c[2])
+            if pending_next and ask >= start:
+                a = self._query(ask)
+                if a[2] is not None and a[2] <= c[2]:
+                    self.next_answer, pending_next = a + (False,), False
+            if here[2] != c[2]:
+                continue  # the lanes of the re-run are cut differently here: try the next idle point with a longer window
+            self.kept.append((frames, start, c[2]))
+            if _same_carry(here[0], here[1], c[0], c[1]) and (not pending_next or nq[2] is None or nq[2] >= c[2]):
+                self.kept.append((self.cold_frames, c[2], self.n))  # from here on the cold decode was right
+                if pending_next:
+                    self.next_answer = nq + (nq[2] is None and self.we >= self.n,)
+                return
+            start, carry = c[2], (here[0], here[1])
+
+    def answer(self):
+        """the message for the successor"""
+        if self.relay is not None:
+            return self.relay
+        if self.next_answer is not None:
+            return self.next_answer
+        blob, base, L = self._query(max(self.next_wb, self.lo))
+        return blob, base, L, (L is None and self.live_end >= self.n)
+
+    def owned(self, hi):
+        out = []
+        for frames, lo, to in self.kept:
+            lo, to = max(lo, self.lo), min(to, hi)
+            out += [f for f in frames if lo <= f[5] < to]
+        return out
+
+
+def decode_long_capture_carry(dec, window, n_samples, n_shards, sigtype, sample_rate, overlap=1 << 18, left=8192, lead=6144, rank=None, group=None,
+                              device=None, stats=None, model_ranks=False, step=1 << 20):
     """Time-sharded decode of ONE capture WITH the inter-shard carry exchange (SURVEY.md 8e "exchange step").
 
     The predecessor of a shard hands over the decoder's CARRY -- protocol state (FSD / FWT / SFGT from RATS / ATS / ATTRIB,
     the Encrypted flag, lastCommand), carrier flags, carrier edge time: NfcDecoder.carry_before -- in front of the first
     lane L that begins at or after the successor's window start (`left` samples before its own range): an idle point of
-    the capture.  Frames that start before L
-    belong to the predecessor, from L on to the successor.  A successor whose cold start would assume another protocol
-    state decodes from `lead` samples before L with the carry injected (NfcDecoder.set_carry) instead of from its
-    overlap window.  Exact for protocol state however old; the overlap stitch alone (decode_long_capture) loses state set
-    further back than the overlap.
+    the capture.  Frames that start before L belong to the predecessor, from L on to the successor.
+
+    rank=None: all shards in this process in time order, every shard decoded ONCE from `lead` samples before its idle
+    point with the carry injected (NfcDecoder.set_carry).
+    rank=r: shard r of a torch.distributed group.  All ranks first decode their windows in parallel, cold.  Then the
+    carries travel rank to rank (NCCL / gloo send-recv of a byte tensor).  A successor whose cold decode holds another state
+    at L re-runs the decoder from L with the received carry -- in pieces that end at the idle points of its cold decode,
+    and only until the state of the re-run equals the cold decode's again (then the rest of the cold decode was right).
+    model_ranks=True runs that rank protocol for all shards in this process (one decoder, shard after shard).
 
     dec: nfc_laboratory_b200.NfcDecoder; window(b, e) -> samples [b, e) of the capture in `sigtype` layout (numpy array or
-    CUDA tensor).  rank=None: all shards in this process in time order (every shard is decoded once).  rank=r: shard r of
-    a torch.distributed group -- all ranks first decode their overlap windows in parallel (cold), then the carries travel
-    rank to rank as byte tensors and only the shards whose assumption was wrong decode again.  Returns this process's
-    frames (absolute sample indices; all frames when rank is None).  stats["redecoded"]: shards decoded from an injected
-    carry."""
-    import numpy as np
-
-    # a window reaches `overlap` samples past the shard (the frames it owns may end there: longest exchange + waiting time)
-    # but only `left` samples before it: what a cold start cannot re-derive over those arrives with the carry
+    CUDA tensor).  Returns this process's frames (absolute sample indices; all frames when rank is None).
+    stats: "redecoded" (shards that ran from a received carry), "redecoded_samples".
+    Not covered: a stretch of activity without any idle point (8 192 quiet samples) longer than the overlap -- there the
+    plain overlap stitch of decode_long_capture is used (cold start `overlap` samples before the shard); a carrier edge older than the window stamps a later carrier frame with the window's start."""
     shards = [(b, e, max(0, b - left) // BLOCK * BLOCK, we) for (b, e, wb, we) in time_shards(n_samples, n_shards, overlap)]
     live = [r for r in range(n_shards) if shards[r][1] > shards[r][0]]
-    NONE = 0xFFFFFFFFFFFFFFFF
-    redecoded = 0
 
-    def decode_window(b, e, carry=None, shift=0):
-        dec.set_carry(carry, shift)
-        fr = dec.decode_batch(window(b, e), sigtype, sample_rate, cap=1 << 18)
-        return [(f.tech_type, f.frame_type, f.frame_flags, f.frame_phase, f.frame_rate, f.sample_start, f.sample_end, f.data) for f in fr]
+    def tup(f, base):
+        return (f.tech_type, f.frame_type, f.frame_flags, f.frame_phase, f.frame_rate, f.sample_start + base, f.sample_end + base, f.data)
 
-    def own(frames, base, lo, hi, first):
-        return [f[:5] + (f[5] + base, f[6] + base) + tuple(f[7:]) for f in frames if (first or f[5] + base >= lo) and f[5] + base < hi]
-
-    def plan(r, blob, L):
-        """(window begin, carry or None, first owned sample) of shard r given its predecessor's answer"""
-        b, e, wb, we = shards[r]
-        if L == NONE or L >= e:
-            return wb, None, b            # no idle point inside the shard: the overlap stitch stands
-        if _same_protocol_state(blob, dec.default_carry()):
-            return wb, None, L            # a cold start assumes exactly this state
-        return max(0, (L - lead) // BLOCK * BLOCK), blob, L
-
-    if rank is None:
-        out = []
-        pending = None  # (frames, base, lo, first) of the previous live shard
-        prev_base = 0
+    if rank is None and not model_ranks:
+        out, redecoded, resamples = [], 0, 0
+        pending = None  # (frames, first owned sample) of the decode in the handle
+        cur_base = cur_end = 0
         for i, r in enumerate(live):
             b, e, wb, we = shards[r]
             if i == 0:
                 base, carry, lo = wb, None, 0
             else:
-                blob, lane = dec.carry_before(max(0, wb - prev_base))  # the decoder still holds the predecessor's decode
-                base, carry, lo = plan(r, blob, NONE if lane is None else prev_base + lane)
+                blob, lane = dec.carry_before(max(0, max(wb, pending[1]) - cur_base))  # never before this decode's own idle point
+                if lane is None:
+                    if cur_end >= n_samples:
+                        break                      # the decode in hand reaches the capture's end: it owns the rest
+                    base, carry, lo = max(0, b - overlap) // BLOCK * BLOCK, None, b  # no idle point in reach: the plain overlap stitch
+                else:
+                    lo = cur_base + lane
+                    base, carry = max(cur_base, (lo - lead) // BLOCK * BLOCK), blob
+                    redecoded += 1
+                    resamples += we - base
             if pending is not None:
-                out += own(pending[0], pending[1], pending[2], lo, pending[3])
-            if carry is not None:
-                redecoded += 1
-            frames = decode_window(base, we, carry, base - prev_base)
-            pending = (frames, base, lo, i == 0)
-            prev_base = base
+                out += [f for f in pending[0] if pending[1] <= f[5] < lo]
+            dec.set_carry(carry, base - cur_base)
+            frames = [tup(f, base) for f in dec.decode_batch(window(base, we), sigtype, sample_rate, cap=1 << 18)]
+            pending = (frames, lo)
+            cur_base, cur_end = base, we
         if pending is not None:
-            out += own(pending[0], pending[1], pending[2], n_samples, pending[3])
+            out += [f for f in pending[0] if pending[1] <= f[5]]
         if stats is not None:
-            stats["redecoded"] = redecoded
+            stats["redecoded"], stats["redecoded_samples"] = redecoded, resamples
         return out
 
+    def worker(r):
+        return _CarryShard(dec, window, n_samples, shards, r, sigtype, sample_rate, lead, step, overlap)
+
+    if rank is None:
+        # the rank protocol, shard after shard on one decoder
+        ws, msg = [], None
+        for i, r in enumerate(live):
+            w = worker(r)
+            w.cold()
+            if i > 0:
+                w.receive(msg)
+            if i + 1 < len(live):
+                msg = w.answer()
+            ws.append(w)
+        out = []
+        for i, w in enumerate(ws):
+            out += w.owned(ws[i + 1].lo if i + 1 < len(ws) else n_samples)
+        if stats is not None:
+            stats["redecoded"] = sum(1 for w in ws if w.decodes)
+            stats["redecoded_samples"] = sum(w.samples for w in ws)
+        return out
+
+    import numpy as np
     import torch
     import torch.distributed as dist
 
     csize = dec.carry_size()
-    b, e, wb, we = shards[rank]
     mine = rank in live
-    base = wb
-    frames = decode_window(wb, we) if mine else []      # pass 1: every rank, in parallel, cold
-    lower = {r: shards[r][0] for r in live}
-    if live:
-        lower[live[0]] = 0
-
+    w = worker(rank) if mine else None
+    if mine:
+        w.cold()                                        # pass 1: every rank, in parallel
+    lo = 0 if (not mine or rank == live[0]) else None
     for i in range(1, len(live)):
         src, dst = live[i - 1], live[i]
-        payload = None
         if rank == src:
-            blob, lane = dec.carry_before(max(0, shards[dst][2] - base))
-            L = NONE if lane is None else base + lane
-            payload = blob + np.array([L, base], dtype="<u8").tobytes()
-            t = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(device)
+            blob, cbase, L, covered = w.answer()
+            tail = np.array([NO_LANE if L is None else L, cbase, 1 if covered else 0], dtype="<u8").tobytes()
+            t = torch.frombuffer(bytearray(blob + tail), dtype=torch.uint8).to(device)
             dist.send(t, dst, group=group)
         elif rank == dst:
-            t = torch.empty(csize + 16, dtype=torch.uint8, device=device)
+            t = torch.empty(csize + 24, dtype=torch.uint8, device=device)
             dist.recv(t, src, group=group)
             payload = t.cpu().numpy().tobytes()
-        if payload is not None:
-            blob, tail = payload[:csize], np.frombuffer(payload[csize:csize + 16], dtype="<u8")
-            L, pred_base = int(tail[0]), int(tail[1])
-            nb, carry, lo = plan(dst, blob, L)
-            lower[dst] = lo
-            if rank == dst and carry is not None:
-                frames = decode_window(nb, shards[dst][3], carry, nb - pred_base)
-                base = nb
-                redecoded += 1
-
+            tail = np.frombuffer(payload[csize:csize + 24], dtype="<u8")
+            L = int(tail[0])
+            w.receive((payload[:csize], int(tail[1]), None if L == NO_LANE else L, bool(tail[2])))
+            lo = w.lo
     if stats is not None:
-        stats["redecoded"] = redecoded
-    if not mine:
-        return []
-    # the bound towards the successor is known to both sides of that boundary only: fetch it from the successor
-    idx = live.index(rank)
-    hi = n_samples
-    bounds = torch.tensor([lower.get(rank, 0)], dtype=torch.int64, device=device)
+        stats["redecoded"] = 1 if (mine and w.decodes) else 0
+        stats["redecoded_samples"] = w.samples if mine else 0
+    # the bound towards the successor is known to the successor: fetch it
+    bounds = torch.tensor([lo if mine else n_samples], dtype=torch.int64, device=device)
     allb = [torch.zeros_like(bounds) for _ in range(dist.get_world_size(group))]
     dist.all_gather(allb, bounds, group=group)
-    if idx + 1 < len(live):
-        hi = int(allb[live[idx + 1]].item())
-    return own(frames, base, lower[rank], hi, idx == 0)
+    if not mine:
+        return []
+    idx = live.index(rank)
+    hi = int(allb[live[idx + 1]].item()) if idx + 1 < len(live) else n_samples
+    return w.owned(hi)

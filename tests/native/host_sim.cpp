@@ -106,8 +106,7 @@ void hostsim_default_carry(uint32_t sampleRate, void *out)
    Params P;
    hostsim_params(sampleRate, 0xF, &P);
    Carry c;
-   carry_init(c, P);
-   c.carrierOn = 1;
+   carry_speculate(c, P);
    std::memcpy(out, &c, sizeof(Carry));
 }
 
@@ -231,14 +230,14 @@ uint32_t hostsim_first_sample(const uint8_t *flags, uint32_t nb, uint32_t bb)
  * one lane per segment, carry chain to the fixed point.  stats: [0] lanes [1] live lanes [2] rounds [3] lane runs
  * [4] samples stepped [5] active blocks
  */
-long hostsim_pipeline(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t enabled, uint8_t *flags, uint32_t nb, sim_frame *out, long cap,
-                      uint64_t *stats, uint32_t group)
+static long pipeline_impl(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t enabled, uint8_t *flags, uint32_t nb, sim_frame *out, long cap,
+                          uint64_t *stats, uint32_t group, const Carry *init, uint32_t query, Carry *qOut, uint32_t *qBegin)
 {
    Params P;
    if (!hostsim_params(sampleRate, enabled, &P))
       return -1;
 
-   blocks_activate(flags, nb);
+   blocks_activate(flags, nb, init == nullptr);
 
    if (group < 1)
       group = 1;
@@ -249,7 +248,15 @@ long hostsim_pipeline(const float *mag, uint64_t n, uint32_t sampleRate, uint32_
 
    for (uint32_t j = 0; j < nseg; j++)
    {
-      if (lanes[j].first == 0)
+      // as segment_fill_kernel (nfc_decode.cuh): an injected carry stands in front of the first lane and is what the later
+      // lanes speculate on
+      if (init)
+      {
+         lanes[j].in = *init;
+         if (lanes[j].first == 0)
+            lanes[j].first = 1;
+      }
+      else if (lanes[j].first == 0)
       {
          carry_init(lanes[j].in, P);
          carry_canon(lanes[j].in);
@@ -311,8 +318,16 @@ long hostsim_pipeline(const float *mag, uint64_t n, uint32_t sampleRate, uint32_
 
       rounds++;
 
-      chain_walk(lanes.data(), nseg, P);
+      chain_walk(lanes.data(), nseg, P, init);
    }
+
+   if (qOut)
+      carry_before(lanes.data(), nseg, P, init, query, *qOut, *qBegin);
+
+   if (getenv("HOSTSIM_LANES"))
+      for (uint32_t j = 0; j < nseg; j++)
+         fprintf(stderr, "lane %u first %u begin %u end %u stop %u dead %u gen %u frames %u\n", j, lanes[j].first, lanes[j].begin, lanes[j].end, lanes[j].stop,
+                 lanes[j].dead, lanes[j].gen, lanes[j].nframes);
 
    long count = 0;
    uint64_t live = 0;
@@ -346,6 +361,36 @@ long hostsim_pipeline(const float *mag, uint64_t n, uint32_t sampleRate, uint32_
    }
 
    return count;
+}
+
+
+long hostsim_pipeline(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t enabled, uint8_t *flags, uint32_t nb, sim_frame *out, long cap,
+                      uint64_t *stats, uint32_t group)
+{
+   return pipeline_impl(mag, n, sampleRate, enabled, flags, nb, out, cap, stats, group, nullptr, 0, nullptr, nullptr);
+}
+
+/*
+ * One window of a time-sharded capture (nfcb200_set_carry / nfcb200_carry_before on the host): carry_in (or null) stands in
+ * front of the window's first lane; carry_out / lane_begin answer the carry query at `query` (lane_begin 0xFFFFFFFF: no lane
+ * begins at or after it)
+ */
+long hostsim_window(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t enabled, uint8_t *flags, uint32_t nb, sim_frame *out, long cap,
+                    const void *carry_in, uint32_t query, void *carry_out, uint32_t *lane_begin)
+{
+   Carry in, q;
+   if (carry_in)
+   {
+      memcpy(&in, carry_in, sizeof(Carry));
+      carry_canon(in);
+   }
+   uint32_t b = 0xFFFFFFFFu;
+   long r = pipeline_impl(mag, n, sampleRate, enabled, flags, nb, out, cap, nullptr, 1, carry_in ? &in : nullptr, query, &q, &b);
+   if (carry_out)
+      memcpy(carry_out, &q, sizeof(Carry));
+   if (lane_begin)
+      *lane_begin = b;
+   return r;
 }
 
 

@@ -217,6 +217,10 @@ def sim_lib():
         lib.hostsim_pipeline2.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(SimFrame), C.c_long,
                                           C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32]
         lib.hostsim_set_noff.argtypes = [C.c_int]
+        lib.hostsim_window.restype = C.c_long
+        lib.hostsim_window.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(SimFrame), C.c_long,
+                                       C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
+        lib.hostsim_default_carry.argtypes = [C.c_uint32, C.c_void_p]
         _sim = lib
     return _sim
 
@@ -271,3 +275,64 @@ def sim_pipeline2(mag, trigger_blocks, rate=10000000, enabled=0xF, cap=65536, gr
 
 def describe(fr):
     return "tech=%x type=%x flags=%02x phase=%x rate=%d [%d..%d] %s" % (fr[0], fr[1], fr[2], fr[3], fr[4], fr[5], fr[6], fr[7].hex(":"))
+
+
+class HostWindowDecoder:
+    """the carry interface of nfc_laboratory_b200.NfcDecoder (set_carry / carry_before / default_carry / carry_size) on the host
+    build of the lane pipeline: the per-shard decoder of dist.decode_long_capture_carry in the CPU tests"""
+
+    def __init__(self, rate):
+        import screen_ref as S
+        self._S = S
+        self.rate = rate
+        self._carry = None
+        self._last = None  # (mag, flags, carry) of the last window
+        self.windows = []  # (n_samples, carry injected?) per decode
+
+    def carry_size(self):
+        return sim_lib().hostsim_carry_size()
+
+    def default_carry(self):
+        buf = C.create_string_buffer(self.carry_size())
+        sim_lib().hostsim_default_carry(self.rate, buf)
+        return buf.raw
+
+    def set_carry(self, blob, clock_shift=0):
+        if blob is None:
+            self._carry = None
+            return
+        b = bytearray(blob)
+        assert len(b) == self.carry_size()
+        edge = int.from_bytes(b[-4:], "little")
+        if edge:
+            edge = edge - clock_shift if edge > clock_shift else 1
+        b[-4:] = edge.to_bytes(4, "little")
+        self._carry = bytes(b)
+
+    def _run(self, query):
+        mag, flags, carry = self._last
+        lib = sim_lib()
+        cap = 65536
+        buf = (SimFrame * cap)()
+        cout = C.create_string_buffer(self.carry_size())
+        begin = C.c_uint32(0)
+        fl = flags.copy()
+        n = lib.hostsim_window(mag.ctypes.data, mag.size, self.rate, 0xF, fl.ctypes.data, fl.size, buf, cap, carry, min(query, 0xFFFFFFFF), cout,
+                               C.byref(begin))
+        assert 0 <= n <= cap
+        return buf[:n], cout.raw, begin.value
+
+    def decode_batch(self, samples, sigtype=None, sample_rate=None, cap=None):
+        from collections import namedtuple
+        F = namedtuple("F", "tech_type frame_type frame_flags frame_phase frame_rate sample_start sample_end data")
+        mag = np.ascontiguousarray(np.asarray(samples).reshape(-1), dtype=np.float32)
+        flags = np.ascontiguousarray(self._S.block_flags(mag, self._S.ScreenParams(self.rate)), dtype=np.uint8)
+        self._last = (mag, flags, self._carry)
+        self.windows.append((mag.size, self._carry is not None))
+        self._carry = None  # one shot
+        frames, _, _ = self._run(0)
+        return [F(f.tech, f.type, f.flags, f.phase, f.rate, f.start, f.end, bytes(f.data[:f.len])) for f in frames]
+
+    def carry_before(self, sample):
+        _, blob, begin = self._run(sample)
+        return blob, (None if begin == 0xFFFFFFFF else begin)

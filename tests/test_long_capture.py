@@ -138,8 +138,67 @@ def test_carry_exchange_makes_a_short_overlap_exact(name):
     mag, rate, _ = U.fixture_wav(name)
     d = N.NfcDecoder()
     full = [f.key() for f in d.decode_batch(mag[None], N.SIG_MAG_F32, rate)]
-    for shards in (2, 3, 4):
+    for ranks, shards in ((False, 2), (False, 4), (True, 3), (True, 7)):
         st = {}
-        got = ND.decode_long_capture_carry(d, lambda b, e: mag[None, b:e], mag.size, shards, N.SIG_MAG_F32, rate, overlap=1 << 18, left=8192, stats=st)
-        assert got == full, (name, shards, st)
+        got = ND.decode_long_capture_carry(d, lambda b, e: mag[None, b:e], mag.size, shards, N.SIG_MAG_F32, rate, overlap=OVERLAP, left=8192, stats=st,
+                                           model_ranks=ranks, step=1 << 16 if shards == 7 else 1 << 20)
+        assert got == full, (name, shards, ranks, st)
     d.close()
+
+
+@pytest.mark.parametrize("ranks", [False, True], ids=["serial", "rank-protocol"])
+@pytest.mark.parametrize("name", NAMES)
+def test_carry_exchange_with_the_lane_pipeline(name, ranks):
+    """dist.decode_long_capture_carry over the host build of the lane pipeline (nfcutil.HostWindowDecoder: the same segment /
+    lane / carry-chain code as the device): with 8 192 samples of left overlap the stitched decode equals the uncut one.
+    serial: every shard decoded once from the injected carry; rank-protocol: cold decodes first, then the re-run from the
+    received carry until it meets the cold decode again (what one process per GPU does)"""
+    from nfc_laboratory_b200 import dist as ND
+    mag, rate, _ = U.fixture_wav(name)
+    full = committed_ref(name)[0]
+    d = U.HostWindowDecoder(rate)
+    for shards in ((3, 7) if ranks else (2, 4)):
+        st = {}
+        got = ND.decode_long_capture_carry(d, lambda b, e: mag[None, b:e], mag.size, shards, None, rate, overlap=OVERLAP, left=8192, stats=st, model_ranks=ranks,
+                                           step=1 << 16 if shards == 7 else 1 << 20)
+        assert got == full, (name, shards, st)
+
+
+def _carry_worker(rank, world, port, name, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import nfcutil as V
+    from nfc_laboratory_b200 import dist as ND
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mag, rate, _ = V.fixture_wav(name)
+    st = {}
+    mine = ND.decode_long_capture_carry(V.HostWindowDecoder(rate), lambda b, e: mag[None, b:e], mag.size, world, None, rate, overlap=OVERLAP, left=8192,
+                                        rank=rank, device="cpu", stats=st)
+    out = [None] * world
+    dist.all_gather_object(out, (mine, st))
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,world", [("test_NFC-A_106kbps_001", 3), ("test_NFC-F_212kbps_001", 2), ("test_NFC-B_106kbps_002", 2)])
+def test_carry_exchange_over_gloo(name, world):
+    """one process per shard: cold decodes in parallel, the carries sent rank to rank (send / recv of a byte tensor), the
+    bounds all-gathered; the concatenation in rank order is the uncut decode"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_carry_worker, args=(r, world, port, name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    frames = [f for part, _ in got for f in part]
+    assert frames == committed_ref(name)[0], [st for _, st in got]
