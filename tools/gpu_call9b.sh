@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
+(time timeout 900 python -m pytest tests/test_long_capture.py -m gpu -q) > gpurun_out/c9_long_capture_tests.log 2>&1
+tail -n 3 gpurun_out/c9_long_capture_tests.log
 for w in nfcb106 mixed nfca424; do
   (time timeout 600 python bench.py --workload $w --steps 2 --warmup 1 --no-e2e --no-wav-set) > gpurun_out/c9_bench_$w.log 2>&1
 done
