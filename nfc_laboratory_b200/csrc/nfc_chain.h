@@ -37,6 +37,7 @@ struct LaneRec
    u32 stream;
    u32 begin;      // own region [begin, end), samples, block aligned (end clipped to the stream length)
    u32 end;
+   u32 end0;       // end of the region as segmented (end grows when the lane takes over its successors)
    u32 first;      // first sample fed to the lane (begin - HALO, or 0)
    u32 stop;       // first sample NOT consumed by the last run
    u32 lockedMask; // techs locked during the last run
@@ -147,6 +148,7 @@ NFC_HD u32 blocks_segments(const u8 *flags, u32 nb, u32 nsamples, u32 stream, La
             l.stream = stream;
             l.begin = b * NFCB200_BLOCK;
             l.end = segEnd;
+            l.end0 = segEnd;
             l.first = lane_first_sample(flags, nb, b);
             l.stop = 0;
             l.lockedMask = 0;
@@ -160,6 +162,7 @@ NFC_HD u32 blocks_segments(const u8 *flags, u32 nb, u32 nsamples, u32 stream, La
       else if (count - 1 < cap)
       {
          out[count - 1].end = segEnd;
+         out[count - 1].end0 = segEnd;
       }
 
       if (++inGroup >= group)
@@ -170,6 +173,36 @@ NFC_HD u32 blocks_segments(const u8 *flags, u32 nb, u32 nsamples, u32 stream, La
 
    return count;
 }
+
+// the lanes that follow a running lane in its stream (time ordered, contiguous in the lane table).  Only first / end0 /
+// stream of those records are read: they never change after the segment pass
+struct LaneSucc
+{
+   const LaneRec *lanes;
+   u32 k, n;       // next candidate, table size
+   u32 stream;
+   u32 nextFirst;  // lanes[k].first, or 0xFFFFFFFF when the stream has no further lane
+
+   NFC_HD void init(const LaneRec *table, u32 self, u32 count)
+   {
+      lanes = table;
+      n = count;
+      k = self + 1;
+      stream = table ? table[self].stream : 0;
+      load();
+   }
+   NFC_HD void load() { nextFirst = (lanes && k < n && lanes[k].stream == stream) ? lanes[k].first : 0xFFFFFFFFu; }
+   NFC_HD void take(u32 pos, u32 &end)
+   {
+      while (pos > nextFirst)
+      {
+         if (lanes[k].end0 > end)
+            end = lanes[k].end0;
+         k++;
+         load();
+      }
+   }
+};
 
 /*
  * Drive one lane from R.first until it retires past R.end (or the stream ends).  Inside its own region the lane skips
@@ -183,10 +216,16 @@ NFC_HD u32 blocks_segments(const u8 *flags, u32 nb, u32 nsamples, u32 stream, La
  * One call = one iteration (at most one sample).  Returns false when the lane has retired.
  */
 template <class MACH, class LOAD, class ACTIVE, class ZERO>
-NFC_HD bool lane_iterate(MACH &M, Lane &L, const Params &P, u32 &pos, u32 end, u32 n, u32 kw, u32 &stepped, LOAD load, ACTIVE active, ZERO zero)
+NFC_HD bool lane_iterate(MACH &M, Lane &L, const Params &P, u32 &pos, u32 &end, u32 n, u32 kw, u32 &stepped, LOAD load, ACTIVE active, ZERO zero,
+                         LaneSucc &succ)
 {
    if (pos >= n)
       return false;
+
+   // still running past the point where the next lane of the stream started its warm-up: that lane will be swallowed
+   // (chain_walk), so its region is taken over right away instead of in a re-run over the extended region
+   if ((pos & 31) == 0 && pos > succ.nextFirst)
+      succ.take(pos, end);
 
    // retirement / skip-ahead is only examined every 32 samples (it costs a walk over all detector states)
    if ((pos & 31) == 0 && !active(pos) && M.dormant())
@@ -244,9 +283,10 @@ NFC_HD bool lane_iterate(MACH &M, Lane &L, const Params &P, u32 &pos, u32 end, u
 NFC_HD void carry_before(LaneRec *lanes, u32 n, const Params &P, const Carry *init, u32 sample, Carry &out, u32 &laneBegin);
 
 // copy the outcome of a finished run into its record
-NFC_HD void lane_record(LaneRec &R, const Lane &L, u32 stop, u32 gen, u32 nframes)
+NFC_HD void lane_record(LaneRec &R, const Lane &L, u32 stop, u32 gen, u32 nframes, u32 end)
 {
    R.stop = stop;
+   R.end = end; // grown over the successors the run took over (lane_iterate)
    R.lockedMask = L.lockedMask;
    R.out = L.c;
    R.out.edgeTime = L.fe.edgeTime;

@@ -345,6 +345,7 @@ __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Par
                uint32_t e = (lastActive + 1) * NFCB200_BLOCK;
                e = e > nsamples ? nsamples : e;
                c.lanes[off + laneIdx - 1].end = e;
+               c.lanes[off + laneIdx - 1].end0 = e;
                close_seg(segIdx - 1, e);
             }
 
@@ -367,6 +368,7 @@ __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Par
                l.stream = s;
                l.begin = (base + p) * NFCB200_BLOCK;
                l.end = l.begin;
+               l.end0 = l.begin;
                l.first = segFirst;
                l.seg0 = segOff + segIdx - 1;
                l.stop = 0;
@@ -395,6 +397,7 @@ __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Par
          uint32_t e = (lastActive + 1) * NFCB200_BLOCK;
          e = e > nsamples ? nsamples : e;
          c.lanes[off + laneIdx - 1].end = e;
+         c.lanes[off + laneIdx - 1].end0 = e;
          close_seg(segIdx - 1, e);
       }
 
@@ -432,6 +435,7 @@ struct LaneConfig
    const uint8_t *flags;
    uint32_t n_blocks;
    LaneRec *lanes;
+   uint32_t n_lanes;         // size of the lane table
    const uint32_t *queue;
    uint32_t queue_count;
    uint32_t *cursor;         // work-stealing cursor over the queue
@@ -501,8 +505,10 @@ __global__ void __launch_bounds__(LANE_THREADS, 4) lanes_kernel(LaneConfig c, co
 
       const uint64_t streamBase = have ? (uint64_t) R.stream * c.n_samples : 0;
       const uint8_t *flags = c.flags + (have ? (size_t) R.stream * c.n_blocks : 0);
-      const uint32_t end = have ? R.end : 0;
+      uint32_t end = have ? R.end : 0;
       const uint32_t n = (uint32_t) c.n_samples;
+      LaneSucc succ;
+      succ.init(have ? c.lanes : nullptr, li, c.n_lanes);
 
       uint32_t pos = have ? R.first : 0;
       uint32_t stepped = 0;
@@ -531,12 +537,12 @@ __global__ void __launch_bounds__(LANE_THREADS, 4) lanes_kernel(LaneConfig c, co
       for (uint32_t kw = 0; __any_sync(0xffffffffu, running); kw++)
       {
          if (running)
-            running = lane_iterate(M, L, dP, pos, end, n, kw, stepped, load, active, zero);
+            running = lane_iterate(M, L, dP, pos, end, n, kw, stepped, load, active, zero, succ);
       }
 
       if (have)
       {
-         lane_record(R, L, pos, sink.gen, sink.seq);
+         lane_record(R, L, pos, sink.gen, sink.seq, end);
          atomicAdd(c.work, (unsigned long long) stepped);
       }
    }
@@ -842,7 +848,7 @@ __global__ void __launch_bounds__(32) wlanes_kernel(WLaneConfig c, const __grid_
 
       if (lane == 0)
       {
-         lane_record(R, sm.L, sm.sh.pos, sink.gen, sink.seq);
+         lane_record(R, sm.L, sm.sh.pos, sink.gen, sink.seq, R.end);
          atomicAdd(c.work, (unsigned long long) sm.sh.stepped);
       }
       __syncwarp();

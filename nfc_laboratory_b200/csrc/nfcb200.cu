@@ -891,6 +891,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
          tc.flags = h->flags.as<uint8_t>();
          tc.n_blocks = n_blocks;
          tc.lanes = h->lanes.as<LaneRec>();
+         tc.n_lanes = nLanes;
          tc.queue = h->queue.as<u32>();
          tc.queue_count = queueCount;
          tc.cursor = &dC->cursor;

@@ -230,6 +230,8 @@ uint32_t hostsim_first_sample(const uint8_t *flags, uint32_t nb, uint32_t bb)
  * one lane per segment, carry chain to the fixed point.  stats: [0] lanes [1] live lanes [2] rounds [3] lane runs
  * [4] samples stepped [5] active blocks
  */
+int g_hostsim_no_takeover = 0; // 1: lanes never take over their successors in-run (the chain walk alone extends regions)
+
 static long pipeline_impl(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t enabled, uint8_t *flags, uint32_t nb, sim_frame *out, long cap,
                           uint64_t *stats, uint32_t group, const Carry *init, uint32_t query, Carry *qOut, uint32_t *qBegin)
 {
@@ -302,10 +304,16 @@ static long pipeline_impl(const float *mag, uint64_t n, uint32_t sampleRate, uin
          auto active = [&](uint32_t p) { return (flags[p / NFCB200_BLOCK] & SCR_ACTIVE) != 0; };
          auto zero = [&]() { std::fill(scratch.begin() + NFCB200_OFF_CA, scratch.end(), 0.0f); };
 
-         while (lane_iterate(M, L, P, pos, R.end, (uint32_t) n, kw, stepped, load, active, zero))
+         uint32_t end = R.end;
+         LaneSucc succ;
+         succ.init(lanes.data(), j, nseg);
+         if (g_hostsim_no_takeover)
+            succ.nextFirst = 0xFFFFFFFFu;
+
+         while (lane_iterate(M, L, P, pos, end, (uint32_t) n, kw, stepped, load, active, zero, succ))
             kw++;
 
-         lane_record(R, L, pos, R.gen + 1, (uint32_t) sink.count);
+         lane_record(R, L, pos, R.gen + 1, (uint32_t) sink.count, end);
          buf.resize(sink.count);
          frames[j] = buf;
 
@@ -518,7 +526,7 @@ long hostsim_pipeline2(const float *mag, uint64_t n, uint32_t sampleRate, uint32
          WL.noff = g_hostsim_noff != 0;
          WL.run(R, seg0[j], (uint32_t) n);
 
-         lane_record(R, L, sh.pos, R.gen + 1, (uint32_t) sink.count);
+         lane_record(R, L, sh.pos, R.gen + 1, (uint32_t) sink.count, R.end);
          buf.resize(std::min<long>(sink.count, (long) buf.size()));
          frames[j] = buf;
          runs++;
@@ -561,6 +569,11 @@ long hostsim_pipeline2(const float *mag, uint64_t n, uint32_t sampleRate, uint32
       stats[7] = total;
    }
    return count;
+}
+
+void hostsim_set_no_takeover(int v)
+{
+   g_hostsim_no_takeover = v;
 }
 
 void hostsim_set_noff(int v)

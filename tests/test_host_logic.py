@@ -106,3 +106,16 @@ def test_lane_warm_up_is_long_only_near_the_carrier_thresholds():
     assert first([bb - 16]) == bb * 256 - 4096 and first([bb - 17]) == bb * 256 - 1536
     assert first([bb + 10]) == bb * 256 - 4096 and first([bb + 11]) == bb * 256 - 1536
     assert first([], b=16) == 0 and first([], b=17) == 17 * 256 - 1536
+
+
+@pytest.mark.parametrize("name", ["test_NFC-V_26kbps_001", "test_NFC-A_424kbps_002", "test_NFC-B_106kbps_002", "test_NFC-F_212kbps_001"])
+def test_in_run_takeover_equals_the_chain_walk_extension(name):
+    """a lane that is still running when it passes its successor's warm-up start takes that lane's region over in the same
+    run (lane_iterate / LaneSucc); without it the chain walk extends the region and the lane runs again: same frames, never
+    more rounds"""
+    mag, rate, _ = U.fixture_wav(name)
+    trig = S.block_flags(mag, S.ScreenParams(rate))
+    a, sa = U.sim_pipeline(mag, trig, rate, takeover=False)
+    b, sb = U.sim_pipeline(mag, trig, rate, takeover=True)
+    assert a == b
+    assert sb["rounds"] <= sa["rounds"] and sb["work"] <= sa["work"] and sb["live"] == sa["live"]

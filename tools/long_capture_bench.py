@@ -58,7 +58,7 @@ def main():
     frames = ND.decode_long_capture_carry(dec, window, n, world, N.SIG_IQ_F32, 10_000_000, overlap=args.overlap, left=args.left,
                                           rank=(rank if world > 1 else None), device=dev, stats=st)
     torch.cuda.synchronize()
-    counts = torch.tensor([len(frames), st.get("redecoded", 0)], dtype=torch.int64, device=dev)
+    counts = torch.tensor([len(frames), st.get("redecoded", 0), st.get("redecoded_samples", 0)], dtype=torch.int64, device=dev)
     if world > 1:
         allc = [torch.zeros_like(counts) for _ in range(world)]
         dist.all_gather(allc, counts)
@@ -98,6 +98,7 @@ def main():
                                                            "left overlap %d, right overlap %d, carry exchange rank to rank" % (args.workload, n, world, args.left, args.overlap)},
             "value": n / dt / 1e6, "unit": "MSamples/s", "n_gpus": world, "seconds": dt, "frames": len(stitched), "uncut_frames": len(ref),
             "stitched_equals_uncut": bool(same), "shards_decoded_from_an_injected_carry": int(sum(int(c[1].item()) for c in allc)),
+            "samples_decoded_again": int(sum(int(c[2].item()) for c in allc)),
             "uncut_one_gpu_msps": n / t_full / 1e6}))
     dec.close()
     if world > 1:
