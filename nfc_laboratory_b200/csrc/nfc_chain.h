@@ -311,6 +311,8 @@ NFC_HD void lane_record(LaneRec &R, const Lane &L, u32 stop, u32 gen, u32 nframe
 #define NFCB200_MOD_WORDS (sizeof(Mod) / 4)
 #define NFCB200_W_PULSE 4 /* Mod::searchPulseWidth     */
 #define NFCB200_W_THR 5   /* Mod::searchValueThreshold */
+#define NFCB200_W_LASTPHASE 7 /* Mod::searchLastPhase   */
+#define NFCB200_W_LASTVALUE 8 /* Mod::searchLastValue   */
 
 NFC_HD float u32_as_float(u32 v)
 {
@@ -358,6 +360,9 @@ NFC_HD LaneObs lane_obs(const LaneRec &L)
  *   - NFC-F searchPulseWidth: read only by `searchPulseWidth++ < 94` (NfcF.cpp:307, 844); until its first reset the run
  *     executed fInc0 such tests, all with the same outcome under both carries iff both stay below / above 94 throughout
  *   - NFC-F searchValueThreshold: until its first assignment it is compared once, against fThrSync (NfcF.cpp:313, 331)
+ *   - NFC-F searchLastValue / searchLastPhase: stale values of an earlier search that the reference never clears; read
+ *     only at a threshold pass (LastValue, NfcF.cpp:344) and at the preamble's final test (LastPhase, :349), normally after
+ *     the run's own assignment (:300, :344) -- the run notes when it was not (fThrRead bits 2.. / 4..)
  */
 NFC_HD bool word_observed_equal(const LaneObs &L, int g, u32 w, u32 a, u32 t)
 {
@@ -389,6 +394,12 @@ NFC_HD bool word_observed_equal(const LaneObs &L, int g, u32 w, u32 a, u32 t)
          float sv = L.fThrSync[r], fa = u32_as_float(a), ft = u32_as_float(t);
          return (sv < fa) == (sv < ft) && (sv > fa) == (sv > ft);
       }
+
+      if (f == NFCB200_W_LASTVALUE)
+         return !((L.fThrRead >> (2 + r)) & 1);
+
+      if (f == NFCB200_W_LASTPHASE)
+         return !((L.fThrRead >> (4 + r)) & 1);
    }
 
    return false;
@@ -431,6 +442,12 @@ NFC_HD u32 compose_word(const LaneObs &L, int g, u32 w, u32 n, u32 o, u32 i)
 
       if (f == NFCB200_W_THR)
          return ((L.fThrWritten >> r) & 1) ? o : n;
+
+      if (f == NFCB200_W_LASTVALUE)
+         return ((L.fThrWritten >> (2 + r)) & 1) ? o : n;
+
+      if (f == NFCB200_W_LASTPHASE)
+         return ((L.fThrWritten >> (4 + r)) & 1) ? o : n;
    }
 
    return o != i ? o : n;
@@ -534,7 +551,7 @@ NFC_HD u32 chain_walk(LaneRec *lanes, u32 n, const Params &P, const Carry *init 
                   carry_group(L.in, g, pa, wa);
                   carry_group(cur, g, pb, wb);
                   for (u32 i = 0; i < wa; i++)
-                     if (pa[i] != pb[i])
+                     if (!word_observed_equal(lane_obs(L), g, i, pa[i], pb[i]))
                         printf("        word %u: assumed %08x true %08x\n", i, pa[i], pb[i]);
 #endif
                }

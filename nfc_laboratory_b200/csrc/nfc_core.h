@@ -161,8 +161,9 @@ struct Lane
    u32 lcWritten;  // bit t: frameStatus.lastCommand of tech t was assigned during this run
    u32 lcLive;     // bit t: ... and was read by a listen frame before any assignment (the run depends on the carry value)
    u32 fZeroed;    // bit r: NFC-F rate r searchPulseWidth was reset during this run (restart / reset / listen clear)
-   u32 fThrWritten;// bit r: NFC-F rate r searchValueThreshold was assigned during this run
-   u32 fThrRead;   // bit r: ... and was compared before any assignment, against fThrSync[r]
+   u32 fThrWritten;// bit r: NFC-F rate r searchValueThreshold was assigned during this run; bit 2 + r: searchLastValue; bit 4 + r: searchLastPhase
+   u32 fThrRead;   // bit r: ... and was compared before any assignment, against fThrSync[r]; bits 2 + r / 4 + r: the incoming
+                   // searchLastValue / searchLastPhase was read before the run assigned it (NfcF.cpp:300, 344, 349)
    u32 edgeWritten;// the carrier edge time was assigned during this run (an edge, or the reset after a carrier frame)
    u32 edgeLive;   // ... and a carrier frame read it before any assignment (the run depends on the carried value)
    u32 fInc0[2];   // `searchPulseWidth++ < 94` tests executed before the first reset (NfcF.cpp:307)
@@ -2499,7 +2500,7 @@ struct Machine
    NFC_HD void F_reset()
    {
       L.fZeroed |= 3;
-      L.fThrWritten |= 3;
+      L.fThrWritten |= 0x3F; // threshold, searchLastValue, searchLastPhase of both rates
       for (int r = 0; r < 2; r++)
       {
          zero_mod(L.c.mF[r]);
@@ -2564,6 +2565,7 @@ struct Machine
       {
          m.searchSyncValue = sd;
          m.searchLastValue = s0;
+         L.fThrWritten |= (&m == &L.c.mF[1]) ? 8u : 4u;
       }
 
       if (clk != m.searchEndTime)
@@ -2600,11 +2602,17 @@ struct Machine
          m.searchStartTime = m.searchSyncTime - b.p8;
          m.searchEndTime = m.searchSyncTime + b.p8;
          m.searchValueThreshold = m.correlatedPeakValue / 2;
+         if (!((L.fThrWritten >> (2 + fr)) & 1))
+            L.fThrRead |= 4u << fr; // the searchLastValue this run started from is used
+         L.fThrWritten |= 16u << fr;
          m.searchLastPhase = m.searchLastValue;
          m.correlatedPeakTime = 0;
          m.correlatedPeakValue = 0;
          return false;
       }
+
+      if (!((L.fThrWritten >> (4 + fr)) & 1))
+         L.fThrRead |= 16u << fr; // no threshold pass in this run yet: the searchLastPhase it started from decides
 
       if ((m.searchLastPhase < 0 && m.searchCorr0Value < 0) || (m.searchLastPhase > 0 && m.searchCorr0Value > 0))
          m.symbolStartTime -= b.p2;
@@ -2909,6 +2917,7 @@ struct Machine
                {
                   clear_for_listen(L.c.mF[F.lockRate - 1], P.F[F.lockRate].corr, P.F[F.lockRate].p1);
                   F_note_zeroed(L.c.mF[F.lockRate - 1]);
+                  L.fThrWritten |= 0x14u << (F.lockRate - 1); // searchLastValue / searchLastPhase cleared as well
                }
 
                return;
@@ -3861,6 +3870,15 @@ NFC_HD void mod_canon(Mod &m, bool isF)
       u32 *raw = (u32 *) &m;
       for (u32 i = 0; i < sizeof(Mod) / 4; i++)
          raw[i] = 0;
+   }
+   else if (isF && !(m.searchSyncTime | m.searchEndTime))
+   {
+      // NFC-F residue (pulse counter / threshold survive between searches, NfcF.cpp:307-345) with no window pending: the
+      // next window can only be opened by a fresh peak, which assigns searchSyncValue and searchCorr0Value before the
+      // window end reads them (NfcF.cpp:283-292) -- the stale values are dead, and carrying them would make every later
+      // lane depend on them
+      m.searchSyncValue = 0;
+      m.searchCorr0Value = 0;
    }
 }
 
