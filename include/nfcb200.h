@@ -175,6 +175,10 @@ int nfcb200_get_block_flags(nfcb200_handle *h, uint8_t *out, uint64_t cap, uint6
  * (one shot; clock_shift is subtracted from the absolute sample times it holds: the next window counts from its own first
  * sample).  The blob is opaque, nfcb200_carry_size() bytes: protocol state (FSD / FWT / SFGT from RATS / ATS / ATTRIB, the
  * Encrypted flag, lastCommand -- NfcA.cpp:1592-1790, NfcB.cpp:1153-1258), carrier flags, the carrier edge time.
+ * A window decoded from an injected carry is a CONTINUATION, not a decoder start: the reference's start-of-stream
+ * behaviour (two carrier-off frames at samples 0 and 1, detectors held off for 1 024 samples) does not apply, its first
+ * 2 048 samples are warm-up only (start the window that far, or further, in front of the idle point the carry belongs
+ * to: nfc_laboratory_b200/dist.py decode_long_capture_carry uses 6 144).
  */
 int nfcb200_carry_size(void);
 int nfcb200_default_carry(nfcb200_handle *h, void *blob, uint64_t cap); /* what a cold-started lane assumes: power-on state, carrier on */
