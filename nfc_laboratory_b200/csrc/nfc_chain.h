@@ -430,6 +430,10 @@ NFC_HD u32 compose_word(const LaneObs &L, int g, u32 w, u32 n, u32 o, u32 i)
    if (g >= 4 && g < 8 && w == 0)
       return ((L.lcWritten >> (g - 4)) & 1) ? o : n;
 
+   // protocol status (TechSt words 11..15): assigned by the run, or passed through
+   if (g >= 4 && g < 8 && w >= sizeof(FrameSt) / 4 && w < (sizeof(FrameSt) + sizeof(Proto)) / 4)
+      return ((L.lcWritten >> (8 + 5 * (g - 4) + (w - sizeof(FrameSt) / 4))) & 1) ? o : n;
+
    if (g == 8 && w == 2)
       return L.edgeWritten ? o : n;
 

@@ -100,6 +100,9 @@ struct TechSt
    u32 chained;
 };
 
+// bit of Lane::lcWritten for word k of Proto (maxFrameSize, frameGuardTime, frameWaitingTime, startUpGuardTime, requestGuardTime)
+#define NFCB200_PSW(t, k) (1u << (8 + 5 * (t) + (k)))
+
 // the part of the decoder that survives between capture segments ("carry"): everything except the front-end
 // recurrences and the rings, which a lane re-derives over its warm-up halo ("segment speculation")
 struct Carry
@@ -158,7 +161,9 @@ struct Lane
    u32 pulseBits; // NFC-V pulse code: 2 or 8 (decoder->pulse)
    u32 lockedMask; // techs that were locked at least once during this run (bit t), for the carry dependency check
    // finer dependency tracking of the run on its incoming carry (nfc_chain.h chain_walk):
-   u32 lcWritten;  // bit t: frameStatus.lastCommand of tech t was assigned during this run
+   u32 lcWritten;  // bit t: frameStatus.lastCommand of tech t was assigned during this run; bit 8 + 5 t + k: word k of tech t's
+                   // protocol status (NFCB200_PSW) was assigned -- only used to PREDICT the carry behind a run that must be
+                   // repeated (nfc_chain.h compose_word): a run that assigns the value it happened to start from did assign it
    u32 lcLive;     // bit t: ... and was read by a listen frame before any assignment (the run depends on the carry value)
    u32 fZeroed;    // bit r: NFC-F rate r searchPulseWidth was reset during this run (restart / reset / listen clear)
    u32 fThrWritten;// bit r: NFC-F rate r searchValueThreshold was assigned during this run; bit 2 + r: searchLastValue; bit 4 + r: searchLastPhase
@@ -882,11 +887,11 @@ struct Machine
 
    NFC_HD void A_default_protocol(Proto &ps)
    {
-      ps.maxFrameSize = 256;
-      ps.startUpGuardTime = P.A_sfgt;
-      ps.frameGuardTime = P.A_fgt;
-      ps.frameWaitingTime = P.A_fwt;
-      ps.requestGuardTime = P.A_rgt;
+      ps.maxFrameSize = 256; L.lcWritten |= NFCB200_PSW(TECH_A, 0);
+      ps.startUpGuardTime = P.A_sfgt; L.lcWritten |= NFCB200_PSW(TECH_A, 3);
+      ps.frameGuardTime = P.A_fgt; L.lcWritten |= NFCB200_PSW(TECH_A, 1);
+      ps.frameWaitingTime = P.A_fwt; L.lcWritten |= NFCB200_PSW(TECH_A, 2);
+      ps.requestGuardTime = P.A_rgt; L.lcWritten |= NFCB200_PSW(TECH_A, 4);
    }
 
    // NfcA::Impl::process and the processXXX chain, NfcA.cpp:1480-1973
@@ -982,7 +987,7 @@ struct Machine
                      int fsdi = (fb(1, len) >> 4) & 0x0F;
                      fs.lastCommand = b0;
             L.lcWritten |= 1u << TECH_A;
-                     ps.maxFrameSize = (u32) nfc_fds_table((int) fsdi);
+                     ps.maxFrameSize = (u32) nfc_fds_table((int) fsdi); L.lcWritten |= NFCB200_PSW(TECH_A, 0);
                      fs.frameWaitingTime = P.fwtActivation;
                      phase = PH_Selection;
                      flags |= !A_crc_ok(len) ? FL_Crc : 0;
@@ -1010,13 +1015,13 @@ struct Machine
                            sfgi = 0;
                         if (fwi == 15)
                            fwi = 4;
-                        ps.startUpGuardTime = (u32) (int) (P.stu * nfc_xgt_table((int) sfgi));
-                        ps.frameWaitingTime = (u32) (int) (P.stu * nfc_xgt_table((int) fwi));
+                        ps.startUpGuardTime = (u32) (int) (P.stu * nfc_xgt_table((int) sfgi)); L.lcWritten |= NFCB200_PSW(TECH_A, 3);
+                        ps.frameWaitingTime = (u32) (int) (P.stu * nfc_xgt_table((int) fwi)); L.lcWritten |= NFCB200_PSW(TECH_A, 2);
                      }
                      else
                      {
-                        ps.startUpGuardTime = P.A_sfgt;
-                        ps.frameWaitingTime = P.A_fwt;
+                        ps.startUpGuardTime = P.A_sfgt; L.lcWritten |= NFCB200_PSW(TECH_A, 3);
+                        ps.frameWaitingTime = P.A_fwt; L.lcWritten |= NFCB200_PSW(TECH_A, 2);
                      }
                   }
 
@@ -2098,11 +2103,11 @@ struct Machine
             {
                fs.lastCommand = b0;
             L.lcWritten |= 1u << TECH_B;
-               ps.maxFrameSize = 256;
-               ps.startUpGuardTime = P.B_sfgt;
-               ps.frameGuardTime = P.B_fgt;
-               ps.frameWaitingTime = P.B_fwt;
-               ps.requestGuardTime = P.B_rgt;
+               ps.maxFrameSize = 256; L.lcWritten |= NFCB200_PSW(TECH_B, 0);
+               ps.startUpGuardTime = P.B_sfgt; L.lcWritten |= NFCB200_PSW(TECH_B, 3);
+               ps.frameGuardTime = P.B_fgt; L.lcWritten |= NFCB200_PSW(TECH_B, 1);
+               ps.frameWaitingTime = P.B_fwt; L.lcWritten |= NFCB200_PSW(TECH_B, 2);
+               ps.requestGuardTime = P.B_rgt; L.lcWritten |= NFCB200_PSW(TECH_B, 4);
                fs.frameGuardTime = P.B_tr0min;
                fs.frameWaitingTime = P.B_fwtAtqb;
                t.chained = 0;
@@ -2115,8 +2120,8 @@ struct Machine
          {
             int fdsi = (fb(10, len) >> 4) & 0x0f;
             int fwi = (fb(11, len) >> 4) & 0x0f;
-            ps.maxFrameSize = (u32) nfc_fds_table((int) fdsi);
-            ps.frameWaitingTime = (u32) (int) (P.stu * nfc_xgt_table((int) fwi));
+            ps.maxFrameSize = (u32) nfc_fds_table((int) fdsi); L.lcWritten |= NFCB200_PSW(TECH_B, 0);
+            ps.frameWaitingTime = (u32) (int) (P.stu * nfc_xgt_table((int) fwi)); L.lcWritten |= NFCB200_PSW(TECH_B, 2);
             phase = PH_Selection;
             flags |= !B_crc_ok(len) ? FL_Crc : 0;
             break;
@@ -2132,11 +2137,12 @@ struct Machine
                u32 param1 = fb(5, len), param2 = fb(6, len);
                u32 tr0i = (param1 >> 6) & 0x3;
                u32 fdsi = param2 & 0xf;
-               ps.maxFrameSize = (u32) nfc_fds_table((int) fdsi);
+               ps.maxFrameSize = (u32) nfc_fds_table((int) fdsi); L.lcWritten |= NFCB200_PSW(TECH_B, 0);
                if (!tr0i)
                   ps.frameGuardTime = P.B_fgt;
                else
                   ps.frameGuardTime = (u32) (int) (P.stu * (tr0i == 1 ? 48 * 16 : tr0i == 2 ? 16 * 16 : 0));
+               L.lcWritten |= NFCB200_PSW(TECH_B, 1);
                fs.frameWaitingTime = P.fwtActivation;
                t.chained = 0;
                phase = PH_Selection;
@@ -2767,11 +2773,11 @@ struct Machine
             fs.lastCommand = b1;
             L.lcWritten |= 1u << TECH_F;
             int tsn = (int) (5 < len ? d[5] : 0);
-            ps.maxFrameSize = 256;
-            ps.startUpGuardTime = P.F_sfgt;
-            ps.frameGuardTime = P.F_fgt;
-            ps.frameWaitingTime = P.F_fwt;
-            ps.requestGuardTime = P.F_rgt;
+            ps.maxFrameSize = 256; L.lcWritten |= NFCB200_PSW(TECH_F, 0);
+            ps.startUpGuardTime = P.F_sfgt; L.lcWritten |= NFCB200_PSW(TECH_F, 3);
+            ps.frameGuardTime = P.F_fgt; L.lcWritten |= NFCB200_PSW(TECH_F, 1);
+            ps.frameWaitingTime = P.F_fwt; L.lcWritten |= NFCB200_PSW(TECH_F, 2);
+            ps.requestGuardTime = P.F_rgt; L.lcWritten |= NFCB200_PSW(TECH_F, 4);
             fs.frameGuardTime = (u32) (P.stu * 1024);
             fs.frameWaitingTime = (u32) (P.stu * (512 * 64 + (tsn + 1) * (256 * 64)));
             t.chained = 0;
