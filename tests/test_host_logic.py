@@ -119,3 +119,19 @@ def test_in_run_takeover_equals_the_chain_walk_extension(name):
     b, sb = U.sim_pipeline(mag, trig, rate, takeover=True)
     assert a == b
     assert sb["rounds"] <= sa["rounds"] and sb["work"] <= sa["work"] and sb["live"] == sa["live"]
+
+
+@pytest.mark.skipif(U.ref_lib() is None, reason="oracle/_ref/libnfcref.so not built")
+@pytest.mark.parametrize("workload,rounds,runs", [("nfca424", 2, 1.8), ("nfcb106", 2, 1.8), ("mixed", 3, 2.8)])
+def test_carry_chain_converges_in_few_rounds_on_sessions_with_sticky_state(workload, rounds, runs):
+    """synthetic sessions that set protocol state (PPS to 424 kbps, ATTRIB parameters) or leave NFC-F search residue behind:
+    the speculative lanes + carry chain still equal the sequential reference, and the chain needs no more rounds than the
+    dependency depth (a regression here is a throughput loss, not an error: every extra round repeats most lanes)"""
+    from nfc_laboratory_b200 import synth
+    iq = synth.synth_batch(workload, 1, 2_000_000, seed=5, device="cpu")[0].numpy()
+    mag = np.sqrt(iq[:, 0].astype(np.float32) ** 2 + iq[:, 1].astype(np.float32) ** 2).astype(np.float32)
+    trig = S.block_flags(mag, S.ScreenParams(10_000_000))
+    frames, st = U.sim_pipeline(mag, trig, 10_000_000)
+    assert frames == U.ref_decode(mag, 10_000_000)
+    assert st["rounds"] <= rounds, st
+    assert st["runs"] <= runs * st["lanes"], st  # mixed: a stalled NFC-B SOF search (live residue, NfcB.cpp:308-361) comes and goes with the carry
