@@ -249,12 +249,13 @@ def full_parity(frames, iq, S, n, threads, budget_s=90.0, chunk_streams=32):
         return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
-def lanes_traffic(exact):
-    """DRAM bytes per launch of the lane kernel from the committed ncu capture of the same workload (profiles/), or None"""
+def lanes_traffic(exact, input_bytes):
+    """DRAM bytes per launch of the lane kernel: the ncu capture committed under profiles/ (dram read + write per input byte
+    of the captured launch) scaled to this launch's input, or None"""
     try:
         with open(os.path.join(ROOT, "profiles", "lanes_kernel_traffic.json")) as f:
             t = json.load(f)
-        return float(t["exact" if exact else "thread"]["dram_bytes_per_launch"])
+        return float(t["exact" if exact else "thread"]["dram_bytes_per_input_byte"]) * input_bytes
     except Exception:
         return None
 
@@ -566,7 +567,7 @@ def main():
     step_achieved = bytes_per_step / (ms_step * 1e-3) / 1e9 if ms_step > 0 else 0.0
     lane_kernel = "wlanes_kernel (K2, warp lanes: one warp per stream, rings in shared memory)" if args.exact else \
         "lanes_kernel (K2, thread lanes: one thread per segment group, exact per-sample decoder)"
-    roofline = {"bound": "hbm", "achieved": lanes_achieved, "peak": peak, "unit": "GB/s", "frac": lanes_achieved / peak, "traffic": lanes_traffic(args.exact),
+    roofline = {"bound": "hbm", "achieved": lanes_achieved, "peak": peak, "unit": "GB/s", "frac": lanes_achieved / peak, "traffic": lanes_traffic(args.exact, bytes_per_step),
                 "kernel": lane_kernel, "peak_source": peak_src, "algorithmic_bytes_per_launch": lanes_bytes, "ms_per_launch": ms_lanes,
                 "note": "algorithmic bytes = the active share of the input the lanes must read (%.3f of %d bytes); all lane + chain launches of a step" % (lane_frac, bytes_per_step)}
     roofline_k1 = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
