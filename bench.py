@@ -489,8 +489,7 @@ def main():
         gather(buf, nf)
 
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()  # every rank watches its own GPU: the slowest rank sets the step time
 
     if world > 1:
         dist.barrier()
@@ -521,7 +520,7 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dt = float(tmax.item())
 
-    clocks = sampler.summary() if rank == 0 else None
+    clocks = sampler.summary()
 
     # host wall time of the decode call and of the gather per step: slowest and fastest rank (the weak-scaling loss is the spread)
     rank_spread = None
@@ -532,6 +531,15 @@ def main():
         dist.all_reduce(vmin, op=dist.ReduceOp.MIN)
         rank_spread = {"decode_call_ms_max": float(vmax[0]), "decode_call_ms_min": float(vmin[0]), "gather_call_ms_max": float(vmax[1]),
                        "gather_call_ms_min": float(vmin[1])}
+        mine = {"rank": rank, "decode_call_ms": statistics.mean(t_decode), "gather_call_ms": statistics.mean(t_gather),
+                "sm_mhz": (clocks or {}).get("sm_mhz"), "power_w_max": (clocks or {}).get("power_w_max"), "reasons": (clocks or {}).get("reasons")}
+        for k in ("ms_screen", "ms_segment", "ms_lanes", "ms_gather", "ms_total", "ms_wall"):
+            mine[k] = statistics.mean(s_[k] for s_ in stats)
+        mine["lanes"] = stats[-1]["lanes"]
+        mine["lane_samples"] = stats[-1]["lane_samples"]
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+        rank_spread["per_rank"] = per_rank
 
     # frame gather phases of the timed steps, max over ranks (the last gather_steps entries: warm-up and e2e gathers excluded)
     gather_phases = {}

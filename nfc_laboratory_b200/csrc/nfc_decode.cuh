@@ -1030,6 +1030,19 @@ __global__ void lane_length_kernel(const LaneRec *lanes, uint32_t n, uint32_t *l
       length[i] = lanes[i].end - lanes[i].first;
 }
 
+// development statistics (NFCB200_TRACE): how far the lanes really ran -- histogram of stop - first in 4 096-sample bins
+// [0..63], the longest run as (length << 32 | lane) in [64..65] (one 64-bit word)
+__global__ void lane_run_stat_kernel(const LaneRec *lanes, uint32_t n, unsigned long long *out)
+{
+   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n || lanes[i].dead || lanes[i].gen == 0)
+      return;
+   const uint32_t len = lanes[i].stop - lanes[i].first;
+   const uint32_t bin = len / 4096 < 63 ? len / 4096 : 63;
+   atomicAdd(&out[bin], 1ull);
+   atomicMax(&out[64], ((unsigned long long) len << 32) | i);
+}
+
 // carry in front of the first lane of stream 0 that begins at or after `sample` (nfc_chain.h carry_before)
 __global__ void carry_before_kernel(LaneRec *lanes, uint32_t n, const Carry *carryIn, uint32_t sample, Carry *out, uint32_t *laneBegin, const __grid_constant__ Params dP)
 {

@@ -912,12 +912,43 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
       launches++;
       CUDA_TRY(cudaGetLastError());
 
+      const u32 ran = queueCount;
       CUDA_TRY(cudaMemcpyAsync(&queueCount, &dC->queueCount, sizeof(u32), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
+      if (tr.on)
+      {
+         char what[64];
+         snprintf(what, sizeof(what), "  round %u: %u lanes", rounds, ran);
+         tr.mark(what);
+      }
    }
 
    S.rounds = rounds;
    tr.mark("lanes + chain");
+
+   if (tr.on && nLanes)
+   {
+      // how far the lanes really ran: the longest run bounds the lane kernel from below whatever the total work is
+      if (h->scratch.reserve(65 * sizeof(unsigned long long)) == 0)
+      {
+         unsigned long long *dStat = (unsigned long long *) h->scratch.ptr;
+         unsigned long long hs[65];
+         cudaMemsetAsync(dStat, 0, sizeof(hs), st);
+         lane_run_stat_kernel<<<(nLanes + 255) / 256, 256, 0, st>>>(h->lanes.as<LaneRec>(), nLanes, dStat);
+         cudaMemcpyAsync(hs, dStat, sizeof(hs), cudaMemcpyDeviceToHost, st);
+         cudaStreamSynchronize(st);
+         LaneRec lr;
+         const u32 li = (u32) (hs[64] & 0xFFFFFFFFu);
+         cudaMemcpy(&lr, h->lanes.as<LaneRec>() + li, sizeof(LaneRec), cudaMemcpyDeviceToHost);
+         fprintf(stderr, "[nfcb200] longest lane run: %llu samples (lane %u, stream %u, first %u begin %u end0 %u end %u stop %u, %u frames)\n[nfcb200] runs by length / 4096:",
+                 hs[64] >> 32, li, lr.stream, lr.first, lr.begin, lr.end0, lr.end, lr.stop, lr.nframes);
+         for (int b = 0; b < 64; b++)
+            if (hs[b])
+               fprintf(stderr, " %d:%llu", b, hs[b]);
+         fprintf(stderr, "\n");
+         tr.mark("(lane run statistics)");
+      }
+   }
 
    cudaEventRecord(h->ev[4], st);
 
