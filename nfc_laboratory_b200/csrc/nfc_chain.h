@@ -442,7 +442,13 @@ NFC_HD u32 compose_word(const LaneObs &L, int g, u32 w, u32 n, u32 o, u32 i)
       u32 r = w / NFCB200_MOD_WORDS, f = w % NFCB200_MOD_WORDS;
 
       if (f == NFCB200_W_PULSE)
-         return ((L.fZeroed >> r) & 1) ? o : n + (o - i);
+      {
+         // not reset: the run added one per window-end test (fInc0); the canonical form saturates at 94 (mod_canon)
+         if ((L.fZeroed >> r) & 1)
+            return o;
+         const u32 v = n + L.fInc0[r];
+         return v > 94 ? 94 : v;
+      }
 
       if (f == NFCB200_W_THR)
          return ((L.fThrWritten >> r) & 1) ? o : n;

@@ -3877,7 +3877,10 @@ NFC_HD void mod_canon(Mod &m, bool isF)
       for (u32 i = 0; i < sizeof(Mod) / 4; i++)
          raw[i] = 0;
    }
-   else if (isF && !(m.searchSyncTime | m.searchEndTime))
+   if (isF && m.searchPulseWidth > 94)
+      m.searchPulseWidth = 94; // only ever read by `searchPulseWidth++ < 94` (NfcF.cpp:307, 844): every value from 94 on behaves alike
+
+   if (!mod_idle(m, isF) && isF && !(m.searchSyncTime | m.searchEndTime))
    {
       // NFC-F residue (pulse counter / threshold survive between searches, NfcF.cpp:307-345) with no window pending: the
       // next window can only be opened by a fresh peak, which assigns searchSyncValue and searchCorr0Value before the

@@ -202,3 +202,21 @@ def test_carry_exchange_over_gloo(name, world):
         assert p.exitcode == 0
     frames = [f for part, _ in got for f in part]
     assert frames == committed_ref(name)[0], [st for _, st in got]
+
+
+def test_rank_protocol_rejoins_the_cold_decode():
+    """a synthetic 424 kbps capture of 1.2 s on two shards: the second shard's cold decode misses the session state, the
+    re-run from the received carry meets it again once the saturating NFC-F pulse counter of the cold decode has caught up
+    (canonical carry: every value from 94 on is one state) -- the rest of the shard is NOT decoded again"""
+    from nfc_laboratory_b200 import synth, dist as ND
+    n = 12_000_000
+    iq = synth.synth_batch("nfca424", 1, n, seed=77, device="cpu")[0].numpy()
+    mag = np.sqrt(iq[:, 0].astype(np.float32) ** 2 + iq[:, 1].astype(np.float32) ** 2).astype(np.float32)
+    d = U.HostWindowDecoder(10_000_000)
+    key = lambda f: (f.tech_type, f.frame_type, f.frame_flags, f.frame_phase, f.frame_rate, f.sample_start, f.sample_end, f.data)
+    full = [key(f) for f in d.decode_batch(mag[None])]
+    st = {}
+    got = ND.decode_long_capture_carry(d, lambda b, e: mag[None, b:e], n, 2, None, 10_000_000, overlap=1 << 18, left=8192, stats=st, model_ranks=True,
+                                       step=1 << 18)
+    assert got == full
+    assert st["redecoded"] == 1 and st["redecoded_samples"] < 0.8 * (n // 2), st
