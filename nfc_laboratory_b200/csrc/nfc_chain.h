@@ -333,11 +333,25 @@ struct LaneObs
    u32 lcWritten, lcLive, fZeroed, fThrWritten, fThrRead;
    u32 fInc0[2];
    float fThrSync[2];
+   u32 inert;      // bit t: the TRUE carry in front of the run has maxFrameSize == 0 for tech t (set by the composing caller)
 };
+
+// a zero maxFrameSize (an RFU frame-size code in ATTRIB / RATS, NfcB.cpp:1235, NfcA.cpp:1664) truncates every later frame of
+// that technology at its first byte: no command is recognised any more, the protocol status is never assigned again.
+// Only used to PREDICT the carry behind a run that must be repeated: the repeat will assign nothing
+NFC_HD u32 carry_inert_mask(const Carry &c)
+{
+   u32 m = 0;
+   for (int t = 0; t < 4; t++)
+      if (c.t[t].ps.maxFrameSize == 0)
+         m |= 1u << t;
+   return m;
+}
 
 NFC_HD LaneObs lane_obs(const LaneRec &L)
 {
    LaneObs o;
+   o.inert = 0;
    o.edgeWritten = L.edgeWritten;
    o.edgeLive = L.edgeLive;
    o.lcWritten = L.lcWritten;
@@ -432,7 +446,11 @@ NFC_HD u32 compose_word(const LaneObs &L, int g, u32 w, u32 n, u32 o, u32 i)
 
    // protocol status (TechSt words 11..15): assigned by the run, or passed through
    if (g >= 4 && g < 8 && w >= sizeof(FrameSt) / 4 && w < (sizeof(FrameSt) + sizeof(Proto)) / 4)
+   {
+      if ((L.inert >> (g - 4)) & 1)
+         return n; // whatever the run assigned, it did so from a state in which frames decode; from the true state none does
       return ((L.lcWritten >> (8 + 5 * (g - 4) + (w - sizeof(FrameSt) / 4))) & 1) ? o : n;
+   }
 
    if (g == 8 && w == 2)
       return L.edgeWritten ? o : n;
@@ -467,7 +485,8 @@ NFC_HD u32 compose_word(const LaneObs &L, int g, u32 w, u32 n, u32 o, u32 i)
 NFC_HD void carry_compose(LaneRec &L, Carry &cur, Carry &next, u32 touched)
 {
    next = cur;
-   const LaneObs obs = lane_obs(L);
+   LaneObs obs = lane_obs(L);
+   obs.inert = carry_inert_mask(cur);
 
    for (int g = 0; g < NFCB200_GROUPS; g++)
    {

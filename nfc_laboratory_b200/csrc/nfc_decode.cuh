@@ -962,7 +962,8 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) chain_warp_kernel(ChainConfi
       const bool ran = L.gen > 0;
       const u32 touched = 0x10F | ((L.lockedMask & 0xF) << 4);
       const u32 wasDirty = L.dirty;
-      const LaneObs obs = lane_obs(L);
+      LaneObs obs = lane_obs(L);
+      obs.inert = carry_inert_mask(*reinterpret_cast<const Carry *>(cur));
       const u32 *in = (const u32 *) &L.in;
       const u32 *out = (const u32 *) &L.out;
 

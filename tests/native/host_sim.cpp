@@ -276,6 +276,7 @@ static long pipeline_impl(const float *mag, uint64_t n, uint32_t sampleRate, uin
    for (;;)
    {
       bool any = false;
+      std::vector<char> ranNow(nseg, 0);
 
       for (uint32_t j = 0; j < nseg; j++)
       {
@@ -285,6 +286,7 @@ static long pipeline_impl(const float *mag, uint64_t n, uint32_t sampleRate, uin
             continue;
 
          any = true;
+         ranNow[j] = 1;
 
          std::fill(scratch.begin(), scratch.end(), 0.0f);
          std::fill(sb.begin(), sb.end(), 0);
@@ -325,6 +327,15 @@ static long pipeline_impl(const float *mag, uint64_t n, uint32_t sampleRate, uin
          break;
 
       rounds++;
+
+      if (getenv("HOSTSIM_ROUNDS"))
+      {
+         fprintf(stderr, "round %llu ran:", (unsigned long long) rounds);
+         for (uint32_t j = 0; j < nseg; j++)
+            if (!lanes[j].dead && lanes[j].dirty == 0 && lanes[j].gen > 0 && lanes[j].nframes + 1 > 0 && lanes[j].stop && ranNow[j])
+               fprintf(stderr, " %u", j);
+         fprintf(stderr, "\n");
+      }
 
       chain_walk(lanes.data(), nseg, P, init);
    }

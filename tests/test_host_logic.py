@@ -135,3 +135,29 @@ def test_carry_chain_converges_in_few_rounds_on_sessions_with_sticky_state(workl
     assert frames == U.ref_decode(mag, 10_000_000)
     assert st["rounds"] <= rounds, st
     assert st["runs"] <= runs * st["lanes"], st  # mixed: a stalled NFC-B SOF search (live residue, NfcB.cpp:308-361) comes and goes with the carry
+
+
+@pytest.mark.skipif(U.ref_lib() is None, reason="oracle/_ref/libnfcref.so not built")
+def test_carry_chain_does_not_crawl_behind_a_zero_frame_size():
+    """an ATTRIB with an RFU frame-size code leaves maxFrameSize = 0 (NfcB.cpp:1235): the reference truncates every later
+    NFC-B frame at its first byte (nothing is emitted) and never assigns the protocol status again.  Every speculative run behind it decodes
+    its session and assigns that status -- predicting the carry from what those runs assigned made the chain advance one
+    lane per round (98 rounds on the nfcb106 batch); the prediction now passes an inert state through"""
+    from nfc_laboratory_b200 import synth as SY
+    fs = 10_000_000
+    reqb = bytes([0x05, 0x00, 0x00])
+    atqb = bytes([0x50, 0x11, 0x22, 0x33, 0x44, 0x00, 0x00, 0x00, 0x00, 0x00, 0x81, 0x81])
+    parts = [np.ones(40000, np.float32)]
+    for k in range(14):
+        attrib = bytes([0x1D, 0x11, 0x22, 0x33, 0x44, 0x00, 0x0D if k == 1 else 0x08, 0x01, 0x00])
+        for poll, listen in ((reqb, atqb), (attrib, b"\x00")):
+            parts += [SY.nfcb_exchange(fs, poll, listen), np.ones(30000, np.float32)]
+    rng = np.random.default_rng(3)
+    x = np.concatenate(parts) * np.float32(0.3)
+    mag = np.abs(x + rng.normal(0, 0.001, x.size)).astype(np.float32)
+    ref = U.ref_decode(mag, fs)
+    trig = S.block_flags(mag, S.ScreenParams(fs))
+    frames, st = U.sim_pipeline(mag, trig, fs)
+    assert frames == ref
+    assert ref[-1][7][:7] == bytes([0x1D, 0x11, 0x22, 0x33, 0x44, 0x00, 0x0D]), "nothing decodes behind the RFU ATTRIB: the state is inert"
+    assert st["rounds"] <= 3, st
