@@ -542,7 +542,9 @@ __global__ void __launch_bounds__(LANE_THREADS, 4) lanes_kernel(LaneConfig c, co
 
       if (have)
       {
-         lane_record(R, L, pos, sink.gen, sink.seq, end);
+         // `end` grew over the successors the run took over; the committed region (R.end) is only moved by the chain walk,
+         // which derives the same swallow decisions from R.stop (a run never retires before the end it grew to)
+         lane_record(R, L, pos, sink.gen, sink.seq, R.end);
          atomicAdd(c.work, (unsigned long long) stepped);
       }
    }

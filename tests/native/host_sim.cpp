@@ -315,7 +315,7 @@ static long pipeline_impl(const float *mag, uint64_t n, uint32_t sampleRate, uin
          while (lane_iterate(M, L, P, pos, end, (uint32_t) n, kw, stepped, load, active, zero, succ))
             kw++;
 
-         lane_record(R, L, pos, R.gen + 1, (uint32_t) sink.count, end);
+         lane_record(R, L, pos, R.gen + 1, (uint32_t) sink.count, R.end); // the committed region only moves in chain_walk
          buf.resize(sink.count);
          frames[j] = buf;
 
