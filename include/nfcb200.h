@@ -105,7 +105,7 @@ typedef struct nfcb200_stats
    float ms_total;            /* whole call, device events                      */
    float ms_wall;             /* whole call, host clock                         */
    float ms_front;            /* front pass (part of ms_segment .. ms_lanes: own event pair) */
-   float reserved0;
+   float straggler_lanes;     /* thread lanes that held the launch and were decoded again by a warp lane (a count)  */
    uint64_t feature_samples;  /* samples the front pass wrote to the feature pool */
 } nfcb200_stats;
 

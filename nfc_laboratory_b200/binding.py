@@ -50,7 +50,7 @@ class CStats(C.Structure):
         ("frames", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("ms_h2d", C.c_float), ("ms_screen", C.c_float), ("ms_segment", C.c_float), ("ms_lanes", C.c_float),
         ("ms_gather", C.c_float), ("ms_total", C.c_float), ("ms_wall", C.c_float),
-        ("ms_front", C.c_float), ("reserved0", C.c_float), ("feature_samples", C.c_uint64),
+        ("ms_front", C.c_float), ("straggler_lanes", C.c_float), ("feature_samples", C.c_uint64),
     ]
 
 

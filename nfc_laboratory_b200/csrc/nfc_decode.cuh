@@ -359,6 +359,7 @@ __global__ void segment_fill_kernel(SegmentConfig c, const __grid_constant__ Par
                S.first = segFirst;
                S.end = S.begin;
                S.band = S.begin - segFirst > NFCB200_HALO_SHORT ? 1u : 0u;
+               S.hasFeat = 0;
                segIdx++;
             }
 
@@ -443,6 +444,12 @@ struct LaneConfig
    uint8_t *sbuf;            // [n_warps * 32][512]
    FramePool pool;
    unsigned long long *work; // samples stepped (statistics)
+   // stragglers: once the queue is empty, a lane that has run bail_margin samples past the length it was queued with gives
+   // up and is decoded again by a warp lane (wlanes_kernel, 0.1-0.3 us per sample instead of 1.4-5): bail_margin 0 = never
+   uint32_t bail_margin;
+   uint32_t bail_always;     // test knob: give up past the margin whether the queue is empty or not
+   uint32_t *overrun;        // [n_lanes] lanes that gave up
+   uint32_t *overrun_count;
 };
 
 #define LANE_THREADS 128
@@ -513,6 +520,8 @@ __global__ void __launch_bounds__(LANE_THREADS, 4) lanes_kernel(LaneConfig c, co
       uint32_t pos = have ? R.first : 0;
       uint32_t stepped = 0;
       bool running = have;
+      bool bailed = false;
+      const uint32_t patience = c.bail_margin ? end - pos + c.bail_margin : 0xFFFFFFFFu;
 
       // the raw sample of the next step is requested one step ahead: every lane walks its own stream, so a warp touches 32
       // different lines and some lane misses the cache on almost every step
@@ -537,10 +546,30 @@ __global__ void __launch_bounds__(LANE_THREADS, 4) lanes_kernel(LaneConfig c, co
       for (uint32_t kw = 0; __any_sync(0xffffffffu, running); kw++)
       {
          if (running)
+         {
             running = lane_iterate(M, L, dP, pos, end, n, kw, stepped, load, active, zero, succ);
+
+            // a straggler holds the whole launch: everything else is done (the queue is empty) and this lane is far past
+            // the length it was queued with
+            if (running && (kw & 1023u) == 1023u && stepped > patience && (c.bail_always || *((volatile uint32_t *) c.cursor) >= c.queue_count))
+            {
+               running = false;
+               bailed = true;
+            }
+         }
       }
 
-      if (have)
+      if (bailed)
+      {
+         // the frames of this run are superseded by the generation of the warp lane's run; the record keeps the carry it
+         // started from and stays dirty
+         R.gen = sink.gen;
+         R.dirty = 1;
+         R.nframes = 0;
+         c.overrun[atomicAdd(c.overrun_count, 1u)] = li;
+         atomicAdd(c.work, (unsigned long long) stepped);
+      }
+      else if (have)
       {
          // `end` grew over the successors the run took over; the committed region (R.end) is only moved by the chain walk,
          // which derives the same swallow decisions from R.stop (a run never retires before the end it grew to)
@@ -586,6 +615,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) front_kernel(FrontConfig c, con
    O.tDev = S.tDev;
    O.tF1 = S.tF1;
    O.tPulse = S.tPulse;
+   O.hasFeat = 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -49,6 +49,8 @@ struct SegRec
    float tEnv, tAvg, tDev, tF1; // front-end state after sample end - 1: a lane that runs past the range continues from it
    u32 tPulse;
    u32 band;   // the warm-up was the long one (carrier average exact)
+   u32 hasFeat; // the front pass of this segment ran: pool[featOff ..] and the t* fields are valid.  Without it a warp lane
+                // runs the front-end recurrences itself (fill_front): the straggler pass of throughput mode
 };
 
 #define NFCB200_PREROLL 400u /* samples of sums + rings before the detectors of a skipped-to segment open (> longest period) */
@@ -149,6 +151,7 @@ struct WShared
    u32 pos, n, mode, si, j, stepped, blockActive;
    float scalEnv, scalAvg, scalDev, scalF1; // front-end state of a lane past its feature range (fill_front)
    u32 scalPulse;
+   u32 scalAge;      // samples since a cold start of that state, saturating (the envelope follows x over the first etu)
    u32 nextB, nextSeg, nextCls, nextFrom; // cached look-ahead of the current inactive run: next active block, its segment, gap class
    u32 jumpCls, jumpTa, jumpGs, jumpT, jumpG, jumpB, jumpSeg;
    float delta[6];
@@ -286,8 +289,8 @@ struct WLane
       if (W::lane() == 0)
       {
          float env = sh.scalEnv, avg = sh.scalAvg, dev = sh.scalDev, f1 = sh.scalF1;
-         u32 pulse = sh.scalPulse, closed = F.closed;
-         const u32 hold = (u32) (P.etu * 10);
+         u32 pulse = sh.scalPulse, closed = F.closed, age = sh.scalAge;
+         const u32 hold = (u32) (P.etu * 10), etu = (u32) P.etu;
 
          for (u32 i = 0; i < n; i++)
          {
@@ -309,6 +312,12 @@ struct WLane
                pulse = 0;
                env = env * P.envW0 + x * P.envW1;
             }
+            else if (age < etu)
+            {
+               env = x; // cold start (front_pass, Machine::front): the envelope follows the signal over the first etu
+            }
+            if (age < 0xFFFFu)
+               age++;
 
             float n0 = x + f1 * P.iirA;
             float w = n0 - f1;
@@ -328,6 +337,7 @@ struct WLane
          sh.scalDev = dev;
          sh.scalF1 = f1;
          sh.scalPulse = pulse;
+         sh.scalAge = age;
          F.closed = closed;
       }
    }
@@ -1004,7 +1014,29 @@ struct WLane
       sh.scalDev = S.tDev;
       sh.scalF1 = S.tF1;
       sh.scalPulse = S.tPulse;
+      sh.scalAge = 0xFFFFu;
       sh.mode = WMODE_SCAL;
+   }
+
+   // a range without features (SegRec::hasFeat == 0) entered at `at`: the front end starts from zero at the range's first
+   // sample like the front pass would, and is brought up to `at` here (one thread, no ring traffic)
+   NFC_HD void enter_scalar_cold(const SegRec &S, u32 at)
+   {
+      SegRec tmp = S;
+      if (at > S.first)
+      {
+         front_pass(P, S.first, at, [&](u32 p) { return src.x(p); }, [](u32, float, float, float, float) {}, tmp);
+         enter_scalar(tmp);
+         const u32 age = at - S.first;
+         sh.scalAge = age < 0xFFFFu ? age : 0xFFFFu;
+      }
+      else
+      {
+         sh.scalEnv = sh.scalAvg = sh.scalDev = sh.scalF1 = 0.0f;
+         sh.scalPulse = 0;
+         sh.scalAge = 0;
+         sh.mode = WMODE_SCAL;
+      }
    }
 
    NFC_HD void plain_chunk(u32 pos, u32 limit)
@@ -1072,7 +1104,7 @@ struct WLane
                      B = N.begin;
                      found = true;
                   }
-                  else if (pos >= N.first + NFCB200_HALO_SHORT)
+                  else if (N.hasFeat && pos >= N.first + NFCB200_HALO_SHORT)
                   {
                      // inside that segment's feature range: its features are exact once the front pass has converged (the
                      // same contraction a lane start relies on), and they continue the lane's own rings without a seam
@@ -1139,6 +1171,8 @@ struct WLane
          sh.pos = R.first;
          sh.mode = WMODE_FEAT;
          sh.si = seg0;
+         if (!src.seg(seg0).hasFeat)
+            enter_scalar_cold(src.seg(seg0), R.first);
          sh.stepped = 0;
          sh.nextB = 0;
       }
@@ -1194,6 +1228,8 @@ struct WLane
                F.closed = 64;
                sh.si = sh.jumpSeg;
                sh.mode = WMODE_FEAT;
+               if (!src.seg(sh.jumpSeg).hasFeat)
+                  enter_scalar_cold(src.seg(sh.jumpSeg), T);
                sh.pos = T;
                sh.stepped += T - from;
             }

@@ -155,6 +155,8 @@ struct Counters
    u32 extCount;
    u32 queueCount;
    u32 cursor;
+   u32 overrunCount; // lanes that gave up in the thread-lane kernel (stragglers), decoded again by warp lanes
+   u32 pad0;
    unsigned long long work;
    unsigned long long live;
    u32 segTotal;
@@ -221,6 +223,9 @@ struct nfcb200_handle
    cudaEvent_t ev[12] = {};
 
    int wlanesPerSm = 7; // resident warp lanes per SM (shared memory: sizeof(WLaneSmem) each)
+   bool stragglerAlways = false;
+   u32 stragglerMargin = 4096; // thread lanes: samples past its queued length after which a lane that holds the launch gives up
+                               // and is decoded again by a warp lane (0: never; development knob NFCB200_STRAGGLER)
    int laneBlocks = 4;  // resident thread-lane blocks per SM (lanes_kernel __launch_bounds__)
    int shortHalo = 1;   // NFCB200_HALO_SHORT=0 forces the long warm-up for every segment (measurement knob)
 
@@ -453,6 +458,13 @@ int nfcb200_create(const nfcb200_config *cfg, nfcb200_handle **out)
 
    if (const char *e = getenv("NFCB200_HALO_SHORT"))
       h->shortHalo = atoi(e) ? 1 : 0;
+   if (const char *e = getenv("NFCB200_STRAGGLER"))
+   {
+      // N > 0: margin in samples; 0: off; N < 0 (tests): margin |N|, and a lane gives up whether the queue is empty or not
+      const int v = atoi(e);
+      h->stragglerMargin = (u32) (v < 0 ? -v : v);
+      h->stragglerAlways = v < 0;
+   }
 
 #define NFCB200_SMEM_ATTR(K) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScreenSmem))
    NFCB200_SMEM_ATTR((screen_kernel<SIG_IQ_F32, false>));
@@ -856,6 +868,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    u32 queueCount = nLanes;
    u32 maxRounds = h->cfg.max_rounds ? h->cfg.max_rounds : 4096;
    u32 rounds = 0;
+   u32 stragglers = 0;
 
    while (queueCount > 0)
    {
@@ -899,7 +912,33 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
          tc.sbuf = h->sbuf.as<uint8_t>();
          tc.pool = pool;
          tc.work = &dC->work;
+         tc.bail_margin = h->stragglerMargin;
+         tc.bail_always = h->stragglerAlways ? 1u : 0u;
+         tc.overrun = h->meta.as<u32>(); // free between the queue ordering and the gather
+         tc.overrun_count = &dC->overrunCount;
+         CUDA_TRY(cudaMemsetAsync(&dC->overrunCount, 0, sizeof(u32), st));
          lanes_kernel<<<blocks, LANE_THREADS, 0, st>>>(tc, h->P);
+
+         if (tc.bail_margin)
+         {
+            u32 overrun = 0;
+            CUDA_TRY(cudaMemcpyAsync(&overrun, &dC->overrunCount, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (overrun)
+            {
+               // the stragglers again, each by a whole warp with its history in shared memory; without a feature pool the
+               // warp lane runs the front end itself (SegRec::hasFeat is 0 in throughput mode)
+               CUDA_TRY(cudaMemsetAsync(&dC->cursor, 0, sizeof(u32), st));
+               lc.queue = h->meta.as<u32>();
+               lc.queue_count = overrun;
+               wlanes_kernel<<<std::min(maxWarps, overrun), 32, sizeof(WLaneSmem), st>>>(lc, h->P);
+               launches++;
+               S.lane_runs += overrun;
+               stragglers += overrun;
+               if (tr.on)
+                  fprintf(stderr, "[nfcb200]   %u straggler lane(s) handed to the warp lanes\n", overrun);
+            }
+         }
       }
       launches++;
       CUDA_TRY(cudaGetLastError());
@@ -924,6 +963,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    }
 
    S.rounds = rounds;
+   S.straggler_lanes += (float) stragglers;
    tr.mark("lanes + chain");
 
    if (tr.on && nLanes)

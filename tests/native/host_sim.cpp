@@ -230,6 +230,29 @@ uint32_t hostsim_first_sample(const uint8_t *flags, uint32_t nb, uint32_t bb)
  * one lane per segment, carry chain to the fixed point.  stats: [0] lanes [1] live lanes [2] rounds [3] lane runs
  * [4] samples stepped [5] active blocks
  */
+struct HostSrc
+{
+   const float *mag;
+   const Feat *pool;
+   const uint8_t *flags;
+   const float *bmeans;
+   const SegRec *segs;
+   uint32_t nsegs;
+   bool exactInt;
+
+   float x(uint32_t pos) const { return mag[pos]; }
+   Feat feat(unsigned long long i) const { return pool[i]; }
+   bool active(uint32_t pos) const { return (flags[pos / NFCB200_BLOCK] & SCR_ACTIVE) != 0; }
+   float bmean(uint32_t b) const { return bmeans[b]; }
+   const SegRec &seg(uint32_t i) const { return segs[i]; }
+   uint32_t nseg() const { return nsegs; }
+   bool exact_int() const { return exactInt; }
+};
+
+int g_hostsim_noff = 0;
+int g_hostsim_nofeat = 0; // 1: no front pass, no feature pool: the warp lanes run the front-end recurrences themselves (the straggler pass)
+int g_hostsim_bail = -1; // >= 0: a thread lane that runs this many samples past its queued length gives up and is decoded again by a warp
+                         // lane without features (the straggler pass of the product, here without the "queue is empty" condition)
 int g_hostsim_no_takeover = 0; // 1: lanes never take over their successors in-run (the chain walk alone extends regions)
 
 static long pipeline_impl(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t enabled, uint8_t *flags, uint32_t nb, sim_frame *out, long cap,
@@ -271,7 +294,29 @@ static long pipeline_impl(const float *mag, uint64_t n, uint32_t sampleRate, uin
    std::vector<float> scratch(NFCB200_SCRATCH_FLOATS);
    std::vector<u8> sb(512);
 
-   uint64_t rounds = 0, runs = 0, work = 0;
+   uint64_t rounds = 0, runs = 0, work = 0, bails = 0;
+
+   // segment table and block means for the straggler pass (group 1: lane j is segment j)
+   std::vector<SegRec> segs(nseg);
+   std::vector<float> bmeans(g_hostsim_bail >= 0 ? nb : 0);
+   if (g_hostsim_bail >= 0)
+   {
+      for (uint32_t j = 0; j < nseg; j++)
+      {
+         std::memset(&segs[j], 0, sizeof(SegRec));
+         segs[j].first = lanes[j].first;
+         segs[j].begin = lanes[j].begin;
+         segs[j].end = lanes[j].end0;
+      }
+      for (uint32_t b = 0; b < nb; b++)
+      {
+         double acc = 0;
+         uint64_t cnt = 0;
+         for (uint64_t i = (uint64_t) b * NFCB200_BLOCK; i < n && i < (uint64_t) (b + 1) * NFCB200_BLOCK; i++, cnt++)
+            acc += mag[i];
+         bmeans[b] = cnt ? (float) (acc / cnt) : 0.0f;
+      }
+   }
 
    for (;;)
    {
@@ -312,8 +357,39 @@ static long pipeline_impl(const float *mag, uint64_t n, uint32_t sampleRate, uin
          if (g_hostsim_no_takeover)
             succ.nextFirst = 0xFFFFFFFFu;
 
+         bool bailed = false;
+         const uint32_t patience = g_hostsim_bail >= 0 ? R.end - R.first + (uint32_t) g_hostsim_bail : 0xFFFFFFFFu;
          while (lane_iterate(M, L, P, pos, end, (uint32_t) n, kw, stepped, load, active, zero, succ))
+         {
             kw++;
+            if (stepped > patience)
+            {
+               bailed = true;
+               break;
+            }
+         }
+
+         if (bailed)
+         {
+            // the product's straggler pass: the lane again, by a warp lane that runs the front end itself
+            bails++;
+            work += stepped;
+            std::fill(scratch.begin(), scratch.end(), 0.0f);
+            std::fill(sb.begin(), sb.end(), 0);
+            sink.count = 0;
+            Lane WLn;
+            WShared sh;
+            std::memset(&sh, 0, sizeof(sh));
+            HostSrc src {mag, nullptr, flags, bmeans.data(), segs.data(), nseg, false};
+            WLane<HostWarp, Sink, HostSrc> WL(P, WLn, scratch.data(), sb.data(), sink, sh, src);
+            WL.run(R, j, (uint32_t) n);
+            lane_record(R, WLn, sh.pos, R.gen + 2, (uint32_t) sink.count, R.end);
+            buf.resize(sink.count);
+            frames[j] = buf;
+            runs++;
+            work += sh.stepped;
+            continue;
+         }
 
          lane_record(R, L, pos, R.gen + 1, (uint32_t) sink.count, R.end); // the committed region only moves in chain_walk
          buf.resize(sink.count);
@@ -377,6 +453,7 @@ static long pipeline_impl(const float *mag, uint64_t n, uint32_t sampleRate, uin
       stats[3] = runs;
       stats[4] = work;
       stats[5] = act;
+      stats[6] = bails;
    }
 
    return count;
@@ -420,26 +497,6 @@ long hostsim_window(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t 
  * per-sample machine (fast-forward paths off) -- the self-check of the fast paths.
  * stats: [0] lanes [1] live lanes [2] rounds [3] lane runs [4] samples stepped [5] active blocks [6] segments [7] feature samples
  */
-struct HostSrc
-{
-   const float *mag;
-   const Feat *pool;
-   const uint8_t *flags;
-   const float *bmeans;
-   const SegRec *segs;
-   uint32_t nsegs;
-   bool exactInt;
-
-   float x(uint32_t pos) const { return mag[pos]; }
-   Feat feat(unsigned long long i) const { return pool[i]; }
-   bool active(uint32_t pos) const { return (flags[pos / NFCB200_BLOCK] & SCR_ACTIVE) != 0; }
-   float bmean(uint32_t b) const { return bmeans[b]; }
-   const SegRec &seg(uint32_t i) const { return segs[i]; }
-   uint32_t nseg() const { return nsegs; }
-   bool exact_int() const { return exactInt; }
-};
-
-int g_hostsim_noff = 0;
 
 long hostsim_pipeline2(const float *mag, uint64_t n, uint32_t sampleRate, uint32_t enabled, uint8_t *flags, uint32_t nb, sim_frame *out, long cap,
                        uint64_t *stats, uint32_t group, uint32_t exactInt)
@@ -478,13 +535,14 @@ long hostsim_pipeline2(const float *mag, uint64_t n, uint32_t sampleRate, uint32
       S.featOff = total;
       total += S.end - S.first;
    }
-   std::vector<Feat> pool(total);
-   for (uint32_t i = 0; i < nseg; i++)
+   std::vector<Feat> pool(g_hostsim_nofeat ? 1 : total);
+   for (uint32_t i = 0; i < nseg && !g_hostsim_nofeat; i++)
    {
       SegRec &S = segs[i];
       Feat *dst = pool.data() + S.featOff;
       front_pass(P, S.first, S.end, [&](uint32_t p) { return mag[p]; },
                  [&](uint32_t i, float w, float env, float dev, float avg) { dst[i] = Feat {w, env, dev, avg}; }, S);
+      S.hasFeat = 1;
    }
 
    // lanes
@@ -585,6 +643,16 @@ long hostsim_pipeline2(const float *mag, uint64_t n, uint32_t sampleRate, uint32
 void hostsim_set_no_takeover(int v)
 {
    g_hostsim_no_takeover = v;
+}
+
+void hostsim_set_bail(int v)
+{
+   g_hostsim_bail = v;
+}
+
+void hostsim_set_nofeat(int v)
+{
+   g_hostsim_nofeat = v;
 }
 
 void hostsim_set_noff(int v)

@@ -218,6 +218,8 @@ def sim_lib():
                                           C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32]
         lib.hostsim_set_noff.argtypes = [C.c_int]
         lib.hostsim_set_no_takeover.argtypes = [C.c_int]
+        lib.hostsim_set_nofeat.argtypes = [C.c_int]
+        lib.hostsim_set_bail.argtypes = [C.c_int]
         lib.hostsim_window.restype = C.c_long
         lib.hostsim_window.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(SimFrame), C.c_long,
                                        C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
@@ -243,7 +245,7 @@ def sim_run(mag, rate=10000000, enabled=0xF, first=0, warm=4096, own_end=0, carr
     return frames, cout.raw, res
 
 
-def sim_pipeline(mag, trigger_blocks, rate=10000000, enabled=0xF, cap=65536, group=1, takeover=True):
+def sim_pipeline(mag, trigger_blocks, rate=10000000, enabled=0xF, cap=65536, group=1, takeover=True, bail=None):
     """segment-speculative pipeline on the host build of the lane machine; trigger_blocks: bool per 256-sample block"""
     lib = sim_lib()
     mag = np.ascontiguousarray(mag, dtype=np.float32)
@@ -251,15 +253,17 @@ def sim_pipeline(mag, trigger_blocks, rate=10000000, enabled=0xF, cap=65536, gro
     buf = (SimFrame * cap)()
     stats = (C.c_uint64 * 8)()
     lib.hostsim_set_no_takeover(0 if takeover else 1)
+    lib.hostsim_set_bail(-1 if bail is None else int(bail))
     n = lib.hostsim_pipeline(mag.ctypes.data, mag.size, rate, enabled, flags.ctypes.data, flags.size, buf, cap, stats, group)
     lib.hostsim_set_no_takeover(0)
+    lib.hostsim_set_bail(-1)
     assert 0 <= n <= cap
     frames = [frame_tuple(f.tech, f.type, f.flags, f.phase, f.rate, f.start, f.end, bytes(f.data[:f.len])) for f in buf[:n]]
-    st = dict(lanes=stats[0], live=stats[1], rounds=stats[2], runs=stats[3], work=stats[4], active_blocks=stats[5])
+    st = dict(lanes=stats[0], live=stats[1], rounds=stats[2], runs=stats[3], work=stats[4], active_blocks=stats[5], bails=stats[6])
     return frames, st
 
 
-def sim_pipeline2(mag, trigger_blocks, rate=10000000, enabled=0xF, cap=65536, group=0, exact_int=False, noff=False):
+def sim_pipeline2(mag, trigger_blocks, rate=10000000, enabled=0xF, cap=65536, group=0, exact_int=False, noff=False, nofeat=False):
     """round-2 pipeline on the host (front pass -> feature pool -> warp lanes, nfc_wlane.h); group=0: one lane per stream"""
     lib = sim_lib()
     mag = np.ascontiguousarray(mag, dtype=np.float32)
@@ -267,8 +271,10 @@ def sim_pipeline2(mag, trigger_blocks, rate=10000000, enabled=0xF, cap=65536, gr
     buf = (SimFrame * cap)()
     stats = (C.c_uint64 * 8)()
     lib.hostsim_set_noff(1 if noff else 0)
+    lib.hostsim_set_nofeat(1 if nofeat else 0)
     n = lib.hostsim_pipeline2(mag.ctypes.data, mag.size, rate, enabled, flags.ctypes.data, flags.size, buf, cap, stats, group, 1 if exact_int else 0)
     lib.hostsim_set_noff(0)
+    lib.hostsim_set_nofeat(0)
     assert 0 <= n <= cap
     frames = [frame_tuple(f.tech, f.type, f.flags, f.phase, f.rate, f.start, f.end, bytes(f.data[:f.len])) for f in buf[:n]]
     st = dict(lanes=stats[0], live=stats[1], rounds=stats[2], runs=stats[3], work=stats[4], active_blocks=stats[5], segments=stats[6],

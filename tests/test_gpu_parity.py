@@ -204,3 +204,48 @@ def test_frames_export_roundtrip_from_the_device(decoder, tmp_path):
         assert json.load(f) == json.load(g)
     X.write_trz(tmp_path / "out.trz", frames, rate)
     assert X.read_trz(tmp_path / "out.trz") == keys(frames)
+
+
+@pytest.fixture(scope="module")
+def straggler_decoder():
+    """a decoder whose thread lanes give up as soon as they run 1 sample past the length they were queued with, whatever the
+    queue holds (NFCB200_STRAGGLER=-1, read at nfcb200_create): every such lane is decoded again by a warp lane"""
+    import os
+    import nfc_laboratory_b200 as N
+    old = os.environ.get("NFCB200_STRAGGLER")
+    os.environ["NFCB200_STRAGGLER"] = "-1"
+    try:
+        d = N.NfcDecoder()
+    finally:
+        if old is None:
+            del os.environ["NFCB200_STRAGGLER"]
+        else:
+            os.environ["NFCB200_STRAGGLER"] = old
+    yield d
+    d.close()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_straggler_pass_equals_reference(straggler_decoder, name):
+    """thread lanes + feature-less warp lanes for the lanes that overran + the carry chain over both == the reference"""
+    import nfc_laboratory_b200 as N
+    mag, rate, _ = U.fixture_wav(name)
+    frames = straggler_decoder.decode_batch(mag[None, :], N.SIG_MAG_F32, rate)
+    assert keys(frames) == committed_ref(name)[0]
+    pcm = np.round(mag * 32768.0).astype(np.int16)
+    frames = straggler_decoder.decode_batch(pcm[None, :], N.SIG_MAG_S16, rate)
+    assert keys(frames) == committed_ref(name)[0]
+
+
+def test_straggler_pass_on_a_float_batch(decoder, straggler_decoder):
+    """64 synthetic float2 IQ streams: the batch with its overrunning lanes handed to warp lanes decodes to the same frames
+    as the plain thread lanes, and lanes were handed over"""
+    import torch
+    import nfc_laboratory_b200 as N
+    from nfc_laboratory_b200 import synth
+    iq = synth.synth_batch("nfca106", 64, 2_000_000, seed=5, device="cuda:0")
+    a = keys(decoder.decode_batch(iq, N.SIG_IQ_F32, 10_000_000, cap=1 << 18))
+    b = keys(straggler_decoder.decode_batch(iq, N.SIG_IQ_F32, 10_000_000, cap=1 << 18))
+    st = straggler_decoder.stats()
+    assert st["straggler_lanes"] > 0
+    assert a == b and len(a) > 1000

@@ -60,3 +60,42 @@ def test_paths_without_a_reference_fixture(name):
     for group in (0, 1):
         out, _ = U.sim_pipeline2(x, S.block_flags_device_model(x, S.ScreenParams(X.FS)), X.FS, group=group)
         assert out == ref
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_warp_lanes_without_a_feature_pool(name):
+    """the straggler pass of throughput mode: no front pass has run (SegRec.hasFeat == 0), the warp lane computes the
+    front-end recurrences itself -- cold at a range's first sample like the front pass, brought up to the entry point after
+    a skipped idle stretch (WLane::enter_scalar_cold).  One lane per segment, and one lane for the whole capture on a cut"""
+    mag, rate, _ = U.fixture_wav(name)
+    trig = S.block_flags(mag, S.ScreenParams(rate))
+    groups = (1, 0) if name in NAMES[::4] else (1,)
+    for group in groups:
+        frames, _ = U.sim_pipeline2(mag, trig, rate, group=group, exact_int=True, nofeat=True)
+        assert frames == committed_ref(name)[0], group
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_thread_lane_stragglers_handed_to_warp_lanes(name):
+    """lanes_kernel + straggler pass on the host: every thread lane that runs past the length it was queued with gives up
+    and is decoded again by a feature-less warp lane; its neighbours stay thread lanes; the carry chain joins them"""
+    mag, rate, _ = U.fixture_wav(name)
+    trig = S.block_flags(mag, S.ScreenParams(rate))
+    frames, st = U.sim_pipeline(mag, trig, rate, bail=0)
+    assert frames == committed_ref(name)[0], st
+
+
+@pytest.mark.skipif(U.ref_lib() is None, reason="oracle/_ref/libnfcref.so not built")
+@pytest.mark.parametrize("workload", ["nfca106", "mixed"])
+def test_straggler_pass_on_float_streams(workload):
+    """float input (cold-started sums in both kinds of lane): thread lanes, thread lanes with every overrunning lane handed
+    to a warp lane, and feature-less warp lanes alone all equal the reference on a synthetic stream"""
+    from nfc_laboratory_b200 import synth
+    iq = synth.synth_batch(workload, 1, 2_500_000, seed=11, device="cpu")[0].numpy()
+    mag = np.sqrt(iq[:, 0].astype(np.float32) ** 2 + iq[:, 1].astype(np.float32) ** 2).astype(np.float32)
+    trig = S.block_flags(mag, S.ScreenParams(FS))
+    ref = U.ref_decode(mag, FS)
+    assert U.sim_pipeline(mag, trig, FS)[0] == ref
+    mixed, st = U.sim_pipeline(mag, trig, FS, bail=0)
+    assert mixed == ref and st["bails"] > 0, st
+    assert U.sim_pipeline2(mag, trig, FS, group=1, exact_int=False, nofeat=True)[0] == ref
