@@ -454,7 +454,9 @@ struct LaneConfig
 
 #define LANE_THREADS 128
 
-// all taps of a step are fetched up front (Machine TAPS = 2), four resident blocks per SM
+// all taps of a step are fetched up front (Machine TAPS = 2), four resident blocks per SM.  BAIL: the straggler hand-over is
+// compiled in (a separate instantiation: the extra state costs the plain kernel registers -- 219 -> 250 ms when it was not)
+template <bool BAIL>
 __global__ void __launch_bounds__(LANE_THREADS, 4) lanes_kernel(LaneConfig c, const __grid_constant__ Params dP)
 {
    const uint32_t lane = threadIdx.x & 31;
@@ -521,7 +523,7 @@ __global__ void __launch_bounds__(LANE_THREADS, 4) lanes_kernel(LaneConfig c, co
       uint32_t stepped = 0;
       bool running = have;
       bool bailed = false;
-      const uint32_t patience = c.bail_margin ? end - pos + c.bail_margin : 0xFFFFFFFFu;
+      const uint32_t patience = BAIL ? end - pos + c.bail_margin : 0xFFFFFFFFu;
 
       // the raw sample of the next step is requested one step ahead: every lane walks its own stream, so a warp touches 32
       // different lines and some lane misses the cache on almost every step
@@ -551,15 +553,18 @@ __global__ void __launch_bounds__(LANE_THREADS, 4) lanes_kernel(LaneConfig c, co
 
             // a straggler holds the whole launch: everything else is done (the queue is empty) and this lane is far past
             // the length it was queued with
-            if (running && (kw & 1023u) == 1023u && stepped > patience && (c.bail_always || *((volatile uint32_t *) c.cursor) >= c.queue_count))
+            if constexpr (BAIL)
             {
-               running = false;
-               bailed = true;
+               if (running && (kw & 1023u) == 1023u && stepped > patience && (c.bail_always || *((volatile uint32_t *) c.cursor) >= c.queue_count))
+               {
+                  running = false;
+                  bailed = true;
+               }
             }
          }
       }
 
-      if (bailed)
+      if (BAIL && bailed)
       {
          // the frames of this run are superseded by the generation of the warp lane's run; the record keeps the carry it
          // started from and stays dirty

@@ -224,7 +224,7 @@ struct nfcb200_handle
 
    int wlanesPerSm = 7; // resident warp lanes per SM (shared memory: sizeof(WLaneSmem) each)
    bool stragglerAlways = false;
-   u32 stragglerMargin = 4096; // thread lanes: samples past its queued length after which a lane that holds the launch gives up
+   u32 stragglerMargin = 0; // thread lanes: samples past its queued length after which a lane that holds the launch gives up
                                // and is decoded again by a warp lane (0: never; development knob NFCB200_STRAGGLER)
    int laneBlocks = 4;  // resident thread-lane blocks per SM (lanes_kernel __launch_bounds__)
    int shortHalo = 1;   // NFCB200_HALO_SHORT=0 forces the long warm-up for every segment (measurement knob)
@@ -917,13 +917,18 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
          tc.overrun = h->meta.as<u32>(); // free between the queue ordering and the gather
          tc.overrun_count = &dC->overrunCount;
          CUDA_TRY(cudaMemsetAsync(&dC->overrunCount, 0, sizeof(u32), st));
-         lanes_kernel<<<blocks, LANE_THREADS, 0, st>>>(tc, h->P);
+         if (tc.bail_margin)
+            lanes_kernel<true><<<blocks, LANE_THREADS, 0, st>>>(tc, h->P);
+         else
+            lanes_kernel<false><<<blocks, LANE_THREADS, 0, st>>>(tc, h->P);
 
          if (tc.bail_margin)
          {
             u32 overrun = 0;
             CUDA_TRY(cudaMemcpyAsync(&overrun, &dC->overrunCount, sizeof(u32), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
+            if (tr.on)
+               tr.mark("  thread lanes");
             if (overrun)
             {
                // the stragglers again, each by a whole warp with its history in shared memory; without a feature pool the
@@ -936,7 +941,12 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
                S.lane_runs += overrun;
                stragglers += overrun;
                if (tr.on)
-                  fprintf(stderr, "[nfcb200]   %u straggler lane(s) handed to the warp lanes\n", overrun);
+               {
+                  cudaStreamSynchronize(st);
+                  char what[64];
+                  snprintf(what, sizeof(what), "  %u straggler(s) on warp lanes", overrun);
+                  tr.mark(what);
+               }
             }
          }
       }
