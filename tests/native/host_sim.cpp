@@ -595,6 +595,10 @@ long hostsim_pipeline2(const float *mag, uint64_t n, uint32_t sampleRate, uint32
          WL.noff = g_hostsim_noff != 0;
          WL.run(R, seg0[j], (uint32_t) n);
 
+         if (getenv("HOSTSIM_PHASES"))
+            fprintf(stderr, "lane %u [%u,%u) stop %u: control %llu fill %llu search %llu machine %llu walk %llu jump %llu scalar %llu locked %llu\n", j, R.first,
+                    R.end, sh.pos, sh.cnt[0], sh.cnt[1], sh.cnt[2], sh.cnt[3], sh.cnt[4], sh.cnt[5], sh.cnt[6], sh.cnt[7]);
+
          lane_record(R, L, sh.pos, R.gen + 1, (uint32_t) sink.count, R.end);
          buf.resize(std::min<long>(sink.count, (long) buf.size()));
          frames[j] = buf;
