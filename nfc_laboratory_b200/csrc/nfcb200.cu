@@ -1015,7 +1015,7 @@ static int decode_resident(nfcb200_handle *h, const void *dSamples, int sigtype,
    CUDA_TRY(cudaStreamSynchronize(st));
 
    S.lane_samples = hc.work;
-   if (tr.on && exact)
+   if (tr.on && (exact || stragglers))
    {
       static const char *names[8] = {"control", "fill", "search", "machine", "walk", "jump", "scalar", "locked"};
       unsigned long long tot = 0;
