@@ -3,7 +3,8 @@
 the compiled reference: random synthetic streams (workload, amplitude 0.05-0.9, noise 3e-4..2e-2, 1.5-4 M samples), decoded by
 the speculative thread lanes and by the thread lanes with every overrunning lane handed to a feature-less warp lane.
 
-usage: python tools/cpu_fuzz_host.py <worker> <n_workers> <seconds>      (test infrastructure: needs oracle/_ref)
+usage: python tools/cpu_fuzz_host.py <worker> <n_workers> <seconds> [s16]      (test infrastructure: needs oracle/_ref)
+s16: quantise every stream to 16 bits first (a WAV capture): the sums are exact there, no stream may differ
 """
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,6 +24,8 @@ while time.time()-t0 < budget:
     ns = int(rng.integers(1_500_000, 4_000_000))
     iq = synth.synth_batch(wl, 1, ns, seed=seed, device="cpu", amplitude=(amp, amp*1.2), sigma=(sig, sig*1.5))[0].numpy()
     mag = np.sqrt(iq[:,0].astype(np.float32)**2 + iq[:,1].astype(np.float32)**2).astype(np.float32)
+    if len(sys.argv) > 4 and sys.argv[4] == "s16":
+        mag = np.round(np.clip(mag, 0, 0.9999) * 32768.0).astype(np.int16).astype(np.float32) / np.float32(32768.0)
     trig = S.block_flags(mag, S.ScreenParams(10_000_000))
     r = U.ref_decode(mag, 10_000_000)
     a, sa = U.sim_pipeline(mag, trig, 10_000_000)
