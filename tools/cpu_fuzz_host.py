@@ -5,6 +5,7 @@ the speculative thread lanes and by the thread lanes with every overrunning lane
 
 usage: python tools/cpu_fuzz_host.py <worker> <n_workers> <seconds> [s16]      (test infrastructure: needs oracle/_ref)
 s16: quantise every stream to 16 bits first (a WAV capture): the sums are exact there, no stream may differ
+exact: the one-lane warp pipeline (exact float sums), with and without a feature pool, instead of the thread lanes
 """
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -28,8 +29,12 @@ while time.time()-t0 < budget:
         mag = np.round(np.clip(mag, 0, 0.9999) * 32768.0).astype(np.int16).astype(np.float32) / np.float32(32768.0)
     trig = S.block_flags(mag, S.ScreenParams(10_000_000))
     r = U.ref_decode(mag, 10_000_000)
-    a, sa = U.sim_pipeline(mag, trig, 10_000_000)
-    b, sb = U.sim_pipeline(mag, trig, 10_000_000, bail=0)
+    if len(sys.argv) > 4 and sys.argv[4] == "exact":
+        a, sa = U.sim_pipeline2(mag, trig, 10_000_000, group=0, exact_int=False)
+        b, sb = U.sim_pipeline2(mag, trig, 10_000_000, group=0, exact_int=False, nofeat=True)
+    else:
+        a, sa = U.sim_pipeline(mag, trig, 10_000_000)
+        b, sb = U.sim_pipeline(mag, trig, 10_000_000, bail=0)
     n+=1
     if a != r or b != r:
         bad+=1
