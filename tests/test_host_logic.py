@@ -161,3 +161,18 @@ def test_carry_chain_does_not_crawl_behind_a_zero_frame_size():
     assert frames == ref
     assert ref[-1][7][:7] == bytes([0x1D, 0x11, 0x22, 0x33, 0x44, 0x00, 0x0D]), "nothing decodes behind the RFU ATTRIB: the state is inert"
     assert st["rounds"] <= 3, st
+
+
+@pytest.mark.parametrize("name", ["test_NFC-A_106kbps_001", "test_NFC-A_424kbps_002", "test_NFC-B_106kbps_002", "test_NFC-F_212kbps_003",
+                                  "test_NFC-V_26kbps_001", "test_POLL_ABF_001"])
+def test_padding_a_capture_with_its_last_sample_adds_no_frame(name):
+    """bench.py's wav_set decodes the 19 captures as one batch call, every capture padded to the longest with its own last
+    sample (an idle carrier that goes on): the poll / listen frames stay the golden ones"""
+    mag, rate, _ = U.fixture_wav(name)
+    x = np.round(mag * 32768.0).astype(np.int16)
+    padded = np.empty(2367232, np.int16)
+    padded[:x.size] = x
+    padded[x.size:] = x[-1]
+    pm = padded.astype(np.float32) / np.float32(32768.0)
+    frames, _ = U.sim_pipeline(pm, S.block_flags_device_model(pm, S.ScreenParams(rate)), rate)
+    assert [k for k in frames if k[1] in (0x102, 0x103)] == U.fixture_golden(name)
